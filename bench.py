@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py - fitness evals/sec (SP+CS) of the GA-DPAMSA generation loop on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|c2]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one whole-population fitness pass (pad + clean + SP + EM/CS for every board, the
+reference's GA.calculate_fitness_score loop, GA.py:156-178) over one synthetic population of
+the named BASELINE.json workload; an "eval" is one board fully scored. Every step consumes a
+FRESH replica of the population (the pass cleans boards in place, so re-scoring the same buffer
+would skip the write-back work); with the replicas the per-step input is also never L2-resident.
+
+One JSON line on rank 0 (see the contract in the task statement): value = device-resident
+throughput, e2e = the same pass through gad_fitness_host with pinned HOST buffers (H2D of the
+boards, D2H of the scores inside the timed region), roofline = algorithmic bytes / measured
+kernel time against the measured HBM copy peak, cpu_baseline = the oracle on the host cores.
+--impl reference times the CPU port of the reference's path on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "ga-dpamsa_b200"))
+os.environ.setdefault("GADPAMSA_PROJECT_ROOT", os.path.join(ROOT, "gpurun_out", "project_root"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (rows, cols, population, mode, description)
+    "c2": (6, 60, 1024, "mo", "6x60 boards, population 1,024, intersection (SP+CS) mode [BASELINE configs[1]]"),
+    "c3": (6, 60, 65536, "mo", "synthetic 6x60 boards, population 65,536 [BASELINE configs[2], the north-star target]"),
+    "c4": (20, 200, 262144, "cs", "synthetic 20x200 boards, population 262,144 [BASELINE configs[3]]"),
+}
+MATCH, MISMATCH, GAPW = 4, -4, -4
+CLONE_RATE, GAP_RATE = 0.25, 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic input: base sequences in the style of datasets/generate_dataset.py,
+# population by the recipe of GA.generate_population (GA.py:71-94) with a vectorised generator
+# ------------------------------------------------------------------------------------------------
+def synth_sequences(rows, cols, seed):
+    rng = np.random.default_rng(seed)
+    seqs = rng.integers(1, 5, size=(rows, cols), dtype=np.uint8)
+    blk = max(1, int(0.3 * cols))
+    off = int(rng.integers(0, cols - blk + 1))
+    seqs[:, off:off + blk] = rng.integers(1, 5, size=blk, dtype=np.uint8)[None, :]
+    mut = rng.random((rows, cols)) < 0.10
+    mut[:, off:off + blk] = False
+    seqs[mut] = rng.integers(1, 5, size=int(mut.sum()), dtype=np.uint8)
+    gapm = rng.random((rows, cols)) < 0.05
+    gapm[:, off:off + blk] = False
+    seqs[gapm] = 5
+    return seqs
+
+
+def synth_population(rows, cols, P, seed):
+    """uint8 boards [P, rows, stride] + int32 rowlen [P, rows]: round(P*CLONE_RATE) clones, the rest
+    with max(1, round(cols*GAP_RATE)) gaps inserted per row at uniform positions."""
+    seqs = synth_sequences(rows, cols, seed)
+    rng = np.random.default_rng(seed + 1)
+    n_gap = max(1, round(cols * GAP_RATE))
+    n_clone = round(P * CLONE_RATE)
+    width = cols + n_gap
+    stride = -(-width // 16) * 16
+    boards = np.full((P, rows, stride), 5, dtype=np.uint8)
+    rowlen = np.empty((P, rows), dtype=np.int32)
+    boards[:n_clone, :, :cols] = seqs[None]
+    rowlen[:n_clone] = cols
+    m = P - n_clone
+    # gap positions: choose n_gap of the `width` output slots per row (same support as repeated insert)
+    keys = rng.random((m, rows, width))
+    gap_slots = np.argsort(keys, axis=2)[:, :, :n_gap]
+    is_gap = np.zeros((m, rows, width), dtype=bool)
+    np.put_along_axis(is_gap, gap_slots, True, axis=2)
+    is_gap[:, :, width - 1] = False            # randint(0, len-1) never appends at the very end
+    src = np.cumsum(~is_gap, axis=2) - 1
+    src = np.clip(src, 0, cols - 1)
+    vals = np.take_along_axis(np.broadcast_to(seqs[None], (m, rows, cols)), src, axis=2)
+    vals[is_gap] = 5
+    n_real = (~is_gap).sum(axis=2)
+    lens = np.minimum(width, cols + is_gap.sum(axis=2)).astype(np.int32)
+    col_idx = np.arange(width)[None, None, :]
+    vals[col_idx >= lens[:, :, None]] = 5
+    boards[n_clone:, :, :width] = vals
+    rowlen[n_clone:] = lens
+    del n_real
+    return boards, rowlen
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(workload):
+    """dram bytes per launch from the committed ncu capture, if one exists for this workload."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get(workload)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baselines (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def _py_worker(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ga_oracle as O
+    boards, rowlen, mode = args
+    pop = O.to_lists(boards, rowlen)
+    t0 = time.perf_counter()
+    O.fitness_scores_literal(pop, mode, O.Weights(MATCH, MISMATCH, GAPW))
+    return time.perf_counter() - t0
+
+
+def cpu_python_port(boards, rowlen, mode, n_sample, procs, pool=None):
+    """The reference's own loop structure (pure python lists, GA.py:156-178 / utils.py:62-76,122-125,
+    404-428) on `procs` processes over a sample of the population. Returns (evals/s, n, seconds);
+    the clock runs from handing the work to the pool until the last chunk is back."""
+    n_sample = min(n_sample, boards.shape[0])
+    idx = np.linspace(0, boards.shape[0] - 1, n_sample).astype(np.int64)
+    chunks = np.array_split(idx, procs)
+    jobs = [(boards[c].copy(), rowlen[c].copy(), mode) for c in chunks if len(c)]
+    t0 = time.perf_counter()
+    if pool is None:
+        [_py_worker(j) for j in jobs]
+    else:
+        pool.map(_py_worker, jobs)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, n_sample, dt
+
+
+def python_pool(procs):
+    import multiprocessing as mp
+    return mp.get_context("fork").Pool(procs) if procs > 1 else None
+
+
+def python_sample_size(rows, cols, P, cores):
+    cells = rows * cols
+    per_core = max(4, int(400000 / cells))          # ~0.3-0.6 s of pure-python scoring per core
+    return min(P, per_core * cores)
+
+
+def cpu_c_port(boards, rowlen, threads, min_seconds=2.0):
+    """oracle/ga_oracle.c (scalar C restatement + OpenMP over boards). Returns evals/s."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ga_oracle as O
+    P = boards.shape[0]
+    done, elapsed = 0, 0.0
+    while elapsed < min_seconds:
+        b, r = boards.copy(), rowlen.copy()
+        t0 = time.perf_counter()
+        O.fitness_population_c(b, r, O.Weights(MATCH, MISMATCH, GAPW), nthreads=threads)
+        elapsed += time.perf_counter() - t0
+        done += P
+    return done / elapsed, done, elapsed
+
+
+# ------------------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def run_reference(args, rank, world):
+    """The CPU port of the reference's path, all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    rows, cols, P, mode, desc = WORKLOADS[args.workload]
+    boards, rowlen = synth_population(rows, cols, P, 20251019)
+    cores = os.cpu_count() or 1
+    n_sample = python_sample_size(rows, cols, P, cores)
+    pool = python_pool(cores)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        _, n, dt = cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
+        t_total += dt
+        n_total += n
+    if pool is not None:
+        pool.close()
+    value = n_total / t_total
+    c_rate, c_n, c_dt = cpu_c_port(boards, rowlen, cores)
+    line = {
+        "impl": "reference", "metric": "fitness evals/sec (SP+CS)", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, desc), "rows": rows, "cols": cols, "population": P,
+                   "mode": mode, "sample_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "language": "pure python lists, the reference's own loop structure",
+                         "sample": "%d boards per step spread over the population, %d processes" % (n_sample, cores)},
+        "cpu_baseline_c_openmp": {"value": c_rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                  "sample": "%d evals in %.2f s, oracle/ga_oracle.c" % (c_n, c_dt)},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import _native as nat
+    from population import DevicePopulation
+
+    nat.require_device()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    rows, cols, P, mode, desc = WORKLOADS[args.workload]
+    boards_h, rowlen_h = synth_population(rows, cols, P, 20251019 + 1000 * rank)
+    stride = boards_h.shape[2]
+    K, W = args.steps, args.warmup
+    board_bytes = boards_h.nbytes
+    n_rep = K + W
+    max_rep = max(2, int(24e9 // board_bytes))
+    fresh = n_rep <= max_rep
+    n_rep = min(n_rep, max_rep)
+    pristine_b = torch.from_numpy(boards_h).to(dev)
+    pristine_r = torch.from_numpy(rowlen_h).to(dev)
+    replicas = []
+    for _ in range(n_rep):
+        replicas.append(DevicePopulation(pristine_b.clone(), pristine_r.clone()))
+    algo_bytes = int(rowlen_h.astype(np.int64).max(axis=1).sum()) * rows + 12 * P      # R*W + 12 per eval
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(W):
+        replicas[i % n_rep].fitness(MATCH, MISMATCH, GAPW)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record()
+    for i in range(K):
+        replicas[(W + i) % n_rep].fitness(MATCH, MISMATCH, GAPW)
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[K])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * P * K / (total_ms_max * 1e-3)
+
+    # ---------------- kernel-only time for the roofline (events around each launch) -------------
+    kern_ms = []
+    for i in range(K):
+        rep = replicas[(W + i) % n_rep]
+        rep.boards.copy_(pristine_b)
+        rep.rowlen.copy_(pristine_r)
+        rep.max_al.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        nat.call("gad_fitness", nat.ptr(rep.boards), nat.ptr(rep.rowlen), P, rows, stride, MATCH, MISMATCH, GAPW,
+                 nat.ptr(rep.sp), nat.ptr(rep.em), nat.ptr(rep.al), nat.ptr(rep.max_al), nat.current_stream_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        kern_ms.append(e0.elapsed_time(e1))
+    kern_avg_ms = sum(kern_ms) / len(kern_ms)
+    peak, peak_src = measured_peak()
+    achieved = algo_bytes / (kern_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "fitness_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_avg_ms, "kernel_ms_min": min(kern_ms),
+                "peak_source": peak_src,
+                "note": "kernel timed alone between syncs (burst HBM peak); launch latency included"}
+
+    # ---------------- end to end through the C-ABI host entry point (`e2e`) ---------------------
+    pin_b = torch.from_numpy(boards_h).pin_memory()
+    pin_r = torch.from_numpy(rowlen_h).pin_memory()
+    work_b = torch.empty_like(pin_b).pin_memory()
+    work_r = torch.empty_like(pin_r).pin_memory()
+    out = torch.zeros(3, P, dtype=torch.int32).pin_memory()
+    def e2e_step():
+        nat.call("gad_fitness_host", work_b.data_ptr(), work_r.data_ptr(), P, rows, stride, MATCH, MISMATCH, GAPW,
+                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), 0)
+    work_b.copy_(pin_b)
+    work_r.copy_(pin_r)
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * K / float(t.item())
+    sp_ref = replicas[(W + K - 1) % n_rep].sp.cpu()
+    assert torch.equal(out[0], sp_ref), "e2e scores differ from the device-resident pass"
+    e2e = {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": boards_h.nbytes + rowlen_h.nbytes,
+           "d2h_bytes_per_step": 12 * P, "ms_per_step": 1e3 * float(t.item()) / K,
+           "api": "gad_fitness_host (C-ABI, pinned host buffers)"}
+
+    line = {
+        "metric": "fitness evals/sec (SP+CS)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.workload, desc), "rows": rows, "cols": cols,
+                   "population_per_gpu": P, "mode": mode, "stride": stride,
+                   "scores": [MATCH, MISMATCH, GAPW],
+                   "l2": ("every step scores a fresh replica of the population (%d replicas x %.1f MB = %.0f MB > "
+                          "126 MB L2)%s" % (n_rep, board_bytes / 1e6, n_rep * board_bytes / 1e6,
+                                            "" if fresh else "; replicas reused round-robin")),
+                   "parallelism": "population sharded by index, %d rank(s), no data-path collective" % world},
+        "e2e": e2e, "roofline": roofline, "clocks": clocks, "gpu_launches": K,
+        "launch_ms": {"median": statistics.median(per_launch_ms), "max": max(per_launch_ms)},
+    }
+
+    # ---------------- CPU baselines on rank 0 at N=1 ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = python_sample_size(rows, cols, P, cores) * 4
+        pool = python_pool(cores)
+        cpu_python_port(boards_h, rowlen_h, mode, 64 * cores, cores, pool)            # warm the workers
+        py_rate, py_n, py_dt = cpu_python_port(boards_h, rowlen_h, mode, n_sample, cores, pool)
+        if pool is not None:
+            pool.close()
+        c_rate, c_n, c_dt = cpu_c_port(boards_h, rowlen_h, cores)
+        line["cpu_baseline"] = {"value": py_rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                "language": "pure python lists, the reference's own loop structure",
+                                "sample": "%d boards in %.2f s on %d processes" % (py_n, py_dt, cores)}
+        line["cpu_baseline_c_openmp"] = {"value": c_rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                         "sample": "%d evals in %.2f s, oracle/ga_oracle.c" % (c_n, c_dt)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

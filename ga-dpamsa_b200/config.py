@@ -1,0 +1,110 @@
+"""Knobs of the GA-DPAMSA generation loop - same names and meaning as the reference's
+``config.py`` (scores ``config.py:21-23``, device ``:33-34``, GA ``:39-46``, paths ``:61-109``,
+external tools ``:115-152``). Every facade function reads these through the module at call
+time, exactly like the reference, so ``config.POPULATION_SIZE = 1024`` takes effect immediately.
+
+``PROJECT_ROOT`` defaults to this directory; set ``GADPAMSA_PROJECT_ROOT`` to point the
+weights / results tree somewhere else (e.g. at a reference checkout with real weights).
+"""
+import math
+import os
+
+import torch
+
+# --- DPAMSA scores and DQN hyper-parameters (reference config.py:21-34) -----------------------
+GAP_PENALTY = -4
+MISMATCH_PENALTY = -4
+MATCH_REWARD = 4
+MAX_EPISODE = 6000
+BATCH_SIZE = 128
+REPLAY_MEMORY_SIZE = 1000
+ALPHA = 0.0001
+EPSILON = 0.8
+GAMMA = 1
+DELTA = 0.05
+DECREMENT_ITERATION = math.ceil(MAX_EPISODE * 0.8 / (EPSILON // DELTA))
+UPDATE_ITERATION = 128
+DEVICE_NAME = "cuda:0" if torch.cuda.is_available() else "cpu"
+# The reference pins 'cpu' here (config.py:34). This build computes on the GPU only; DEVICE names
+# the CUDA device the generation loop runs on. LOCAL_RANK selects it under torchrun.
+DEVICE = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+
+# --- GA parameters (reference config.py:39-46) -------------------------------------------------
+AGENT_WINDOW_ROW = 3
+AGENT_WINDOW_COLUMN = 30
+GA_ITERATIONS = 3
+POPULATION_SIZE = 5
+CLONE_RATE = 0.25
+GAP_RATE = 0.05
+SELECTION_RATE = 0.5
+MUTATION_RATE = 0.25
+
+# --- B200 build only: crossover kind. The reference code has horizontal crossover only
+# (GA.py:262-301); 'vertical' is the variant of its supplement table A5 / img/vertical-crossover.png.
+CROSSOVER_KIND = "horizontal"
+
+for _ok, _msg in (
+    (0 < BATCH_SIZE <= REPLAY_MEMORY_SIZE, "batch size must be in (0, replay memory size]"),
+    (ALPHA > 0, "alpha must be positive"),
+    (0 <= GAMMA <= 1, "gamma must be in [0, 1]"),
+    (0 <= EPSILON <= 1, "epsilon must be in [0, 1]"),
+    (0 <= DELTA <= EPSILON, "delta must be in [0, epsilon]"),
+    (0 < DECREMENT_ITERATION, "decrement iteration must be positive"),
+):
+    assert _ok, _msg
+
+# --- paths (reference config.py:61-109) ----------------------------------------------------------
+PROJECT_ROOT = os.environ.get("GADPAMSA_PROJECT_ROOT", os.path.dirname(os.path.abspath(__file__)))
+
+
+def _p(*parts):
+    return os.path.join(PROJECT_ROOT, *parts)
+
+
+BASE_DATASETS_PATH = _p("datasets")
+FASTA_FILES_PATH = _p("datasets", "fasta_files")
+TRAINING_DATASET_PATH = _p("datasets", "training_dataset")
+INFERENCE_DATASET_PATH = _p("datasets", "inference_dataset")
+DPAMSA_WEIGHTS_PATH = _p("DPAMSA", "weights")
+RUNS_PATH = _p("DPAMSA", "runs")
+BASE_RESULTS_PATH = _p("results")
+REPORTS_PATH = _p("results", "reports")
+DPAMSA_REPORTS_PATH = _p("results", "reports", "DPAMSA")
+GA_DPAMSA_REPORTS_PATH = _p("results", "reports", "GA-DPAMSA")
+DATASETS_REPORTS_PATH = _p("results", "reports", "datasets")
+BENCHMARKS_PATH = _p("results", "benchmarks")
+TOOLS_OUTPUT_PATH = _p("results", "tools_output")
+CSV_PATH = _p("results", "benchmarks", "csv")
+DATASETS_CSV_PATH = _p("results", "benchmarks", "csv", "datasets")
+INFERENCE_CSV_PATH = _p("results", "benchmarks", "csv", "inference")
+DPAMSA_INF_CSV_PATH = _p("results", "benchmarks", "csv", "inference", "DPAMSA")
+GA_DPAMSA_INF_CSV_PATH = _p("results", "benchmarks", "csv", "inference", "GA-DPAMSA")
+CHARTS_PATH = _p("results", "benchmarks", "charts")
+
+REQUIRED_DIRECTORIES = [
+    DPAMSA_WEIGHTS_PATH, RUNS_PATH, BASE_RESULTS_PATH, DPAMSA_REPORTS_PATH, GA_DPAMSA_REPORTS_PATH,
+    DATASETS_REPORTS_PATH, BENCHMARKS_PATH, TOOLS_OUTPUT_PATH, CSV_PATH, DATASETS_CSV_PATH,
+    INFERENCE_CSV_PATH, DPAMSA_INF_CSV_PATH, GA_DPAMSA_INF_CSV_PATH, CHARTS_PATH,
+]
+if os.environ.get("GADPAMSA_NO_MKDIR") != "1":
+    for _d in REQUIRED_DIRECTORIES:       # the reference creates these at import (config.py:107-109)
+        os.makedirs(_d, exist_ok=True)
+
+
+# --- external MSA tools (reference config.py:115-152; out of scope, kept so callers import) ---
+def _tool(name, command):
+    return {"command": command,
+            "output_dir": os.path.join(TOOLS_OUTPUT_PATH, name),
+            "report_dir": os.path.join(REPORTS_PATH, name)}
+
+
+TOOLS = {
+    "ClustalOmega": _tool("ClustalOmega", lambda src, dst: ["clustalo", "-i", src, "-o", dst]),
+    "MSAProbs": _tool("MSAProbs", lambda src, dst: ["msaprobs", src, "-o", dst]),
+    "ClustalW": _tool("ClustalW", lambda src, dst: ["clustalw", "-INFILE=%s" % src, "-OUTPUT=FASTA",
+                                                    "-OUTFILE=%s" % dst]),
+    "MAFFT": _tool("MAFFT", lambda src, dst: "mafft --auto %s > %s" % (src, dst)),
+    "MUSCLE5": _tool("MUSCLE5", lambda src, dst: ["muscle5", "-align", src, "-output", dst]),
+    "UPP": _tool("UPP", lambda src, dst: ["run_upp.py", "-s", src, "-m", "dna", "-d", dst]),
+    "PASTA": _tool("PASTA", lambda src, dst: ["run_pasta.py", "-i", src, "-o", dst]),
+}

@@ -1,0 +1,131 @@
+// Shared helpers for libgadpamsa (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/gadpamsa.h"
+
+#define GAD_GAP 5
+#define GAD_NUM_SMS 148
+
+void gad_set_error(const char *fmt, ...);
+
+#define GAD_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            gad_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return GAD_ECUDA;                                                            \
+        }                                                                                \
+    } while (0)
+
+#define GAD_REQUIRE(cond, ...)                                                           \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            gad_set_error(__VA_ARGS__);                                                  \
+            return GAD_EINVAL;                                                           \
+        }                                                                                \
+    } while (0)
+
+#define GAD_LAUNCH_CHECK()                                                               \
+    do {                                                                                 \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess) {                                                         \
+            gad_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GAD_ECUDA;                                                            \
+        }                                                                                \
+    } while (0)
+
+static inline cudaStream_t gad_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------
+// Packed-byte column arithmetic. One 32-bit word = 4 adjacent columns of one row; cell
+// codes are 1..5 (3 bits), so the per-symbol indicator of every byte is one LOP3 over the
+// three bit planes of the word, and per-column symbol counts over <=255 rows accumulate
+// as four independent byte lanes with plain integer adds.
+// ---------------------------------------------------------------------------------------
+#define GAD_LSB4 0x01010101u
+#define GAD_MSB4 0x80808080u
+
+struct ColCounts {
+    uint32_t c1, c2, c3, c4;   // per byte lane: rows holding A / T / C / G in that column
+    uint32_t diff;             // per byte lane: OR over rows of (cell XOR first row's cell)
+};
+
+__device__ __forceinline__ void colcounts_clear(ColCounts &c) { c.c1 = c.c2 = c.c3 = c.c4 = 0u; c.diff = 0u; }
+
+__device__ __forceinline__ void colcounts_add(ColCounts &c, uint32_t x, uint32_t x_first)
+{
+    const uint32_t b0 = x & GAD_LSB4;
+    const uint32_t b1 = (x >> 1) & GAD_LSB4;
+    const uint32_t b2 = (x >> 2) & GAD_LSB4;
+    c.c1 += b0 & ~b1 & ~b2;    // 001
+    c.c2 += b1 & ~b0;          // 010 (b2 is 0 whenever b1 is set for codes 1..5)
+    c.c3 += b0 & b1;           // 011
+    c.c4 += b2 & ~b0;          // 100
+    c.diff |= x ^ x_first;
+}
+
+// bit 7 of every byte lane that is non-zero (exact per lane, lanes may hold up to 255)
+__device__ __forceinline__ uint32_t nonzero_lanes(uint32_t v)
+{
+    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & GAD_MSB4;
+}
+
+// Per-board accumulators over the kept (not all-gap) columns.
+struct BoardSums {
+    uint32_t q2;     // sum over columns of c1^2+c2^2+c3^2+c4^2
+    uint32_t s1;     // sum over columns of non-gap cells
+    uint32_t s2;     // sum over columns of (non-gap cells)^2
+    uint32_t kept;   // columns that are not all-gap
+    uint32_t exact;  // kept columns whose cells are all equal
+};
+
+__device__ __forceinline__ void boardsums_clear(BoardSums &b) { b.q2 = b.s1 = b.s2 = b.kept = b.exact = 0u; }
+
+// Fold one word (4 columns) of finished column counts into the board sums; returns the
+// keep mask (bit 7 of each lane whose column has at least one non-gap cell).
+// `lane_valid` has bit 7 set for the lanes that are real columns of the window.
+__device__ __forceinline__ uint32_t boardsums_fold(BoardSums &b, const ColCounts &c, uint32_t lane_valid,
+                                                   bool count_allgap_columns)
+{
+    const uint32_t s = c.c1 + c.c2 + c.c3 + c.c4;          // non-gap cells per column
+    uint32_t keep = nonzero_lanes(s) & lane_valid;
+    const uint32_t uniform = ~nonzero_lanes(c.diff) & GAD_MSB4 & lane_valid;
+    if (count_allgap_columns) {
+        // windowed utils.get_column_score counts an all-gap column as exact and
+        // utils.get_sum_of_pairs scores its pairs as gaps: keep every valid lane.
+        keep = lane_valid;
+    }
+    // lanes outside `keep` must not contribute: all-gap lanes have zero counts already;
+    // invalid lanes are masked here (0xFF per kept lane).
+    const uint32_t m = (keep >> 7) * 0xFFu;
+    const uint32_t a1 = c.c1 & m, a2 = c.c2 & m, a3 = c.c3 & m, a4 = c.c4 & m, as = s & m;
+    b.q2 = __dp4a(a1, a1, b.q2);
+    b.q2 = __dp4a(a2, a2, b.q2);
+    b.q2 = __dp4a(a3, a3, b.q2);
+    b.q2 = __dp4a(a4, a4, b.q2);
+    b.s1 = __dp4a(as, GAD_LSB4, b.s1);
+    b.s2 = __dp4a(as, as, b.s2);
+    b.kept += __popc(keep);
+    b.exact += __popc(uniform & keep);
+    return keep;
+}
+
+// Closed form of utils.py:62-76 from the board sums over `kept` columns of `rows` cells:
+//   match pairs    M  = sum c(c-1)/2                      = (q2 - s1)/2
+//   gap pairs      Gp = sum g(g-1)/2 + g(rows-g), g=rows-s = ((2 rows-1) G1 - G2)/2
+//   mismatch pairs    = kept*rows(rows-1)/2 - M - Gp
+__device__ __forceinline__ long long sum_of_pairs_closed_form(const BoardSums &b, int rows, int match, int mismatch,
+                                                              int gap)
+{
+    const long long R = rows, nk = b.kept, s1 = b.s1, s2 = b.s2, q2 = b.q2;
+    const long long M = (q2 - s1) / 2;
+    const long long G1 = R * nk - s1;
+    const long long G2 = R * R * nk - 2 * R * s1 + s2;
+    const long long Gp = ((2 * R - 1) * G1 - G2) / 2;
+    const long long T = nk * R * (R - 1) / 2;
+    return (long long)match * M + (long long)gap * Gp + (long long)mismatch * (T - M - Gp);
+}

@@ -1,0 +1,193 @@
+"""CUDA fitness pass (gad_fitness / gad_fitness_host / gad_window_score_host through the C-ABI)
+against the oracle and the reference's published golden vectors. Bit-exact integer parity."""
+import copy
+import random
+
+import numpy as np
+import pytest
+
+import ga_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(native_lib):
+    native_lib.require_device()
+    import torch
+    torch.cuda.set_device(0)
+    return torch
+
+
+def run_device(pop, weights=(4, -4, -4), stride=None):
+    from population import DevicePopulation
+    import torch
+    dev = DevicePopulation.from_lists(pop, stride=stride)
+    sp, em, al = dev.fitness(*weights)
+    torch.cuda.synchronize()
+    return sp.cpu().numpy(), em.cpu().numpy(), al.cpu().numpy(), dev
+
+
+def run_oracle(pop, weights=(4, -4, -4), stride=None):
+    boards, rowlen = O.to_arrays(pop, stride=stride)
+    sp, em, al = O.fitness_population_c(boards, rowlen, O.Weights(*weights))
+    return sp, em, al, O.to_lists(boards, rowlen)
+
+
+def assert_parity(pop, weights=(4, -4, -4), stride=None):
+    sp, em, al, dev = run_device(copy.deepcopy(pop), weights, stride)
+    osp, oem, oal, oboards = run_oracle(copy.deepcopy(pop), weights, dev.stride)
+    assert np.array_equal(sp, osp)
+    assert np.array_equal(em, oem)
+    assert np.array_equal(al, oal)
+    assert dev.to_lists() == oboards
+    assert int(dev.max_al.item()) == (int(oal.max()) if len(oal) else 0)
+    return sp, em, al
+
+
+def test_golden_report_vectors(gpu, report_vectors):
+    """All 1340 published alignments: device SP / EM / AL equal the recorded values."""
+    by_rows = {}
+    for rec in report_vectors:
+        by_rows.setdefault(len(rec["rows"]), []).append(rec)
+    checked = 0
+    for R, recs in by_rows.items():
+        pop = [O.encode([s.upper() for s in rec["rows"]]) for rec in recs]
+        sp, em, al = assert_parity(pop)
+        for i, rec in enumerate(recs):
+            board = pop[i]
+            if any(all(row[c] == 5 for row in board) for c in range(len(board[0]))):
+                continue
+            assert (sp[i], em[i], al[i]) == (rec["sp"], rec["em"], rec["al"])
+            checked += 1
+    assert checked > 1300
+
+
+@pytest.mark.parametrize("R,Wmax,stride", [(2, 9, None), (3, 31, None), (6, 63, 64), (6, 63, 128), (4, 101, None),
+                                           (12, 150, None), (20, 210, None), (5, 300, 512), (64, 130, None)])
+def test_random_ragged_boards(gpu, R, Wmax, stride):
+    rng = random.Random(R * 1000 + Wmax)
+    pop = []
+    for _ in range(257):
+        W = rng.randint(1, Wmax)
+        b = [[rng.choice([1, 2, 3, 4, 5, 5]) for _ in range(rng.randint(max(0, W - 7), W))] for _ in range(R)]
+        if rng.random() < 0.5:
+            for c in rng.sample(range(W), min(W, rng.randint(1, 6))):
+                for row in b:
+                    if c < len(row):
+                        row[c] = 5
+        pop.append(b)
+    assert_parity(pop, stride=stride)
+    assert_parity(pop, weights=(5, -3, -7), stride=stride)      # the three pair classes are separated
+
+
+def test_edge_cases(gpu):
+    pop = [
+        [[], [], []],                                       # empty board
+        [[5, 5, 5], [5, 5], [5]],                           # only gaps -> cleans to width 0
+        [[1], [1], [1]],                                    # single exact column
+        [[1, 2, 3, 4], [], [5, 5, 5, 5, 5, 5, 1]],          # very ragged
+        [[5, 1, 5, 5, 2, 5], [5, 1, 5, 5, 3, 5], [5, 5, 5, 5, 4, 5]],
+        [[1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2, 3, 4]] * 3,
+    ]
+    sp, em, al = assert_parity(pop)
+    assert al.tolist() == [0, 0, 1, 7, 2, 16]
+    assert em.tolist()[2] == 1 and em.tolist()[5] == 16
+    assert sp.tolist()[5] == 16 * 3 * 4
+
+
+def test_single_row_and_wide_rows(gpu):
+    rng = random.Random(5)
+    pop = [[[rng.choice([1, 2, 3, 4, 5]) for _ in range(rng.randint(1, 1100))]] for _ in range(40)]
+    assert_parity(pop)
+    pop = [[[rng.choice([1, 2, 3, 4, 5]) for _ in range(1050)] for _ in range(64)] for _ in range(6)]
+    assert_parity(pop)
+
+
+def test_clean_boards_are_left_untouched(gpu):
+    """A second pass over already-clean boards is idempotent (GA.selection re-evaluates survivors)."""
+    import torch
+    rng = random.Random(9)
+    pop = [[[rng.choice([1, 2, 3, 4]) for _ in range(60)] for _ in range(6)] for _ in range(100)]
+    sp, em, al, dev = run_device(pop)
+    before = dev.boards.clone()
+    sp2, em2, al2 = dev.fitness(4, -4, -4)
+    torch.cuda.synchronize()
+    assert torch.equal(before, dev.boards)
+    assert np.array_equal(sp, sp2.cpu().numpy()) and np.array_equal(al, al2.cpu().numpy())
+
+
+def test_host_buffer_entry_point(gpu, native_lib):
+    from population import pack_boards, unpack_boards
+    rng = random.Random(21)
+    pop = [[[rng.choice([1, 2, 3, 4, 5, 5]) for _ in range(rng.randint(20, 33))] for _ in range(4)] for _ in range(500)]
+    boards, rowlen = pack_boards(copy.deepcopy(pop))
+    P, R, stride = boards.shape
+    sp = np.zeros(P, np.int32)
+    em = np.zeros(P, np.int32)
+    al = np.zeros(P, np.int32)
+    native_lib.call("gad_fitness_host", boards.ctypes.data, rowlen.ctypes.data, P, R, stride, 4, -4, -4,
+                    sp.ctypes.data, em.ctypes.data, al.ctypes.data, 1)
+    osp, oem, oal, oboards = run_oracle(pop, stride=stride)
+    assert np.array_equal(sp, osp) and np.array_equal(em, oem) and np.array_equal(al, oal)
+    assert unpack_boards(boards, rowlen) == oboards
+
+
+def test_facade_free_functions(gpu):
+    """utils.get_sum_of_pairs / get_column_score / clean_unnecessary_gaps keep the reference's
+    signatures and return types (utils.py:27-128, 390-428)."""
+    import utils
+    import config
+    rng = random.Random(4)
+    for _ in range(40):
+        R, W = rng.randint(2, 8), rng.randint(1, 70)
+        b = [[rng.choice([1, 2, 3, 4, 5, 5]) for _ in range(W)] for _ in range(R)]
+        fr = rng.randint(0, R - 1)
+        tr = rng.randint(fr + 1, R)
+        fc = rng.randint(0, W - 1)
+        tc = rng.randint(fc, W)
+        sp = utils.get_sum_of_pairs(b, fr, tr, fc, tc)
+        cs = utils.get_column_score(b, fr, tr, fc, tc)
+        assert isinstance(sp, int) and sp == O.sum_of_pairs(b, fr, tr, fc, tc)
+        assert cs == O.column_score(b, fr, tr, fc, tc)
+        b1, b2 = copy.deepcopy(b), copy.deepcopy(b)
+        utils.clean_unnecessary_gaps(b1)
+        O.clean_unnecessary_gaps(b2)
+        assert b1 == b2
+    old = (config.MATCH_REWARD, config.MISMATCH_PENALTY, config.GAP_PENALTY)
+    try:
+        config.MATCH_REWARD, config.MISMATCH_PENALTY, config.GAP_PENALTY = 5, -3, -7   # read live
+        b = [[1, 2, 5, 4], [1, 3, 5, 4], [2, 3, 1, 5]]
+        assert utils.get_sum_of_pairs(b, 0, 3, 0, 4) == O.sum_of_pairs(b, 0, 3, 0, 4, O.Weights(5, -3, -7))
+    finally:
+        config.MATCH_REWARD, config.MISMATCH_PENALTY, config.GAP_PENALTY = old
+    assert utils.get_nucleotides_seqs([[1, 2, 3, 5], [4, 3, 2, 1]]) == ["ATC-", "GCAT"]
+    assert utils.get_column_score([[1, 2, 3, 3]] * 3, 0, 3, 0, 4) == 1.0
+
+
+def test_full_size_population_properties(gpu):
+    """BASELINE config c3 size (P=65,536, 6x60): size-independent properties instead of the oracle -
+    (1) row permutation invariance, (2) idempotence of the cleaned boards, (3) a sampled oracle check."""
+    import torch
+    from population import DevicePopulation
+    rng = np.random.default_rng(3)
+    P, R, W = 65536, 6, 63
+    boards = rng.integers(1, 6, size=(P, R, 64), dtype=np.uint8)
+    boards[:, :, W:] = 5
+    boards[rng.random((P, 1, 64)).repeat(R, 1) < 0.03] = 5          # some all-gap columns
+    rowlen = np.full((P, R), W, np.int32)
+    dev = DevicePopulation.from_numpy(boards.copy(), rowlen.copy())
+    sp, em, al = [t.clone() for t in dev.fitness(4, -4, -4)]
+    perm = DevicePopulation.from_numpy(np.ascontiguousarray(boards[:, ::-1, :]), rowlen.copy())
+    sp_p, em_p, al_p = perm.fitness(4, -4, -4)
+    torch.cuda.synchronize()
+    assert torch.equal(sp, sp_p) and torch.equal(em, em_p) and torch.equal(al, al_p)
+    sp2, em2, al2 = dev.fitness(4, -4, -4)
+    torch.cuda.synchronize()
+    assert torch.equal(sp, sp2) and torch.equal(em, em2) and torch.equal(al, al2)
+    idx = rng.choice(P, 2048, replace=False)
+    ob, orl = boards[idx].copy(), rowlen[idx].copy()
+    osp, oem, oal = O.fitness_population_c(ob, orl)
+    assert np.array_equal(sp.cpu().numpy()[idx], osp)
+    assert np.array_equal(em.cpu().numpy()[idx], oem)
+    assert np.array_equal(al.cpu().numpy()[idx], oal)
