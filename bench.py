@@ -29,7 +29,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "ga-dpamsa_b200"))
-os.environ.setdefault("GADPAMSA_PROJECT_ROOT", os.path.join(ROOT, "gpurun_out", "project_root"))
+os.environ.setdefault("GADPAMSA_PROJECT_ROOT", os.path.join("/tmp", "gadpamsa_project_root"))
 
 import numpy as np  # noqa: E402
 

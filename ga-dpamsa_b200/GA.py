@@ -1,0 +1,319 @@
+"""GA-DPAMSA generation loop with the reference's ``GA`` class surface (reference GA.py:38-545) on a
+device-resident population.
+
+Every method keeps the reference's name, arguments and observable result; the per-individual python
+loops are replaced by one libgadpamsa launch per phase over all individuals (``population.py``).
+``population`` / ``population_score`` / ``hall_of_fame`` are materialised from the device on read and
+uploaded on assignment, so debug printing and callers that inspect them keep working.
+
+Deliberate deviations:
+  * the agent runs in eval mode (the reference leaves dropout on, which makes results random);
+  * ``'sp'`` mode keeps an SP score of 0 as 0 (the reference's ``sp or cs`` turns it into None and the
+    next sort raises TypeError, GA.py:178);
+  * weights are loaded once per model instead of once per individual (GA.py:354-355);
+  * crossover with fewer than 2 survivors / rows raises ValueError instead of looping forever
+    (GA.py:281-290).
+"""
+from __future__ import annotations
+
+import fractions
+import random
+
+import numpy as np
+import torch
+
+import config
+import utils
+import _native as nat
+from DPAMSA import dqn as _dqn
+from population import DevicePopulation, pack_boards, unpack_boards
+
+# Map nucleotide characters to numerical values (gaps are represented by 5)  - reference GA.py:35
+nucleotides_map = {'A': 1, 'T': 2, 'C': 3, 'G': 4, 'a': 1, 't': 2, 'c': 3, 'g': 4, '-': 5}
+
+
+def _mt_state():
+    """CPython's MT19937 state as a uint32[625] array (624 words + position)."""
+    version, words, gauss = random.getstate()
+    return np.array(words, dtype=np.uint32), (version, gauss)
+
+
+def _mt_restore(arr, meta):
+    random.setstate((meta[0], tuple(int(x) for x in arr), meta[1]))
+
+
+class GA:
+    def __init__(self, sequences, mode):
+        self.sequences = sequences
+        self.mode = mode
+        self.population_size = config.POPULATION_SIZE
+        self.current_iteration = 0
+        self._dev = None                 # DevicePopulation
+        self._device = torch.device(config.DEVICE)
+
+    # ------------------------------------------------------------------ device <-> python views
+    def _weights(self):
+        return int(config.MATCH_REWARD), int(config.MISMATCH_PENALTY), int(config.GAP_PENALTY)
+
+    def _adopt(self, boards, rowlen):
+        """Upload a host population (keeps the hall of fame of the previous device population)."""
+        old = self._dev
+        torch.cuda.set_device(self._device)
+        cap = max(int(config.POPULATION_SIZE), self.population_size, boards.shape[0])
+        extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
+        stride = -(-(boards.shape[2] + extra) // 16) * 16
+        wide = np.full((boards.shape[0], boards.shape[1], stride), 5, dtype=np.uint8)
+        wide[:, :, :boards.shape[2]] = boards
+        self._dev = DevicePopulation.from_numpy(wide, rowlen, device=self._device, capacity=cap)
+        if old is not None and old.hof_valid and old.R == self._dev.R:
+            self._dev.ensure_stride(old.stride)
+            old.ensure_stride(self._dev.stride)
+            self._dev.hof_board.copy_(old.hof_board)
+            self._dev.hof.copy_(old.hof)
+            self._dev.hof_valid = True
+            self._dev.evals, self._dev.forwards = old.evals, old.forwards
+
+    @property
+    def population(self):
+        """Snapshot of the device population as the reference's list of boards of rows of ints.
+        Assign a list to upload it; in-place edits of a returned snapshot are not seen by the device."""
+        return [] if self._dev is None else self._dev.to_lists()
+
+    @population.setter
+    def population(self, boards):
+        if not boards:
+            self._dev = None if self._dev is None or not self._dev.hof_valid else self._dev
+            if self._dev is not None:
+                self._dev.n = 0
+            return
+        self._adopt(*pack_boards(boards))
+
+    @property
+    def population_score(self):
+        """(index, sp) / (index, cs) / (index, sp, cs) tuples like GA.py:175-178 (an SP of 0 stays 0)."""
+        if self._dev is None:
+            return []
+        sp, em, al = self._dev.scores_numpy()
+        out = []
+        for i in range(self._dev.n):
+            cs = int(em[i]) / int(al[i]) if al[i] > 0 else 0
+            if self.mode == 'mo':
+                out.append((i, int(sp[i]), cs))
+            else:
+                out.append((i, int(sp[i]) if self.mode == 'sp' else cs))
+        return out
+
+    @population_score.setter
+    def population_score(self, scores):
+        """Upload externally supplied score tuples (used by callers that drive single phases)."""
+        if self._dev is None or len(scores) != self._dev.n:
+            raise ValueError("population_score must have one tuple per individual of the current population")
+        n = len(scores)
+        sp = np.zeros(n, np.int32)
+        em = np.zeros(n, np.int32)
+        al = np.ones(n, np.int32)
+        for i, t in enumerate(scores):
+            if t[0] != i:
+                raise ValueError("score tuple %d carries index %r" % (i, t[0]))
+            cs = None
+            if len(t) == 3:
+                sp[i], cs = t[1], t[2]
+            elif self.mode == 'sp':
+                sp[i] = t[1]
+            else:
+                cs = t[1]
+            if cs is not None:
+                fr = fractions.Fraction(cs).limit_denominator(1 << 20)
+                if fr.numerator / fr.denominator != cs:
+                    raise ValueError("column score %r is not a ratio of small integers" % (cs,))
+                em[i], al[i] = fr.numerator, fr.denominator
+        b = self._dev.cur
+        for name, arr in (("sp", sp), ("em", em), ("al", al)):
+            getattr(b, name)[:n].copy_(torch.from_numpy(arr))
+
+    def _score_tuple(self, idx, sp, em, al):
+        cs = em / al if al > 0 else 0
+        if self.mode == 'mo':
+            return (idx, sp, cs)
+        return (idx, sp if self.mode == 'sp' else cs)
+
+    @property
+    def hall_of_fame(self):
+        if self._dev is None or not self._dev.hof_valid:
+            return []
+        board, (idx, sp, em, al) = self._dev.hof_numpy()
+        return ([row.tolist() for row in board], self._score_tuple(idx, sp, em, al))
+
+    @hall_of_fame.setter
+    def hall_of_fame(self, value):
+        if value:
+            raise ValueError("the hall of fame lives on the device; only clearing it is supported")
+        if self._dev is not None:
+            self._dev.hof_valid = False
+
+    # ------------------------------------------------------------------ a3
+    def generate_population(self):
+        """GA.py:71-94 through the CPython-compatible MT19937 replay (same draws as the reference)."""
+        nat.require_device()
+        seqs = [[nucleotides_map[nuc] for nuc in seq] for seq in self.sequences]      # KeyError like GA.py:79
+        R = len(seqs)
+        P = self.population_size
+        n_clone = round(P * config.CLONE_RATE)
+        ngaps = np.array([max(1, round(len(s) * config.GAP_RATE)) for s in seqs], dtype=np.int32)
+        seqlen = np.array([len(s) for s in seqs], dtype=np.int32)
+        if n_clone < P and int(seqlen.min()) < 1:
+            raise ValueError("empty range in randrange(0, 0)")                        # random.randint(0, -1)
+        cstride = max(1, int(seqlen.max()))
+        seq_arr = np.full((R, cstride), 5, dtype=np.uint8)
+        for r, s in enumerate(seqs):
+            seq_arr[r, :len(s)] = s
+        stride = -(-(cstride + int(ngaps.max())) // 16) * 16
+        boards = np.empty((P, R, stride), dtype=np.uint8)
+        rowlen = np.empty((P, R), dtype=np.int32)
+        state, meta = _mt_state()
+        nat.call("gad_mt_population_host", state.ctypes.data, seq_arr.ctypes.data, seqlen.ctypes.data, cstride,
+                 ngaps.ctypes.data, R, P, n_clone, boards.ctypes.data, rowlen.ctypes.data, stride)
+        _mt_restore(state, meta)
+        hof_keep = self._dev
+        self._dev = None
+        self._adopt(boards, rowlen)
+        del hof_keep
+
+    # ------------------------------------------------------------------ a4 + a8
+    def update_hall_of_fame(self):
+        self._dev.hof_update(self.mode)
+
+    def calculate_fitness_score(self):
+        """GA.py:154-181: pad, clean, score every board (one launch), then the hall of fame."""
+        if self._dev is None or self._dev.n == 0:
+            raise ValueError("empty population")
+        self._dev.fitness(*self._weights())
+        self.update_hall_of_fame()
+
+    # ------------------------------------------------------------------ a10 / a11
+    def _find_pareto_front(self):
+        """GA.py:195-211 (computed in O(P log P) on the device, same set, index order)."""
+        keep, _ = self._dev.select_flags('mo', -1)
+        flags = keep.cpu().numpy()
+        scores = self.population_score
+        return [scores[i] for i in np.nonzero(flags)[0]]
+
+    def selection(self):
+        """GA.py:232-260"""
+        top_n = int(self.population_size * config.SELECTION_RATE)
+        self._dev.select(self.mode, top_n)
+        self.calculate_fitness_score()
+
+    # ------------------------------------------------------------------ a12 / a13
+    def _crossover(self, kind):
+        dev = self._dev
+        n_children = int(config.POPULATION_SIZE) - dev.n
+        if n_children > 0:
+            widths = None
+            if kind == 1:
+                widths = dev.cur.al[:dev.n].cpu().numpy().astype(np.int32)
+            plan = np.empty((n_children, 3), dtype=np.int32)
+            state, meta = _mt_state()
+            nat.call("gad_mt_crossover_plan_host", state.ctypes.data, dev.n, dev.R, n_children,
+                     None if widths is None else widths.ctypes.data, plan.ctypes.data)
+            _mt_restore(state, meta)
+            dev.crossover(plan, kind)
+        self.calculate_fitness_score()
+
+    def horizontal_crossover(self):
+        """GA.py:281-301"""
+        self._crossover(0)
+
+    def vertical_crossover(self):
+        """Extension (supplement table A5; no reference code): every child row is
+        parent1[:cut] + parent2[cut:], cut = randint(1, min(width1, width2) - 1)."""
+        self._crossover(1)
+
+    # ------------------------------------------------------------------ a14
+    def mutation(self, model_path):
+        """GA.py:323-373 for all selected individuals at once."""
+        dev = self._dev
+        rw, cw = int(config.AGENT_WINDOW_ROW), int(config.AGENT_WINDOW_COLUMN)
+        n = round(config.POPULATION_SIZE * config.MUTATION_RATE)
+        n = min(n, dev.n)
+        if n <= 0:
+            return
+        if rw > dev.R:
+            raise ValueError("AGENT_WINDOW_ROW is larger than the sequence count.")
+        qnet = _dqn.load_qnet(model_path, rw, cw)
+        idx = dev.rank_order(self.mode, n)
+        tile = dev.worst_tiles(idx, rw, cw, self.mode, *self._weights())
+        if int(tile.min().item()) < 0:
+            raise ValueError("min() arg is an empty sequence")          # no tile fits (utils.py:291)
+        max_reward = rw * (rw - 1) / 2 * config.MATCH_REWARD            # env.py:79
+        dev.mutate(qnet, idx, tile, cw * max_reward)                    # GA.py:354
+
+    # ------------------------------------------------------------------ a22
+    def print_hall_of_fame(self):
+        if not self.hall_of_fame:
+            print("Hall of Fame is empty! No best individual found yet.")
+            return
+        hof_individual, hof_score = self.hall_of_fame
+        print("\nHALL OF FAME - BEST INDIVIDUAL SO FAR:")
+        print("=" * 50)
+        for sequence in utils.get_nucleotides_seqs(hof_individual):
+            print("   %s" % sequence)
+        if self.mode in {"sp", "cs"}:
+            print("   Best %s Score: %s" % ("SP" if self.mode == "sp" else "CS", hof_score[1]))
+        else:
+            print("   SP Score: %s" % (hof_score[1],))
+            print("   CS Score: %s" % (hof_score[2],))
+        print("=" * 50)
+
+    def print_population(self):
+        print("\nCURRENT POPULATION (Iteration {}):".format(self.current_iteration))
+        print("=" * 50)
+        population = self.population
+        if not population:
+            print("Empty Population! Make sure your population was generated correctly.")
+            return
+        for i, (individual, scores) in enumerate(zip(population, self.population_score), start=1):
+            print("Individual %d:" % i)
+            for sequence in utils.get_nucleotides_seqs(individual):
+                print("   %s" % sequence)
+            if self.mode in {'sp', 'cs'}:
+                print("   Fitness Score (%s): %s" % ("SP" if self.mode == "sp" else "CS", scores[1]))
+            else:
+                print("   SP Score: %s" % (scores[1],))
+                print("   CS Score: %s" % (scores[2],))
+            print("-" * 50)
+        self.print_hall_of_fame()
+        print("\nPopulation entirely printed.\n")
+
+    # ------------------------------------------------------------------ a19
+    def run(self, model_path, debug_mode=False):
+        """GA.py:471-545"""
+        self.generate_population()
+        self.calculate_fitness_score()
+        if debug_mode:
+            self.print_population()
+        dev = self._dev
+        if config.AGENT_WINDOW_ROW > dev.R:
+            raise ValueError("AGENT_WINDOW_ROW is larger than the sequence count.")
+        sequence_min_length = int(dev.cur.rowlen[0].min().item())
+        if config.AGENT_WINDOW_COLUMN > sequence_min_length:
+            raise ValueError("AGENT_WINDOW_COLUMN is larger than the shortest sequence length.")
+        for i in range(config.GA_ITERATIONS):
+            if debug_mode:
+                print("Iteration %d/%d..." % (i + 1, config.GA_ITERATIONS))
+            self.current_iteration += 1
+            self.mutation(model_path)
+            self.calculate_fitness_score()
+            if debug_mode:
+                self.print_population()
+            self.selection()
+            if debug_mode:
+                self.print_population()
+            if getattr(config, "CROSSOVER_KIND", "horizontal") == "vertical":
+                self.vertical_crossover()
+            else:
+                self.horizontal_crossover()
+            if debug_mode:
+                self.print_population()
+        best_chromosome, _ = self.hall_of_fame
+        return utils.get_nucleotides_seqs(best_chromosome)

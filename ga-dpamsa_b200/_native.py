@@ -40,6 +40,26 @@ SIGNATURES = {
     "gad_fitness_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int]),
     "gad_window_score_host": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_i64p, c_i32p]),
+    "gad_workspace_bytes": (c_int, [c_i64, ctypes.POINTER(ctypes.c_size_t)]),
+    "gad_rank_keys": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "gad_rank_order": (c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "gad_select": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "gad_compact": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                            c_vp, c_vp]),
+    "gad_hof_update": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp,
+                               ctypes.c_size_t, c_vp]),
+    "gad_crossover": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "gad_mt_crossover_plan_host": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
+    "gad_mt_population_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_int]),
+    "gad_worst_tiles": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_vp, c_vp]),
+    "gad_qnet_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, c_int, c_int,
+                                ctypes.POINTER(c_vp)]),
+    "gad_qnet_destroy": (c_int, [c_vp]),
+    "gad_qnet_dims": (c_int, [c_vp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "gad_qnet_forward": (c_int, [c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_vp, c_vp]),
+    "gad_qnet_forward_host": (c_int, [c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_vp]),
+    "gad_mutate": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_i64p, c_vp]),
 }
 
 

@@ -1,0 +1,131 @@
+// CPython-compatible MT19937 replay on the host.
+// The reference draws every random number through CPython's `random` module
+// (GA.py:90 randint, GA.py:283-284 choice, GA.py:293 randint), i.e. through
+// Random._randbelow_with_getrandbits over genrand_uint32 (Lib/random.py, Modules/_randommodule.c).
+// These entry points take the 625-word state of random.getstate() (624 words + position), consume
+// exactly the draws the reference would and hand the advanced state back for random.setstate(),
+// so "identical seeds" gives identical populations and crossover plans at any population size.
+#include "gad_common.cuh"
+
+#include <string.h>
+#include <vector>
+
+namespace {
+
+struct MT {
+    uint32_t *mt;      // 624 words, caller's buffer
+    int pos;
+
+    void reload()
+    {
+        const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAG = 0x9908b0dfu;
+        int kk;
+        for (kk = 0; kk < 624 - 397; ++kk) {
+            const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+            mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+        }
+        for (; kk < 623; ++kk) {
+            const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+            mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+        }
+        const uint32_t y = (mt[623] & UPPER) | (mt[0] & LOWER);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+        pos = 0;
+    }
+
+    uint32_t next32()
+    {
+        if (pos >= 624) reload();
+        uint32_t y = mt[pos++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+
+    // Random._randbelow_with_getrandbits for 0 < n < 2^32: k = n.bit_length(); draw getrandbits(k) until < n
+    uint32_t randbelow(uint32_t n)
+    {
+        int k = 0;
+        for (uint32_t t = n; t; t >>= 1) ++k;
+        uint32_t r = next32() >> (32 - k);
+        while (r >= n) r = next32() >> (32 - k);
+        return r;
+    }
+};
+
+}  // namespace
+
+// GA.py:281-293: while children are missing: p1 = choice(pop), p2 = choice(pop); same object -> retry;
+// cut = randint(1, rows - 1). Vertical (h_widths != NULL): cut = randint(1, min(width1, width2) - 1).
+extern "C" int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
+                                          const int32_t *h_widths, int32_t *h_plan)
+{
+    GAD_REQUIRE(mt_state && (h_plan || n_children == 0), "gad_mt_crossover_plan_host: null pointer");
+    GAD_REQUIRE(n_children >= 0 && n_parents >= 0 && n_parents < (1ll << 31), "gad_mt_crossover_plan_host: bad sizes");
+    if (n_children == 0) return GAD_OK;
+    // the reference never terminates in these cases (GA.py:285-290)
+    GAD_REQUIRE(n_parents >= 2, "crossover needs at least 2 survivors (the reference loops forever with %lld)",
+                (long long)n_parents);
+    GAD_REQUIRE(h_widths || n_rows >= 2, "horizontal crossover needs at least 2 rows (the reference loops forever)");
+    MT g{mt_state, (int)mt_state[624]};
+    GAD_REQUIRE(g.pos >= 0 && g.pos <= 624, "gad_mt_crossover_plan_host: corrupt MT19937 position %d", g.pos);
+    for (int64_t c = 0; c < n_children;) {
+        const uint32_t a = g.randbelow((uint32_t)n_parents);
+        const uint32_t b = g.randbelow((uint32_t)n_parents);
+        if (a == b) continue;
+        int cut;
+        if (h_widths) {
+            const int m = h_widths[a] < h_widths[b] ? h_widths[a] : h_widths[b];
+            GAD_REQUIRE(m >= 2, "vertical crossover needs parents at least 2 columns wide");
+            cut = 1 + (int)g.randbelow((uint32_t)(m - 1));
+        } else {
+            cut = 1 + (int)g.randbelow((uint32_t)(n_rows - 1));
+        }
+        h_plan[3 * c + 0] = (int32_t)a;
+        h_plan[3 * c + 1] = (int32_t)b;
+        h_plan[3 * c + 2] = cut;
+        ++c;
+    }
+    mt_state[624] = (uint32_t)g.pos;
+    return GAD_OK;
+}
+
+// GA.py:71-94: n_clone exact copies first, then every row of every other individual gets h_ngaps[r] gaps
+// inserted one at a time at randint(0, len_now - 1) (the row grows with every insert; never appended).
+// Output in the library's layout: uint8 boards[P][R][stride] (gap code beyond each row), int32 rowlen[P][R].
+extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
+                                      int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
+                                      uint8_t *h_boards, int32_t *h_rowlen, int stride)
+{
+    GAD_REQUIRE(mt_state && h_seqs && h_seqlen && h_ngaps && h_boards && h_rowlen, "gad_mt_population_host: null pointer");
+    GAD_REQUIRE(R >= 1 && P >= 0 && n_clone >= 0 && n_clone <= P && stride >= 1, "gad_mt_population_host: bad sizes");
+    for (int r = 0; r < R; ++r) {
+        GAD_REQUIRE(h_seqlen[r] >= 0 && h_seqlen[r] <= seq_stride, "gad_mt_population_host: bad sequence length");
+        const bool grows = n_clone < P;
+        GAD_REQUIRE(h_seqlen[r] + (grows ? h_ngaps[r] : 0) <= stride, "gad_mt_population_host: row %d does not fit the stride", r);
+        GAD_REQUIRE(!grows || h_seqlen[r] >= 1, "empty sequence: the reference raises ValueError in randint(0, -1)");
+    }
+    MT g{mt_state, (int)mt_state[624]};
+    GAD_REQUIRE(g.pos >= 0 && g.pos <= 624, "gad_mt_population_host: corrupt MT19937 position %d", g.pos);
+    memset(h_boards, GAD_GAP, (size_t)P * R * stride);
+    for (int64_t p = 0; p < P; ++p) {
+        for (int r = 0; r < R; ++r) {
+            uint8_t *row = h_boards + ((size_t)p * R + r) * stride;
+            int len = h_seqlen[r];
+            memcpy(row, h_seqs + (size_t)r * seq_stride, (size_t)len);
+            if (p >= n_clone) {
+                for (int k = 0; k < h_ngaps[r]; ++k) {
+                    const int at = (int)g.randbelow((uint32_t)len);      // randint(0, len - 1)
+                    memmove(row + at + 1, row + at, (size_t)(len - at));
+                    row[at] = GAD_GAP;
+                    ++len;
+                }
+            }
+            h_rowlen[(size_t)p * R + r] = len;
+        }
+    }
+    mt_state[624] = (uint32_t)g.pos;
+    return GAD_OK;
+}

@@ -1,0 +1,742 @@
+// Batched DPAMSA Q-network and alignment-environment episodes: the mutation phase of the generation
+// loop for every mutating individual at once. Replaces the per-individual python loop of GA.mutation
+// (reference GA.py:335-373): Environment.reset/step/padding (DPAMSA/env.py:139-153,231-259,338-351),
+// DQN.predict (DPAMSA/dqn.py:151-154) and Net.forward (dqn.py:69-79; models.py:241-249,190-207,87-95),
+// in eval mode (dropout is the identity).
+//
+// B200-first restructuring of the encoder (not a translation of the torch graph):
+//   * tokens are in {0..5} and the positional encoding is fixed, so everything per-token - embedding,
+//     positional add, first LayerNorm and the bias-free Q/K/V projections - depends only on
+//     (token, position). At load time the host folds them (in fp64) into three small tables:
+//         X [6][L][64]      first-LayerNorm output (also the residual)
+//         T [6][L][6][L]    attention logit  (x_i Wq^T / sqrt(dk)) . (x_j Wk^T)  for every pair
+//         VF[6][L][64]      (x_j Wv^T) Wfc^T  - the value projection with the output projection folded in
+//     so one forward needs no QKV or fc GEMM: logits are gathers from T (L2-resident), the
+//     attention output is softmax(T) . VF.
+//   * what remains dense is l1 (L*64 -> h1, ~95 % of the weights), l2 and l3: l1/l2 run as one tiled
+//     GEMM over all active episodes; l3 + tanh + argmax + Environment.step are fused in one kernel.
+//   * episodes run in lock-step on device with an active list that shrinks as episodes finish; the
+//     host only polls the active count.
+#include "gad_common.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#define QN_D 64            // d_model of the reference encoder (dqn.py:54)
+#define QN_VOCAB 6         // 0 = padding, 1..5 = A T C G gap
+
+struct gad_qnet {
+    int rows, cols, L, A, K, h1, h2;
+    // parameters / folded tables (device, fp32)
+    float *X = nullptr, *T = nullptr, *VF = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *W3 = nullptr, *b3 = nullptr;
+    // activation scratch for `cap` states
+    long long cap = 0;
+    uint8_t *tok = nullptr;
+    float *Z = nullptr, *H1 = nullptr, *H2 = nullptr, *Q = nullptr;
+    int32_t *act = nullptr;
+    // episode state for `ecap` episodes
+    long long ecap = 0;
+    uint8_t *sub = nullptr, *heads = nullptr, *aligned = nullptr;
+    int32_t *steps = nullptr, *list0 = nullptr, *list1 = nullptr, *counts = nullptr;   // counts[2]
+    int32_t *h_count = nullptr;   // pinned
+};
+
+namespace {
+
+const long long kMaxBatch = 32768;     // states per lock-step chunk (Z is kMaxBatch * K * 4 bytes)
+
+// ---------------------------------------------------------------------------------------------
+// encoder: tokens -> Z[row][L*64]  (attention over table logits, + residual, second LayerNorm)
+// ---------------------------------------------------------------------------------------------
+#define ENC_QT 4           // query rows per warp trip
+
+// tokens of episode e from its sub-board and head pointers (env.py:147-153): every row's remaining
+// tokens followed by one gap code, rows concatenated, zero padding up to L
+__device__ __forceinline__ int build_tokens(uint8_t *tok, const uint8_t *sub, const uint8_t *heads, int rows, int cols,
+                                            int L)
+{
+    __shared__ int s_off[33];
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int r = 0; r < rows; ++r) {
+            s_off[r] = o;
+            o += cols - heads[r] + 1;
+        }
+        s_off[rows] = o;
+    }
+    __syncthreads();
+    const int nvalid = s_off[rows];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        uint8_t t = 0;
+        if (i < nvalid) {
+            int r = 0;
+            while (i >= s_off[r + 1]) ++r;
+            const int k = i - s_off[r];
+            const int rem = cols - heads[r];
+            t = k < rem ? sub[r * cols + heads[r] + k] : (uint8_t)GAD_GAP;
+        }
+        tok[i] = t;
+    }
+    __syncthreads();
+    return nvalid;
+}
+
+__global__ void __launch_bounds__(256)
+encode_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
+              const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout)
+{
+    extern __shared__ float smem[];
+    const int L = net.L;
+    const int nw = blockDim.x >> 5;
+    float *Pw = smem;                                         // [nw][L][ENC_QT]
+    uint8_t *tok = reinterpret_cast<uint8_t *>(smem + (size_t)nw * L * ENC_QT);   // [L]
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();
+        int nvalid;
+        if (tok_in) {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
+            __syncthreads();
+            nvalid = 0;                                        // keys are masked where the token is 0 (dqn.py:67)
+            for (int i = 0; i < L; ++i) nvalid += tok[i] != 0;
+        } else {
+            const int e = active[row];
+            nvalid = build_tokens(tok, net.sub + (size_t)e * net.rows * net.cols, net.heads + (size_t)e * net.rows,
+                                  net.rows, net.cols, L);
+        }
+        // Valid keys are not necessarily a prefix when tokens are given explicitly: build the key list.
+        // (For environment states they are exactly the first nvalid positions.)
+        float *P = Pw + (size_t)warp * L * ENC_QT;
+        for (int i0 = warp * ENC_QT; i0 < L; i0 += nw * ENC_QT) {
+            float mx[ENC_QT], sum[ENC_QT];
+            const float *trow[ENC_QT];
+#pragma unroll
+            for (int q = 0; q < ENC_QT; ++q) {
+                const int i = min(i0 + q, L - 1);
+                trow[q] = net.T + ((size_t)tok[i] * L + i) * (QN_VOCAB * L);
+                mx[q] = -INFINITY;
+                sum[q] = 0.f;
+            }
+            // logits (masked keys get -1e9 like models.py:90-91)
+            for (int j = lane; j < L; j += 32) {
+                const int tj = tok[j];
+#pragma unroll
+                for (int q = 0; q < ENC_QT; ++q) {
+                    const float s = tj ? __ldg(trow[q] + tj * L + j) : -1e9f;
+                    P[j * ENC_QT + q] = s;
+                    mx[q] = fmaxf(mx[q], s);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < ENC_QT; ++q)
+                for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xFFFFFFFFu, mx[q], o));
+            __syncwarp();
+            for (int j = lane; j < L; j += 32) {
+#pragma unroll
+                for (int q = 0; q < ENC_QT; ++q) {
+                    const float e = expf(P[j * ENC_QT + q] - mx[q]);
+                    P[j * ENC_QT + q] = e;
+                    sum[q] += e;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < ENC_QT; ++q)
+                for (int o = 16; o > 0; o >>= 1) sum[q] += __shfl_xor_sync(0xFFFFFFFFu, sum[q], o);
+            __syncwarp();
+            // attention output with the fc projection folded in: acc[q][c] = sum_j e[q][j] * VF[tok_j][j][c]
+            float acc0[ENC_QT], acc1[ENC_QT];
+#pragma unroll
+            for (int q = 0; q < ENC_QT; ++q) acc0[q] = acc1[q] = 0.f;
+            for (int j = 0; j < L; ++j) {
+                const int tj = tok[j];
+                if (tj == 0 && nvalid) continue;               // exp(-1e9 - max) == 0 exactly
+                const float *vf = net.VF + ((size_t)tj * L + j) * QN_D;
+                const float v0 = __ldg(vf + lane), v1 = __ldg(vf + lane + 32);
+                const float4 p = *reinterpret_cast<const float4 *>(P + j * ENC_QT);
+                acc0[0] = fmaf(p.x, v0, acc0[0]);
+                acc1[0] = fmaf(p.x, v1, acc1[0]);
+                acc0[1] = fmaf(p.y, v0, acc0[1]);
+                acc1[1] = fmaf(p.y, v1, acc1[1]);
+                acc0[2] = fmaf(p.z, v0, acc0[2]);
+                acc1[2] = fmaf(p.z, v1, acc1[2]);
+                acc0[3] = fmaf(p.w, v0, acc0[3]);
+                acc1[3] = fmaf(p.w, v1, acc1[3]);
+            }
+            const float g0 = net.ln2_g[lane], g1 = net.ln2_g[lane + 32], be0 = net.ln2_b[lane], be1 = net.ln2_b[lane + 32];
+#pragma unroll
+            for (int q = 0; q < ENC_QT; ++q) {
+                const int i = i0 + q;
+                if (i >= L) break;
+                const float *x = net.X + ((size_t)tok[i] * L + i) * QN_D;
+                const float inv = 1.f / sum[q];
+                const float y0 = fmaf(acc0[q], inv, x[lane]), y1 = fmaf(acc1[q], inv, x[lane + 32]);   // + residual
+                float s = y0 + y1;
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+                const float mu = s * (1.f / QN_D);
+                const float d0 = y0 - mu, d1 = y1 - mu;
+                float v = d0 * d0 + d1 * d1;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                const float rstd = rsqrtf(v * (1.f / QN_D) + 1e-6f);       // LayerNorm(eps=1e-6), models.py:166
+                float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D;
+                z[lane] = d0 * rstd * g0 + be0;
+                z[lane + 32] = d1 * rstd * g1 + be1;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense layers: C[M][N] = leaky_relu(A[M][K] . W[N][K]^T + b), fp32 SIMT tiles 128x128x16
+// ---------------------------------------------------------------------------------------------
+#define GM_BM 128
+#define GM_BN 128
+#define GM_BK 16
+
+__global__ void __launch_bounds__(256)
+dense_kernel(const float *__restrict__ A, const float *__restrict__ W, const float *__restrict__ bias,
+             float *__restrict__ C, const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky)
+{
+    __shared__ __align__(16) float As[2][GM_BK][GM_BM + 4];
+    __shared__ __align__(16) float Bs[2][GM_BK][GM_BN + 4];
+    const long long M = m_ptr ? (long long)*m_ptr : m_fixed;
+    const long long m0 = (long long)blockIdx.y * GM_BM;
+    const int n0 = blockIdx.x * GM_BN;
+    if (m0 >= M) return;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    // loader mapping: each thread moves 2 float4 of A and 2 of W per k-tile
+    const int lrow = tid >> 2;            // 0..63 (+64)
+    const int lk = (tid & 3) * 4;         // 0,4,8,12
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb[2];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long r = m0 + lrow + 64 * h;
+            const int n = n0 + lrow + 64 * h;
+            const int k = k0 + lk;
+            ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < K) {
+                if (r < M) ra[h] = *reinterpret_cast<const float4 *>(A + (size_t)r * K + k);
+                if (n < N) rb[h] = __ldg(reinterpret_cast<const float4 *>(W + (size_t)n * K + k));
+            }
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lrow + 64 * h;
+            As[buf][lk + 0][r] = ra[h].x;
+            As[buf][lk + 1][r] = ra[h].y;
+            As[buf][lk + 2][r] = ra[h].z;
+            As[buf][lk + 3][r] = ra[h].w;
+            Bs[buf][lk + 0][r] = rb[h].x;
+            Bs[buf][lk + 1][r] = rb[h].y;
+            Bs[buf][lk + 2][r] = rb[h].z;
+            Bs[buf][lk + 3][r] = rb[h].w;
+        }
+    };
+    const int nk = (K + GM_BK - 1) / GM_BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * GM_BK);
+#pragma unroll
+        for (int k = 0; k < GM_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4 + 64]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4 + 64]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = m0 + ty * 4 + (i & 3) + 64 * (i >> 2);
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + tx * 4 + (j & 3) + 64 * (j >> 2);
+            if (n >= N) continue;
+            float v = acc[i][j] + bias[n];
+            if (leaky) v = v > 0.f ? v : 0.01f * v;            // nn.LeakyReLU default slope, dqn.py:58,60
+            C[(size_t)r * N + n] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// l3 + tanh * max_value + greedy argmax (+ Environment.step when episodes are running)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_step_kernel(const gad_qnet net, const float *__restrict__ H2, const int32_t *__restrict__ n_rows_ptr,
+                 long long n_rows_fixed, float max_value, float *__restrict__ Qout, int32_t *__restrict__ act_out,
+                 const int32_t *__restrict__ active, int32_t *__restrict__ next_active,
+                 int32_t *__restrict__ next_count)
+{
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int h2 = net.h2, A = net.A;
+    const float *h = H2 + (size_t)row * h2;
+    float best = 0.f;
+    int best_a = -1;
+    for (int a = 0; a < A; ++a) {
+        const float *w = net.W3 + (size_t)a * h2;
+        float s = 0.f;
+        for (int k = lane; k < h2; k += 32) s = fmaf(h[k], __ldg(w + k), s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        const float q = tanhf(s + net.b3[a]) * max_value;      // dqn.py:76-77
+        if (Qout && lane == 0) Qout[(size_t)row * A + a] = q;
+        if (best_a < 0 || q > best) {                          // torch.argmax: first maximum
+            best = q;
+            best_a = a;
+        }
+    }
+    if (lane != 0) return;
+    if (act_out) act_out[row] = best_a;
+    if (!active) return;
+    // Environment.step (env.py:246-259) for this episode
+    const int e = active[row];
+    const int rows = net.rows, cols = net.cols;
+    uint8_t *hd = net.heads + (size_t)e * rows;
+    for (int r = 0; r < rows; ++r)
+        if (!((best_a >> r) & 1) && hd[r] >= cols) return;    // illegal action: nothing changes, episode ends
+    const int t = net.steps[e];
+    const int cap = rows * cols;
+    const uint8_t *sub = net.sub + (size_t)e * rows * cols;
+    uint8_t *al = net.aligned + (size_t)e * rows * cap;
+    int left = 0;
+    for (int r = 0; r < rows; ++r) {
+        uint8_t v = GAD_GAP;
+        if (!((best_a >> r) & 1)) v = sub[r * cols + hd[r]++];
+        al[(size_t)r * cap + t] = v;
+        left += cols - hd[r];
+    }
+    net.steps[e] = t + 1;
+    if (left > 0) next_active[atomicAdd(next_count, 1)] = e;   // done == 1: the episode continues
+}
+
+// ---------------------------------------------------------------------------------------------
+// episodes: set-up and splice
+// ---------------------------------------------------------------------------------------------
+__global__ void episode_init_kernel(const gad_qnet net, const uint8_t *__restrict__ boards, int R, int stride,
+                                    const int32_t *__restrict__ idx, const int32_t *__restrict__ tile, long long M,
+                                    int32_t *__restrict__ list, int32_t *__restrict__ counts)
+{
+    const long long m = blockIdx.x;
+    const int rows = net.rows, cols = net.cols;
+    const long long p = idx ? idx[m] : m;
+    const int fr = tile[2 * m], fc = tile[2 * m + 1];
+    if (fr < 0 || fc < 0) {                                // no tile fits this board (gad_worst_tiles): not mutated
+        if (threadIdx.x == 0) net.steps[m] = -1;
+        return;
+    }
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        net.sub[(size_t)m * rows * cols + i] = boards[((size_t)p * R + fr + r) * stride + fc + c];
+    }
+    if (threadIdx.x < rows) net.heads[(size_t)m * rows + threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        net.steps[m] = 0;
+        list[atomicAdd(&counts[0], 1)] = (int32_t)m;      // order inside the list is irrelevant: episodes are independent
+    }
+}
+
+// Environment.padding (env.py:344-351) + the splice of GA.py:369-373, one warp per episode.
+// The tile's rows become old[:fc] + aligned + leftovers + gaps + old[fc+cols:], i.e. they grow by
+// d = steps + longest leftover - cols >= 0; the other rows keep their cells.
+__global__ void __launch_bounds__(128)
+splice_kernel(const gad_qnet net, uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, int R, int stride,
+              const int32_t *__restrict__ idx, const int32_t *__restrict__ tile, long long M,
+              int32_t *__restrict__ status)
+{
+    const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int rows = net.rows, cols = net.cols, cap = rows * cols;
+    const long long p = idx ? idx[m] : m;
+    const int fr = tile[2 * m], fc = tile[2 * m + 1];
+    const uint8_t *hd = net.heads + (size_t)m * rows;
+    const int T = net.steps[m];
+    if (T < 0) return;
+    int longest = 0;
+    for (int r = 0; r < rows; ++r) longest = max(longest, cols - (int)hd[r]);
+    const int newlen = T + longest;                 // length of every aligned row after padding
+    const int d = newlen - cols;
+    int wmax = 0;
+    for (int r = 0; r < R; ++r) {
+        const int l = rowlen[p * R + r];
+        wmax = max(wmax, (r >= fr && r < fr + rows) ? l + d : l);
+    }
+    if (wmax > stride) {                            // cannot happen when the caller sized the stride (gadpamsa.h)
+        if (lane == 0) atomicOr(status, 1);
+        return;
+    }
+    __syncwarp();
+    for (int r = 0; r < rows; ++r) {
+        uint8_t *row = boards + ((size_t)p * R + fr + r) * stride;
+        const int len = rowlen[p * R + fr + r];
+        __syncwarp();
+        const int tail0 = fc + cols;                // first cell after the window
+        // move the tail right by d, highest addresses first so the move is safe in place
+        if (d > 0) {
+            for (int hi = len; hi > tail0; hi -= 32) {
+                const int c = hi - 1 - lane;
+                uint8_t v = 0;
+                if (c >= tail0) v = row[c];
+                __syncwarp();
+                if (c >= tail0) row[c + d] = v;
+                __syncwarp();
+            }
+        }
+        const uint8_t *al = net.aligned + ((size_t)m * rows + r) * cap;
+        const uint8_t *sub = net.sub + ((size_t)m * rows + r) * cols;
+        const int h = hd[r];
+        for (int c = lane; c < newlen; c += 32) {
+            uint8_t v;
+            if (c < T) v = al[c];
+            else if (c - T < cols - h) v = sub[h + c - T];      // leftovers (env.py:346-347)
+            else v = GAD_GAP;                                   // right padding (env.py:349-350)
+            row[fc + c] = v;
+        }
+        if (lane == 0) rowlen[p * R + fr + r] = len + d;
+    }
+    // layout invariant: every row holds the gap code from its own length up to roundup4(board width)
+    __syncwarp();
+    const int pad_to = min(stride, (wmax + 3) & ~3);
+    for (int r = 0; r < R; ++r) {
+        uint8_t *row = boards + ((size_t)p * R + r) * stride;
+        const int len = rowlen[p * R + r];
+        for (int c = len + lane; c < pad_to; c += 32) row[c] = GAD_GAP;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+int dev_alloc(T **p, size_t n)
+{
+    GAD_CUDA(cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)));
+    return GAD_OK;
+}
+
+int upload(float **dst, const std::vector<float> &src)
+{
+    int rc = dev_alloc(dst, src.size());
+    if (rc) return rc;
+    GAD_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return GAD_OK;
+}
+
+int upload(float **dst, const float *src, size_t n)
+{
+    int rc = dev_alloc(dst, n);
+    if (rc) return rc;
+    GAD_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return GAD_OK;
+}
+
+int ensure_states(gad_qnet *q, long long B)
+{
+    if (B <= q->cap) return GAD_OK;
+    cudaFree(q->tok); cudaFree(q->Z); cudaFree(q->H1); cudaFree(q->H2); cudaFree(q->Q); cudaFree(q->act);
+    q->tok = nullptr; q->Z = q->H1 = q->H2 = q->Q = nullptr; q->act = nullptr;
+    q->cap = 0;
+    int rc;
+    if ((rc = dev_alloc(&q->tok, (size_t)B * q->L))) return rc;
+    if ((rc = dev_alloc(&q->Z, (size_t)B * q->K))) return rc;
+    if ((rc = dev_alloc(&q->H1, (size_t)B * q->h1))) return rc;
+    if ((rc = dev_alloc(&q->H2, (size_t)B * q->h2))) return rc;
+    if ((rc = dev_alloc(&q->Q, (size_t)B * q->A))) return rc;
+    if ((rc = dev_alloc(&q->act, (size_t)B))) return rc;
+    q->cap = B;
+    return GAD_OK;
+}
+
+int ensure_episodes(gad_qnet *q, long long M)
+{
+    if (M <= q->ecap) return GAD_OK;
+    cudaFree(q->sub); cudaFree(q->heads); cudaFree(q->aligned); cudaFree(q->steps); cudaFree(q->list0); cudaFree(q->list1);
+    q->sub = q->heads = q->aligned = nullptr; q->steps = q->list0 = q->list1 = nullptr;
+    q->ecap = 0;
+    const size_t rc_ = (size_t)q->rows * q->cols;
+    int rc;
+    if ((rc = dev_alloc(&q->sub, (size_t)M * rc_))) return rc;
+    if ((rc = dev_alloc(&q->heads, (size_t)M * q->rows))) return rc;
+    if ((rc = dev_alloc(&q->aligned, (size_t)M * q->rows * rc_))) return rc;
+    if ((rc = dev_alloc(&q->steps, (size_t)M))) return rc;
+    if ((rc = dev_alloc(&q->list0, (size_t)M))) return rc;
+    if ((rc = dev_alloc(&q->list1, (size_t)M))) return rc;
+    q->ecap = M;
+    return GAD_OK;
+}
+
+int encode_smem_bytes(int L, int warps) { return warps * L * ENC_QT * (int)sizeof(float) + ((L + 15) & ~15); }
+
+// one forward over `n` rows (device count in n_ptr, or n_fixed): tokens/episodes -> H2, then the head kernel
+int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const int32_t *n_ptr, long long n_max,
+                   float max_value, float *Qout, int32_t *act_out, int32_t *next_active, int32_t *next_count,
+                   cudaStream_t st)
+{
+    int warps = 8;
+    while (warps > 1 && encode_smem_bytes(q->L, warps) > 200 * 1024) warps >>= 1;
+    const int smem = encode_smem_bytes(q->L, warps);
+    GAD_REQUIRE(smem <= 227 * 1024, "agent window too large for the encoder kernel (L=%d)", q->L);
+    if (smem > 48 * 1024)
+        GAD_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    long long grid = n_max < (long long)GAD_NUM_SMS * 16 ? n_max : (long long)GAD_NUM_SMS * 16;
+    encode_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z);
+    GAD_LAUNCH_CHECK();
+    const unsigned mt = (unsigned)((n_max + GM_BM - 1) / GM_BM);
+    dense_kernel<<<dim3((q->h1 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->Z, q->W1, q->b1, q->H1, n_ptr, n_max, q->h1,
+                                                                        q->K, 1);
+    dense_kernel<<<dim3((q->h2 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->H1, q->W2, q->b2, q->H2, n_ptr, n_max, q->h2,
+                                                                        q->h1, 1);
+    head_step_kernel<<<(unsigned)((n_max + 7) / 8), 256, 0, st>>>(*q, q->H2, n_ptr, n_max, max_value, Qout, act_out,
+                                                                  active, next_active, next_count);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+void layer_norm64(const double *x, const float *g, const float *b, double *y)
+{
+    double mu = 0, var = 0;
+    for (int c = 0; c < QN_D; ++c) mu += x[c];
+    mu /= QN_D;
+    for (int c = 0; c < QN_D; ++c) var += (x[c] - mu) * (x[c] - mu);
+    var /= QN_D;
+    const double rstd = 1.0 / sqrt(var + 1e-6);
+    for (int c = 0; c < QN_D; ++c) y[c] = (x[c] - mu) * rstd * g[c] + b[c];
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+// h_weights: the 16 tensors of the reference state_dict in this order (DPAMSA/dqn.py:187-199):
+//  0 encoder.src_word_emb.weight (6,64)       1 encoder.position_enc.pos_table (1,L,64)
+//  2 encoder.layer_norm.weight (64)            3 encoder.layer_norm.bias (64)
+//  4 w_qs.weight (d_k,64)   5 w_ks.weight (d_k,64)   6 w_vs.weight (d_v,64)   7 fc.weight (64,d_v)
+//  8 self_attention.layer_norm.weight (64)     9 self_attention.layer_norm.bias (64)
+// 10 l1.weight (h1, L*64)  11 l1.bias  12 l2.weight (h2,h1)  13 l2.bias  14 l3.weight (A,h2)  15 l3.bias
+extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int d_v, int h1, int h2,
+                               const float *const *h_weights)
+{
+    GAD_REQUIRE(out && h_weights, "gad_qnet_create: null pointer");
+    GAD_REQUIRE(rows >= 1 && rows <= 16 && cols >= 1 && cols <= 254, "gad_qnet_create: window %dx%d unsupported", rows, cols);
+    GAD_REQUIRE(d_k >= 1 && d_v >= 1 && h1 >= 4 && h1 % 4 == 0 && h2 >= 4 && h2 % 4 == 0,
+                "gad_qnet_create: bad layer sizes (h1 and h2 must be multiples of 4)");
+    for (int i = 0; i < 16; ++i) GAD_REQUIRE(h_weights[i], "gad_qnet_create: weight tensor %d is null", i);
+    gad_qnet *q = new gad_qnet();
+    q->rows = rows;
+    q->cols = cols;
+    q->L = rows * (cols + 1);
+    q->A = (1 << rows) - 1;
+    q->K = q->L * QN_D;
+    q->h1 = h1;
+    q->h2 = h2;
+    const int L = q->L, V = QN_VOCAB;
+    const float *emb = h_weights[0], *pos = h_weights[1], *g1 = h_weights[2], *be1 = h_weights[3];
+    const float *wq = h_weights[4], *wk = h_weights[5], *wv = h_weights[6], *wfc = h_weights[7];
+
+    // fold (fp64): X, M = Wq^T Wk / sqrt(dk), N = Wfc Wv
+    std::vector<double> Xd((size_t)V * L * QN_D), Mq((size_t)QN_D * QN_D), Nf((size_t)QN_D * QN_D);
+    for (int t = 0; t < V; ++t)
+        for (int p = 0; p < L; ++p) {
+            double e[QN_D];
+            for (int c = 0; c < QN_D; ++c) e[c] = (double)(float)(emb[t * QN_D + c] + pos[(size_t)p * QN_D + c]);
+            layer_norm64(e, g1, be1, &Xd[((size_t)t * L + p) * QN_D]);
+        }
+    const double temp = sqrt((double)d_k);
+    for (int a = 0; a < QN_D; ++a)
+        for (int b = 0; b < QN_D; ++b) {
+            double s = 0;
+            for (int d = 0; d < d_k; ++d) s += (double)wq[d * QN_D + a] * (double)wk[d * QN_D + b];
+            Mq[(size_t)a * QN_D + b] = s / temp;
+            double n = 0;
+            for (int d = 0; d < d_v; ++d) n += (double)wfc[(size_t)a * d_v + d] * (double)wv[d * QN_D + b];
+            Nf[(size_t)a * QN_D + b] = n;
+        }
+    const size_t n = (size_t)V * L;
+    std::vector<double> QM(n * QN_D);
+    std::vector<float> Xf(n * QN_D), VFf(n * QN_D), Tf(n * n);
+    for (size_t i = 0; i < n; ++i) {
+        const double *x = &Xd[i * QN_D];
+        for (int b = 0; b < QN_D; ++b) {
+            double s = 0, v = 0;
+            for (int a = 0; a < QN_D; ++a) s += x[a] * Mq[(size_t)a * QN_D + b];
+            for (int a = 0; a < QN_D; ++a) v += Nf[(size_t)b * QN_D + a] * x[a];
+            QM[i * QN_D + b] = s;
+            VFf[i * QN_D + b] = (float)v;
+            Xf[i * QN_D + b] = (float)x[b];
+        }
+    }
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = 0; j < n; ++j) {
+            double s = 0;
+            const double *a = &QM[i * QN_D], *b = &Xd[j * QN_D];
+            for (int c = 0; c < QN_D; ++c) s += a[c] * b[c];
+            Tf[i * n + j] = (float)s;
+        }
+    int rc = GAD_OK;
+    auto up = [&](float **dst, const float *src, size_t cnt) { if (!rc) rc = upload(dst, src, cnt); };
+    up(&q->X, Xf.data(), Xf.size());
+    up(&q->T, Tf.data(), Tf.size());
+    up(&q->VF, VFf.data(), VFf.size());
+    up(&q->ln2_g, h_weights[8], QN_D);
+    up(&q->ln2_b, h_weights[9], QN_D);
+    up(&q->W1, h_weights[10], (size_t)h1 * q->K);
+    up(&q->b1, h_weights[11], h1);
+    up(&q->W2, h_weights[12], (size_t)h2 * h1);
+    up(&q->b2, h_weights[13], h2);
+    up(&q->W3, h_weights[14], (size_t)q->A * h2);
+    up(&q->b3, h_weights[15], q->A);
+    if (!rc) rc = dev_alloc(&q->counts, 2);
+    if (!rc && cudaMallocHost((void **)&q->h_count, 2 * sizeof(int32_t)) != cudaSuccess) {
+        gad_set_error("gad_qnet_create: cudaMallocHost failed");
+        rc = GAD_ECUDA;
+    }
+    if (rc) {
+        delete q;
+        return rc;
+    }
+    *out = q;
+    return GAD_OK;
+}
+
+extern "C" int gad_qnet_destroy(gad_qnet *q)
+{
+    if (!q) return GAD_OK;
+    float *f[] = {q->X, q->T, q->VF, q->ln2_g, q->ln2_b, q->W1, q->b1, q->W2, q->b2, q->W3, q->b3, q->Z, q->H1, q->H2, q->Q};
+    for (float *p : f) cudaFree(p);
+    cudaFree(q->tok); cudaFree(q->act); cudaFree(q->sub); cudaFree(q->heads); cudaFree(q->aligned);
+    cudaFree(q->steps); cudaFree(q->list0); cudaFree(q->list1); cudaFree(q->counts);
+    if (q->h_count) cudaFreeHost(q->h_count);
+    delete q;
+    return GAD_OK;
+}
+
+extern "C" int gad_qnet_dims(const gad_qnet *q, int *L, int *A)
+{
+    GAD_REQUIRE(q && L && A, "gad_qnet_dims: null pointer");
+    *L = q->L;
+    *A = q->A;
+    return GAD_OK;
+}
+
+// Net.forward + argmax for B explicit states (uint8 tokens [B][L], device). d_q [B][A] and d_action [B]
+// are optional device outputs. Asynchronous on `stream`.
+extern "C" int gad_qnet_forward(gad_qnet *q, const uint8_t *d_states, int64_t B, float max_value, float *d_q,
+                                int32_t *d_action, void *stream)
+{
+    GAD_REQUIRE(q && d_states && B >= 0, "gad_qnet_forward: bad argument");
+    cudaStream_t st = gad_stream(stream);
+    for (int64_t b0 = 0; b0 < B; b0 += kMaxBatch) {
+        const long long nb = B - b0 < kMaxBatch ? B - b0 : kMaxBatch;
+        int rc = ensure_states(q, nb);
+        if (rc) return rc;
+        rc = launch_forward(q, d_states + (size_t)b0 * q->L, nullptr, nullptr, nb, max_value,
+                            d_q ? d_q + (size_t)b0 * q->A : nullptr, d_action ? d_action + b0 : nullptr, nullptr,
+                            nullptr, st);
+        if (rc) return rc;
+    }
+    return GAD_OK;
+}
+
+// Same through host buffers (DQN.predict for one state from python). Synchronises.
+extern "C" int gad_qnet_forward_host(gad_qnet *q, const uint8_t *h_states, int64_t B, float max_value, float *h_q,
+                                     int32_t *h_action)
+{
+    GAD_REQUIRE(q && h_states && B >= 0, "gad_qnet_forward_host: bad argument");
+    if (B == 0) return GAD_OK;
+    uint8_t *d_states = nullptr;
+    float *d_q = nullptr;
+    int32_t *d_a = nullptr;
+    int rc = dev_alloc(&d_states, (size_t)B * q->L);
+    if (!rc) rc = dev_alloc(&d_q, (size_t)B * q->A);
+    if (!rc) rc = dev_alloc(&d_a, (size_t)B);
+    if (!rc && cudaMemcpy(d_states, h_states, (size_t)B * q->L, cudaMemcpyHostToDevice) != cudaSuccess) rc = GAD_ECUDA;
+    if (!rc) rc = gad_qnet_forward(q, d_states, B, max_value, d_q, d_a, nullptr);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = GAD_ECUDA;
+    if (!rc && h_q && cudaMemcpy(h_q, d_q, (size_t)B * q->A * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GAD_ECUDA;
+    if (!rc && h_action && cudaMemcpy(h_action, d_a, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GAD_ECUDA;
+    if (rc == GAD_ECUDA) gad_set_error("gad_qnet_forward_host: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_states);
+    cudaFree(d_q);
+    cudaFree(d_a);
+    return rc;
+}
+
+// GA.mutation for M individuals (GA.py:335-373): d_idx[m] is the individual, d_tile[m] = {from_row,
+// from_col} of its worst tile (gad_worst_tiles). Runs the greedy episodes in lock-step chunks, then
+// pads and splices the aligned sub-boards back. The stride must leave room for the growth:
+// max row length + (rows-1)*cols <= stride, otherwise bit 0 of *d_status is set and that board is
+// left unchanged. h_steps_run (optional) receives the number of lock-step forwards. Synchronises.
+extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int R, int stride, const int32_t *d_idx,
+                          const int32_t *d_tile, int64_t M, float max_value, int32_t *d_status,
+                          int64_t *h_forwards, void *stream)
+{
+    GAD_REQUIRE(q && d_boards && d_rowlen && d_tile && d_status, "gad_mutate: null pointer");
+    GAD_REQUIRE(M >= 0 && R >= q->rows && stride >= 16 && stride % 16 == 0, "gad_mutate: bad shape");
+    cudaStream_t st = gad_stream(stream);
+    int64_t forwards = 0;
+    for (int64_t m0 = 0; m0 < M; m0 += kMaxBatch) {
+        const long long nb = M - m0 < kMaxBatch ? M - m0 : kMaxBatch;
+        int rc = ensure_states(q, nb);
+        if (!rc) rc = ensure_episodes(q, nb);
+        if (rc) return rc;
+        const int32_t *idx = d_idx ? d_idx + m0 : nullptr;
+        const int32_t *tile = d_tile + 2 * m0;
+        GAD_CUDA(cudaMemsetAsync(q->counts, 0, 2 * sizeof(int32_t), st));
+        episode_init_kernel<<<(unsigned)nb, 64, 0, st>>>(*q, d_boards, R, stride, idx, tile, nb, q->list0, q->counts);
+        GAD_LAUNCH_CHECK();
+        long long n_max = nb;
+        const int max_steps = q->rows * q->cols;            // every step consumes at least one token
+        int cur = 0;
+        for (int s = 0; s < max_steps && n_max > 0; ++s) {
+            int32_t *list = cur ? q->list1 : q->list0, *next = cur ? q->list0 : q->list1;
+            rc = launch_forward(q, nullptr, list, q->counts + cur, n_max, max_value, nullptr, nullptr, next,
+                                q->counts + (cur ^ 1), st);
+            if (rc) return rc;
+            GAD_CUDA(cudaMemsetAsync(q->counts + cur, 0, sizeof(int32_t), st));   // becomes the "next" counter of step s+1
+            cur ^= 1;
+            ++forwards;
+            if ((s & 3) == 3 || s + 1 == max_steps) {       // poll the active count every 4 steps
+                GAD_CUDA(cudaMemcpyAsync(q->h_count, q->counts + cur, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                GAD_CUDA(cudaStreamSynchronize(st));
+                n_max = q->h_count[0];
+            }
+        }
+        splice_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(*q, d_boards, d_rowlen, R, stride, idx, tile, nb, d_status);
+        GAD_LAUNCH_CHECK();
+    }
+    GAD_CUDA(cudaStreamSynchronize(st));
+    if (h_forwards) *h_forwards = forwards;
+    return GAD_OK;
+}

@@ -1,0 +1,590 @@
+// Ranking, selection, survivor compaction and the hall of fame, all on device.
+// Replaces utils.get_index_of_the_best_fitted_individuals (reference utils.py:316-355),
+// GA._find_pareto_front (GA.py:183-211), GA.selection (GA.py:213-260) and
+// GA.update_hall_of_fame (GA.py:96-136).
+//
+// Every ordering rule of the reference is a stable descending python sort, so ties keep
+// ascending index. Keys are fp64 computed with the same IEEE operations python performs
+// (int/int true division and float subtract/divide/add, no contraction), which makes the
+// device order bit-identical to the reference's. Device-wide sort and scan are CUB primitives
+// (toolkit headers); the kernels that move boards are hand-written.
+#include "gad_common.cuh"
+
+#include <cub/cub.cuh>
+
+namespace {
+
+typedef unsigned long long u64;
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Stats {            // lives at the head of the workspace
+    int sp_min, sp_max;
+    u64 cs_min, cs_max;   // bit patterns of non-negative doubles (order-preserving)
+    int winner;           // argbest of the last hof pass
+    int n_front;          // size of the Pareto front of the last selection
+    int n_keep;
+    unsigned int ticket;  // last-block-done counter
+};
+
+struct Workspace {
+    Stats *stats;
+    u64 *k0, *k1;         // sort keys (double buffer)
+    int *v0, *v1;         // sort values (double buffer)
+    int *ord_a, *ord_b, *ord_c;   // extra orders kept by the MO selection
+    u64 *scan_u64;
+    int *gstart, *flags, *scan;
+    double *part_key;     // per-block argmax partials
+    int *part_idx;
+    void *cub_tmp;
+    size_t cub_bytes;
+};
+
+const int kArgBlocks = 1024;
+
+size_t cub_temp_bytes(long long n)
+{
+    size_t a = 0, b = 0, c = 0, d = 0;
+    cub::DoubleBuffer<u64> keys((u64 *)nullptr, (u64 *)nullptr);
+    cub::DoubleBuffer<int> vals((int *)nullptr, (int *)nullptr);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, a, keys, vals, (int)n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int *)nullptr, (int *)nullptr, (int)n);
+    cub::DeviceScan::InclusiveScan(nullptr, c, (u64 *)nullptr, (u64 *)nullptr, cub::Max(), (int)n);
+    cub::DeviceScan::InclusiveScan(nullptr, d, (int *)nullptr, (int *)nullptr, cub::Max(), (int)n);
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    m = m > d ? m : d;
+    return align256(m + 256);
+}
+
+size_t carve(Workspace &w, void *base, long long n, size_t cub_bytes)
+{
+    char *p = (char *)base;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void *q = p ? p + off : nullptr; off += align256(bytes); return q; };
+    w.stats = (Stats *)take(sizeof(Stats));
+    w.k0 = (u64 *)take(sizeof(u64) * n);
+    w.k1 = (u64 *)take(sizeof(u64) * n);
+    w.v0 = (int *)take(sizeof(int) * n);
+    w.v1 = (int *)take(sizeof(int) * n);
+    w.ord_a = (int *)take(sizeof(int) * n);
+    w.ord_b = (int *)take(sizeof(int) * n);
+    w.ord_c = (int *)take(sizeof(int) * n);
+    w.scan_u64 = (u64 *)take(sizeof(u64) * n);
+    w.gstart = (int *)take(sizeof(int) * n);
+    w.flags = (int *)take(sizeof(int) * n);
+    w.scan = (int *)take(sizeof(int) * n);
+    w.part_key = (double *)take(sizeof(double) * kArgBlocks);
+    w.part_idx = (int *)take(sizeof(int) * kArgBlocks);
+    w.cub_tmp = take(cub_bytes);
+    w.cub_bytes = cub_bytes;
+    return off;
+}
+
+int open_workspace(Workspace &w, void *ws, size_t ws_bytes, long long n, const char *who)
+{
+    GAD_REQUIRE(ws != nullptr, "%s: null workspace", who);
+    GAD_REQUIRE(n < (1ll << 31) - 2, "%s: population too large for 32-bit indices", who);
+    const size_t cb = cub_temp_bytes(n);
+    const size_t need = carve(w, ws, n, cb);
+    GAD_REQUIRE(need <= ws_bytes, "%s: workspace of %zu bytes is too small, need %zu (gad_workspace_bytes)", who,
+                ws_bytes, need);
+    return GAD_OK;
+}
+
+__device__ __forceinline__ u64 sortable(double v)
+{
+    const u64 b = (u64)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// python: exact / num_columns (utils.py:128), 0 when there are no columns
+__device__ __forceinline__ double column_score(int em, int al) { return al > 0 ? __ddiv_rn((double)em, (double)al) : 0.0; }
+
+// ---------------------------------------------------------------------------------------------
+// keys
+// ---------------------------------------------------------------------------------------------
+__global__ void stats_init_kernel(Stats *s)
+{
+    s->sp_min = 0x7fffffff;
+    s->sp_max = (int)0x80000000;
+    s->cs_min = ~0ull;
+    s->cs_max = 0ull;
+}
+
+// element i < P comes from the population, element P (when n == P + 1) from the hall of fame
+__device__ __forceinline__ void load_score(const int *sp, const int *em, const int *al, const int *hof, long long P,
+                                           long long i, int &s, int &e, int &a)
+{
+    if (i < P) {
+        s = sp[i];
+        e = em[i];
+        a = al[i];
+    } else {
+        s = hof[2];
+        e = hof[3];
+        a = hof[4];
+    }
+}
+
+__global__ void stats_kernel(const int *__restrict__ sp, const int *__restrict__ em, const int *__restrict__ al,
+                             const int *__restrict__ hof, long long P, long long n, Stats *st)
+{
+    int lo = 0x7fffffff, hi = (int)0x80000000;
+    u64 clo = ~0ull, chi = 0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int s, e, a;
+        load_score(sp, em, al, hof, P, i, s, e, a);
+        lo = min(lo, s);
+        hi = max(hi, s);
+        const u64 c = (u64)__double_as_longlong(column_score(e, a));
+        clo = c < clo ? c : clo;
+        chi = c > chi ? c : chi;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+        const u64 a = __shfl_xor_sync(0xFFFFFFFFu, clo, o), b = __shfl_xor_sync(0xFFFFFFFFu, chi, o);
+        clo = a < clo ? a : clo;
+        chi = b > chi ? b : chi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&st->sp_min, lo);
+        atomicMax(&st->sp_max, hi);
+        atomicMin(&st->cs_min, clo);
+        atomicMax(&st->cs_max, chi);
+    }
+}
+
+// utils.py:332-351: single metric -> the metric; MO -> (sp-min)/(max-min) + (cs-min)/(max-min), 0.5 when flat
+__global__ void keys_kernel(const int *__restrict__ sp, const int *__restrict__ em, const int *__restrict__ al,
+                            const int *__restrict__ hof, long long P, long long n, int mode, const Stats *st,
+                            double *__restrict__ key)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s, e, a;
+    load_score(sp, em, al, hof, P, i, s, e, a);
+    double k;
+    if (mode == GAD_MODE_SP) {
+        k = (double)s;
+    } else if (mode == GAD_MODE_CS) {
+        k = column_score(e, a);
+    } else {
+        const long long lo = st->sp_min, hi = st->sp_max;
+        const double clo = __longlong_as_double((long long)st->cs_min), chi = __longlong_as_double((long long)st->cs_max);
+        const double nsp = hi > lo ? __ddiv_rn((double)((long long)s - lo), (double)(hi - lo)) : 0.5;
+        const double c = column_score(e, a);
+        const double ncs = chi > clo ? __ddiv_rn(__dsub_rn(c, clo), __dsub_rn(chi, clo)) : 0.5;
+        k = __dadd_rn(nsp, ncs);
+    }
+    key[i] = k;
+}
+
+int compute_keys(const int *sp, const int *em, const int *al, const int *hof, long long P, int mode, double *key,
+                 Workspace &w, cudaStream_t st)
+{
+    const long long n = P + (hof ? 1 : 0);
+    if (n == 0) return GAD_OK;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (mode == GAD_MODE_MO) {
+        stats_init_kernel<<<1, 1, 0, st>>>(w.stats);
+        stats_kernel<<<blocks < 592u ? blocks : 592u, threads, 0, st>>>(sp, em, al, hof, P, n, w.stats);
+    }
+    keys_kernel<<<blocks, threads, 0, st>>>(sp, em, al, hof, P, n, mode, w.stats, key);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable descending order of fp64 keys (ties keep ascending index)
+// ---------------------------------------------------------------------------------------------
+__global__ void sort_prepare_kernel(const double *__restrict__ key, long long n, u64 *__restrict__ k, int *__restrict__ v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    k[i] = sortable(key[i]);
+    v[i] = (int)i;
+}
+
+// sorts (w.k0, w.v0) descending, result copied to `order`
+int sort_desc(Workspace &w, long long n, int *order, cudaStream_t st)
+{
+    cub::DoubleBuffer<u64> keys(w.k0, w.k1);
+    cub::DoubleBuffer<int> vals(w.v0, w.v1);
+    size_t bytes = w.cub_bytes;
+    GAD_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, bytes, keys, vals, (int)n, 0, 64, st));
+    GAD_CUDA(cudaMemcpyAsync(order, vals.Current(), sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+    return GAD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// selection
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_int_kernel(int *p, long long n, int v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void mark_prefix_kernel(const int *__restrict__ order, long long top_n, int *__restrict__ flags)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < top_n) flags[order[t]] = 1;
+}
+
+// keys for the MO sorts: which = 0 -> cs of element i, 1 -> sp of element i, 2 -> sp of element perm[i]
+__global__ void mo_sort_keys_kernel(const int *__restrict__ sp, const int *__restrict__ em, const int *__restrict__ al,
+                                    const int *__restrict__ perm, long long n, int which, u64 *__restrict__ k,
+                                    int *__restrict__ v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int src = which == 2 ? perm[i] : (int)i;
+    k[i] = which == 0 ? sortable(column_score(em[src], al[src])) : sortable((double)sp[src]);
+    v[i] = src;
+}
+
+// Along the (sp desc, cs desc, index asc) order: group heads and the cs sequence for the max-scan.
+__global__ void front_prepare_kernel(const int *__restrict__ order, const int *__restrict__ sp,
+                                     const int *__restrict__ em, const int *__restrict__ al, long long n,
+                                     u64 *__restrict__ cs_seq, int *__restrict__ head_pos)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int i = order[t];
+    cs_seq[t] = (u64)__double_as_longlong(column_score(em[i], al[i]));
+    head_pos[t] = (t == 0 || sp[order[t - 1]] != sp[i]) ? (int)t : 0;
+}
+
+// GA.py:199-209 in sorted order: i is dominated iff a strictly-higher-sp point has cs >= cs_i (prefix max
+// over earlier groups) or a same-sp point has cs > cs_i (the group's first element holds the group max).
+__global__ void front_flags_kernel(const u64 *__restrict__ cs_seq, const u64 *__restrict__ cs_prefmax,
+                                   const int *__restrict__ gstart, long long n, int *__restrict__ front)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int g = gstart[t];
+    const u64 c = cs_seq[t];
+    bool keep = c == cs_seq[g];
+    if (g > 0) keep = keep && c > cs_prefmax[g - 1];
+    front[t] = keep ? 1 : 0;
+}
+
+// GA.py:246-254. front_rank = exclusive scan of `front` along the sorted order.
+__global__ void mo_decide_kernel(const int *__restrict__ order, const int *__restrict__ front,
+                                 const int *__restrict__ front_rank, const int *__restrict__ ord_sp,
+                                 const int *__restrict__ ord_cs, long long n, long long top_n, Stats *st,
+                                 int *__restrict__ flags)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int n_front = front_rank[n - 1] + front[n - 1];
+    if (t == 0) st->n_front = n_front;
+    if (top_n < 0) {                                       // the Pareto front itself (GA._find_pareto_front)
+        if (front[t]) flags[order[t]] = 1;
+    } else if (n_front < top_n) {
+        if (front[t]) flags[order[t]] = 1;
+        if (t < top_n) {
+            flags[ord_sp[t]] = 1;
+            flags[ord_cs[t]] = 1;
+        }
+    } else if (front[t] && front_rank[t] < top_n) {
+        flags[order[t]] = 1;
+    }
+}
+
+__global__ void keep_finish_kernel(const int *__restrict__ flags, const int *__restrict__ scan, long long n,
+                                   uint8_t *__restrict__ keep, int *__restrict__ dst, int *__restrict__ count, Stats *st)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keep[i] = (uint8_t)flags[i];
+    dst[i] = scan[i];
+    if (i == n - 1) {
+        const int c = scan[i] + flags[i];
+        *count = c;
+        st->n_keep = c;
+    }
+}
+
+// One warp per (board,row) unit: survivors move to their compacted slot, 16 bytes per lane per trip.
+__global__ void __launch_bounds__(256)
+compact_kernel(const uint8_t *__restrict__ src, const int *__restrict__ src_rowlen, const int *__restrict__ src_sp,
+               const int *__restrict__ src_em, const int *__restrict__ src_al, const uint8_t *__restrict__ keep,
+               const int *__restrict__ dst_of, long long P, int R, int stride, uint8_t *__restrict__ dst,
+               int *__restrict__ dst_rowlen, int *__restrict__ dst_sp, int *__restrict__ dst_em,
+               int *__restrict__ dst_al)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long units = P * R;
+    for (long long u = warp0; u < units; u += nwarps) {
+        const long long p = u / R;
+        const int r = (int)(u - p * R);
+        if (!keep[p]) continue;
+        const long long q = dst_of[p];
+        int w = 0;
+        for (int i = 0; i < R; ++i) w = max(w, src_rowlen[p * R + i]);
+        const int n16 = min(stride >> 4, (w + 15) >> 4);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + ((size_t)p * R + r) * stride);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + ((size_t)q * R + r) * stride);
+        for (int j = lane; j < n16; j += 32) d4[j] = s4[j];
+        if (lane == 0) {
+            dst_rowlen[q * R + r] = src_rowlen[p * R + r];
+            if (r == 0) {
+                dst_sp[q] = src_sp[p];
+                dst_em[q] = src_em[p];
+                dst_al[q] = src_al[p];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hall of fame
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better(double ka, int ia, double kb, int ib)
+{
+    return ka > kb || (ka == kb && ia < ib);      // first maximum wins (stable descending sort, utils.py:340,351)
+}
+
+__global__ void __launch_bounds__(256)
+argbest_kernel(const double *__restrict__ key, long long n, double *__restrict__ part_key,
+               int *__restrict__ part_idx, Stats *st)
+{
+    __shared__ double sk[8];
+    __shared__ int si[8];
+    __shared__ bool last;
+    double bk = 0.0;
+    int bi = 0x7fffffff;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double k = key[i];
+        if (bi == 0x7fffffff || better(k, (int)i, bk, bi)) {
+            bk = k;
+            bi = (int)i;
+        }
+    }
+    auto warp_reduce = [&]() {
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ok, oi, bk, bi))) {
+                bk = ok;
+                bi = oi;
+            }
+        }
+    };
+    warp_reduce();
+    if ((threadIdx.x & 31) == 0) {
+        sk[threadIdx.x >> 5] = bk;
+        si[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bk = threadIdx.x < 8 ? sk[threadIdx.x] : 0.0;
+        bi = threadIdx.x < 8 ? si[threadIdx.x] : 0x7fffffff;
+        warp_reduce();
+        if (threadIdx.x == 0) {
+            part_key[blockIdx.x] = bk;
+            part_idx[blockIdx.x] = bi;
+            __threadfence();
+            last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    bk = 0.0;
+    bi = 0x7fffffff;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        const double k = part_key[b];
+        const int i = part_idx[b];
+        if (i != 0x7fffffff && (bi == 0x7fffffff || better(k, i, bk, bi))) {
+            bk = k;
+            bi = i;
+        }
+    }
+    warp_reduce();
+    if ((threadIdx.x & 31) == 0) {
+        sk[threadIdx.x >> 5] = bk;
+        si[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bk = threadIdx.x < 8 ? sk[threadIdx.x] : 0.0;
+        bi = threadIdx.x < 8 ? si[threadIdx.x] : 0x7fffffff;
+        warp_reduce();
+        if (threadIdx.x == 0) {
+            st->winner = bi;
+            st->ticket = 0u;
+        }
+    }
+}
+
+// GA.py:110-136: the winner's board and score tuple become the hall of fame. Winner == P is the old
+// hall of fame itself, re-labelled with the fresh index len(scores) (GA.py:127-132).
+__global__ void hof_commit_kernel(const uint8_t *__restrict__ boards, const int *__restrict__ sp,
+                                  const int *__restrict__ em, const int *__restrict__ al, long long P, int R,
+                                  int stride, const Stats *st, uint8_t *__restrict__ hof_board, int *__restrict__ hof)
+{
+    const int win = st->winner;
+    const int r = blockIdx.x;
+    if (win >= P) {
+        if (r == 0 && threadIdx.x == 0) hof[1] = (int)P;
+        return;
+    }
+    const int w = al[win];
+    const int n16 = min(stride >> 4, (w + 15) >> 4);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(boards + ((size_t)win * R + r) * stride);
+    uint4 *d4 = reinterpret_cast<uint4 *>(hof_board + (size_t)r * stride);
+    for (int j = threadIdx.x; j < n16; j += blockDim.x) d4[j] = s4[j];
+    if (r == 0 && threadIdx.x == 0) {
+        hof[0] = 1;
+        hof[1] = win;
+        hof[2] = sp[win];
+        hof[3] = em[win];
+        hof[4] = w;
+    }
+}
+
+inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int gad_workspace_bytes(int64_t P, size_t *bytes)
+{
+    GAD_REQUIRE(bytes && P >= 0, "gad_workspace_bytes: bad argument");
+    Workspace w;
+    const long long n = P + 1;
+    *bytes = carve(w, nullptr, n, cub_temp_bytes(n));
+    return GAD_OK;
+}
+
+extern "C" int gad_rank_keys(const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, int64_t P, int mode,
+                             const int32_t *d_hof, double *d_key, void *d_ws, size_t ws_bytes, void *stream)
+{
+    GAD_REQUIRE(d_sp && d_em && d_al && d_key, "gad_rank_keys: null device pointer");
+    GAD_REQUIRE(mode >= GAD_MODE_SP && mode <= GAD_MODE_MO, "gad_rank_keys: unknown mode %d", mode);
+    Workspace w;
+    int rc = open_workspace(w, d_ws, ws_bytes, P + 1, "gad_rank_keys");
+    if (rc) return rc;
+    return compute_keys(d_sp, d_em, d_al, d_hof, P, mode, d_key, w, gad_stream(stream));
+}
+
+extern "C" int gad_rank_order(const double *d_key, int64_t n, int32_t *d_order, void *d_ws, size_t ws_bytes,
+                              void *stream)
+{
+    GAD_REQUIRE(d_key && d_order && n >= 0, "gad_rank_order: bad argument");
+    if (n == 0) return GAD_OK;
+    Workspace w;
+    int rc = open_workspace(w, d_ws, ws_bytes, n, "gad_rank_order");
+    if (rc) return rc;
+    cudaStream_t st = gad_stream(stream);
+    sort_prepare_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_key, n, w.k0, w.v0);
+    GAD_LAUNCH_CHECK();
+    return sort_desc(w, n, d_order, st);
+}
+
+extern "C" int gad_select(const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, int64_t P, int mode,
+                          int64_t top_n, uint8_t *d_keep, int32_t *d_dst, int32_t *d_count, void *d_ws,
+                          size_t ws_bytes, void *stream)
+{
+    GAD_REQUIRE(d_sp && d_em && d_al && d_keep && d_dst && d_count, "gad_select: null device pointer");
+    GAD_REQUIRE(mode >= GAD_MODE_SP && mode <= GAD_MODE_MO, "gad_select: unknown mode %d", mode);
+    GAD_REQUIRE(P >= 1 && top_n >= -1, "gad_select: need P >= 1 and top_n >= 0 (or -1: Pareto front only)");
+    GAD_REQUIRE(top_n >= 0 || mode == GAD_MODE_MO, "gad_select: the Pareto front needs mode 'mo'");
+    if (top_n > P) top_n = P;
+    Workspace w;
+    int rc = open_workspace(w, d_ws, ws_bytes, P + 1, "gad_select");
+    if (rc) return rc;
+    cudaStream_t st = gad_stream(stream);
+    const unsigned nb = blocks_for(P, 256);
+    fill_int_kernel<<<nb, 256, 0, st>>>(w.flags, P, 0);
+    if (mode != GAD_MODE_MO) {
+        // GA.py:234-238: stable descending sort on the single metric, first top_n positions
+        mo_sort_keys_kernel<<<nb, 256, 0, st>>>(d_sp, d_em, d_al, nullptr, P, mode == GAD_MODE_SP ? 1 : 0, w.k0, w.v0);
+        GAD_LAUNCH_CHECK();
+        if ((rc = sort_desc(w, P, w.ord_a, st))) return rc;
+        if (top_n > 0) mark_prefix_kernel<<<blocks_for(top_n, 256), 256, 0, st>>>(w.ord_a, top_n, w.flags);
+    } else {
+        // order by cs (also "top_n by CS"), by sp ("top_n by SP"), and by (sp, cs) for the front
+        mo_sort_keys_kernel<<<nb, 256, 0, st>>>(d_sp, d_em, d_al, nullptr, P, 0, w.k0, w.v0);
+        GAD_LAUNCH_CHECK();
+        if ((rc = sort_desc(w, P, w.ord_b, st))) return rc;                       // ord_b = by cs
+        mo_sort_keys_kernel<<<nb, 256, 0, st>>>(d_sp, d_em, d_al, nullptr, P, 1, w.k0, w.v0);
+        if ((rc = sort_desc(w, P, w.ord_a, st))) return rc;                       // ord_a = by sp
+        mo_sort_keys_kernel<<<nb, 256, 0, st>>>(d_sp, d_em, d_al, w.ord_b, P, 2, w.k0, w.v0);
+        if ((rc = sort_desc(w, P, w.ord_c, st))) return rc;                       // ord_c = by (sp, cs)
+        const int *order = w.ord_c;
+        front_prepare_kernel<<<nb, 256, 0, st>>>(order, d_sp, d_em, d_al, P, w.k0, w.v1);   // k0 = cs seq, v1 = head pos
+        GAD_LAUNCH_CHECK();
+        size_t bytes = w.cub_bytes;
+        GAD_CUDA(cub::DeviceScan::InclusiveScan(w.cub_tmp, bytes, w.k0, w.scan_u64, cub::Max(), (int)P, st));
+        bytes = w.cub_bytes;
+        GAD_CUDA(cub::DeviceScan::InclusiveScan(w.cub_tmp, bytes, w.v1, w.gstart, cub::Max(), (int)P, st));
+        front_flags_kernel<<<nb, 256, 0, st>>>(w.k0, w.scan_u64, w.gstart, P, w.v1);        // v1 = front flag
+        bytes = w.cub_bytes;
+        GAD_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.v1, w.scan, (int)P, st));
+        mo_decide_kernel<<<nb, 256, 0, st>>>(order, w.v1, w.scan, w.ord_a, w.ord_b, P, top_n, w.stats, w.flags);
+    }
+    GAD_LAUNCH_CHECK();
+    size_t bytes = w.cub_bytes;
+    GAD_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.flags, w.scan, (int)P, st));
+    keep_finish_kernel<<<nb, 256, 0, st>>>(w.flags, w.scan, P, d_keep, d_dst, d_count, w.stats);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+extern "C" int gad_compact(const uint8_t *d_src_boards, const int32_t *d_src_rowlen, const int32_t *d_src_sp,
+                           const int32_t *d_src_em, const int32_t *d_src_al, const uint8_t *d_keep,
+                           const int32_t *d_dst, int64_t P, int R, int stride, uint8_t *d_dst_boards,
+                           int32_t *d_dst_rowlen, int32_t *d_dst_sp, int32_t *d_dst_em, int32_t *d_dst_al,
+                           void *stream)
+{
+    GAD_REQUIRE(d_src_boards && d_src_rowlen && d_src_sp && d_src_em && d_src_al && d_keep && d_dst && d_dst_boards &&
+                    d_dst_rowlen && d_dst_sp && d_dst_em && d_dst_al,
+                "gad_compact: null device pointer");
+    GAD_REQUIRE(P >= 0 && R >= 1 && stride >= 16 && stride % 16 == 0, "gad_compact: bad shape");
+    GAD_REQUIRE(d_src_boards != d_dst_boards, "gad_compact: source and destination must be different buffers");
+    if (P == 0) return GAD_OK;
+    const long long units = (long long)P * R;
+    long long blocks = (units + 7) / 8;
+    const long long cap = (long long)GAD_NUM_SMS * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    compact_kernel<<<(unsigned)blocks, 256, 0, gad_stream(stream)>>>(d_src_boards, d_src_rowlen, d_src_sp, d_src_em,
+                                                                      d_src_al, d_keep, d_dst, P, R, stride,
+                                                                      d_dst_boards, d_dst_rowlen, d_dst_sp, d_dst_em,
+                                                                      d_dst_al);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+extern "C" int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al,
+                              int64_t P, int R, int stride, int mode, uint8_t *d_hof_board, int32_t *d_hof,
+                              int hof_valid, void *d_ws, size_t ws_bytes, void *stream)
+{
+    GAD_REQUIRE(d_boards && d_sp && d_em && d_al && d_hof_board && d_hof, "gad_hof_update: null device pointer");
+    GAD_REQUIRE(mode >= GAD_MODE_SP && mode <= GAD_MODE_MO, "gad_hof_update: unknown mode %d", mode);
+    GAD_REQUIRE(P >= 1 && R >= 1 && stride >= 16 && stride % 16 == 0, "gad_hof_update: bad shape");
+    Workspace w;
+    int rc = open_workspace(w, d_ws, ws_bytes, P + 1, "gad_hof_update");
+    if (rc) return rc;
+    cudaStream_t st = gad_stream(stream);
+    double *key = reinterpret_cast<double *>(w.k0);
+    const long long n = P + (hof_valid ? 1 : 0);
+    if ((rc = compute_keys(d_sp, d_em, d_al, hof_valid ? d_hof : nullptr, P, mode, key, w, st))) return rc;
+    GAD_CUDA(cudaMemsetAsync(&w.stats->ticket, 0, sizeof(unsigned), st));
+    unsigned blocks = blocks_for(n, 256 * 4);
+    if (blocks > (unsigned)kArgBlocks) blocks = kArgBlocks;
+    if (blocks < 1) blocks = 1;
+    argbest_kernel<<<blocks, 256, 0, st>>>(key, n, w.part_key, w.part_idx, w.stats);
+    hof_commit_kernel<<<R, 128, 0, st>>>(d_boards, d_sp, d_em, d_al, P, R, stride, w.stats, d_hof_board, d_hof);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}

@@ -1,11 +1,14 @@
-"""Device-resident population: uint8 boards[P][R][stride] + int32 rowlen[P][R] in HBM.
+"""Device-resident population and the GA phases on it.
 
-Replaces the reference's ``list[P] of list[R] of list[W] of int`` (GA.py:54-56). PyTorch owns
-the allocations and the stream; all arithmetic is done by libgadpamsa kernels (``_native``).
-Layout invariant (see include/gadpamsa.h): with w = max_r rowlen[p][r], the cells
-[rowlen[p][r], roundup4(w)) of every row hold the gap code 5.
+Replaces the reference's ``list[P] of list[R] of list[W] of int`` (GA.py:54-56) by
+uint8 ``boards[P][R][stride]`` + int32 ``rowlen[P][R]`` in HBM (two buffers: selection compacts the
+survivors from one into the other). PyTorch owns the allocations and the stream; all arithmetic is
+done by libgadpamsa kernels (``_native``). Layout invariant (include/gadpamsa.h): with
+w = max_r rowlen[p][r], the cells [rowlen[p][r], roundup4(w)) of every row hold the gap code 5.
 """
 from __future__ import annotations
+
+import ctypes
 
 import numpy as np
 import torch
@@ -13,6 +16,7 @@ import torch
 import _native as nat
 
 GAP = 5
+MODE_ID = nat.MODE_ID
 
 
 def round_up(x: int, m: int) -> int:
@@ -20,8 +24,8 @@ def round_up(x: int, m: int) -> int:
 
 
 def pack_boards(population, stride=None, extra_capacity=0):
-    """list-of-boards -> pinned-able numpy (boards uint8 [P,R,stride], rowlen int32 [P,R]) with the
-    layout invariant established (everything beyond a row's own cells is the gap code)."""
+    """list-of-boards -> numpy (boards uint8 [P,R,stride], rowlen int32 [P,R]) with the layout
+    invariant established (everything beyond a row's own cells is the gap code)."""
     P = len(population)
     R = len(population[0]) if P else 1
     width = max((len(row) for b in population for row in b), default=0)
@@ -46,56 +50,247 @@ def unpack_boards(boards: np.ndarray, rowlen: np.ndarray):
             for p in range(boards.shape[0])]
 
 
-class DevicePopulation:
-    """P boards of R rows resident on one GPU."""
+class _Buffer:
+    def __init__(self, cap, R, stride, dev):
+        self.boards = torch.full((cap, R, stride), GAP, dtype=torch.uint8, device=dev)
+        self.rowlen = torch.zeros((cap, R), dtype=torch.int32, device=dev)
+        self.sp = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.em = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.al = torch.zeros(cap, dtype=torch.int32, device=dev)
 
-    def __init__(self, boards: torch.Tensor, rowlen: torch.Tensor):
+
+class DevicePopulation:
+    """Up to ``capacity`` boards of R rows resident on one GPU, plus the GA state that goes with them
+    (scores, hall of fame, ranking workspace)."""
+
+    def __init__(self, boards: torch.Tensor, rowlen: torch.Tensor, capacity=None):
         assert boards.is_cuda and boards.dtype == torch.uint8 and boards.dim() == 3
         assert rowlen.dtype == torch.int32 and rowlen.shape == boards.shape[:2]
         assert boards.is_contiguous() and rowlen.is_contiguous()
-        self.boards = boards
-        self.rowlen = rowlen
-        P = boards.shape[0]
-        dev = boards.device
-        self.sp = torch.zeros(P, dtype=torch.int32, device=dev)
-        self.em = torch.zeros(P, dtype=torch.int32, device=dev)
-        self.al = torch.zeros(P, dtype=torch.int32, device=dev)
+        assert boards.shape[2] % 16 == 0
+        self.device = boards.device
+        self.n = boards.shape[0]
+        self.capacity = max(capacity or 0, self.n, 1)
+        self.R = boards.shape[1]
+        self.stride = boards.shape[2]
+        if self.capacity == self.n:
+            self.cur = _Buffer.__new__(_Buffer)
+            self.cur.boards, self.cur.rowlen = boards, rowlen
+            for name in ("sp", "em", "al"):
+                setattr(self.cur, name, torch.zeros(self.capacity, dtype=torch.int32, device=self.device))
+        else:
+            self.cur = _Buffer(self.capacity, self.R, self.stride, self.device)
+            self.cur.boards[:self.n].copy_(boards)
+            self.cur.rowlen[:self.n].copy_(rowlen)
+        self.alt = None                          # second buffer, allocated by the first selection
+        dev = self.device
         self.max_al = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hof_board = torch.full((self.R, self.stride), GAP, dtype=torch.uint8, device=dev)
+        self.hof = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.hof_valid = False
+        self._ws = None
+        self._keys = None
+        self._order = None
+        self._keep = None
+        self._dst = None
+        self._count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.evals = 0                           # boards scored so far (reference-equivalent accounting)
+        self.forwards = 0                        # lock-step Q-net forwards so far
 
     # ------------------------------------------------------------------ construction / readback
     @classmethod
-    def from_lists(cls, population, device="cuda", stride=None, extra_capacity=0):
+    def from_lists(cls, population, device="cuda", stride=None, extra_capacity=0, capacity=None):
         nat.require_device()
         boards, rowlen = pack_boards(population, stride, extra_capacity)
-        return cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device))
+        return cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity)
 
     @classmethod
-    def from_numpy(cls, boards: np.ndarray, rowlen: np.ndarray, device="cuda"):
+    def from_numpy(cls, boards: np.ndarray, rowlen: np.ndarray, device="cuda", capacity=None):
         nat.require_device()
-        return cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device))
+        return cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity)
+
+    def to_numpy(self):
+        return self.cur.boards[:self.n].cpu().numpy(), self.cur.rowlen[:self.n].cpu().numpy()
 
     def to_lists(self):
-        return unpack_boards(self.boards.cpu().numpy(), self.rowlen.cpu().numpy())
+        return unpack_boards(*self.to_numpy())
 
+    # legacy names used by the first tests / bench
     @property
     def P(self) -> int:
-        return self.boards.shape[0]
+        return self.n
 
     @property
-    def R(self) -> int:
-        return self.boards.shape[1]
+    def boards(self):
+        return self.cur.boards[:self.n]
 
     @property
-    def stride(self) -> int:
-        return self.boards.shape[2]
+    def rowlen(self):
+        return self.cur.rowlen[:self.n]
 
-    # ------------------------------------------------------------------ a4-a7
+    @property
+    def sp(self):
+        return self.cur.sp[:self.n]
+
+    @property
+    def em(self):
+        return self.cur.em[:self.n]
+
+    @property
+    def al(self):
+        return self.cur.al[:self.n]
+
+    def scores_numpy(self):
+        s = torch.stack((self.cur.sp[:self.n], self.cur.em[:self.n], self.cur.al[:self.n])).cpu().numpy()
+        return s[0], s[1], s[2]
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return nat.current_stream_ptr()
+
+    def _workspace(self):
+        if self._ws is None:
+            nbytes = ctypes.c_size_t(0)
+            nat.call("gad_workspace_bytes", self.capacity, ctypes.byref(nbytes))
+            dev = self.device
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            self._keys = torch.empty(self.capacity + 1, dtype=torch.float64, device=dev)
+            self._order = torch.empty(self.capacity + 1, dtype=torch.int32, device=dev)
+            self._keep = torch.empty(self.capacity, dtype=torch.uint8, device=dev)
+            self._dst = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+        return self._ws
+
+    def ensure_stride(self, need: int):
+        """Re-lay the population out with a wider row stride (rows grow under mutation)."""
+        need = round_up(need, 16)
+        if need <= self.stride:
+            return
+        for name in ("cur", "alt"):
+            buf = getattr(self, name)
+            if buf is None:
+                continue
+            wide = torch.full((buf.boards.shape[0], self.R, need), GAP, dtype=torch.uint8, device=self.device)
+            wide[:, :, :self.stride].copy_(buf.boards)
+            buf.boards = wide
+        hof = torch.full((self.R, need), GAP, dtype=torch.uint8, device=self.device)
+        hof[:, :self.stride].copy_(self.hof_board)
+        self.hof_board = hof
+        self.stride = need
+
+    def ensure_capacity(self, cap: int):
+        if cap <= self.capacity:
+            return
+        for name in ("cur", "alt"):
+            buf = getattr(self, name)
+            if buf is None:
+                continue
+            big = _Buffer(cap, self.R, self.stride, self.device)
+            for f in ("boards", "rowlen", "sp", "em", "al"):
+                getattr(big, f)[:self.capacity].copy_(getattr(buf, f))
+            setattr(self, name, big)
+        self.capacity = cap
+        self._ws = None
+
+    # ------------------------------------------------------------------ a4-a7 + a8
     def fitness(self, match: int, mismatch: int, gap: int):
-        """One fused pad+clean+SP+EM pass (GA.py:156-178). Asynchronous on the current stream;
-        results land in self.sp / self.em / self.al (int32 device tensors)."""
+        """One fused pad+clean+SP+EM pass over the live boards (GA.py:156-178). Asynchronous on the
+        current stream; results land in self.sp / self.em / self.al (int32 device tensors)."""
         nat.require_device()
         self.max_al.zero_()
-        nat.call("gad_fitness", nat.ptr(self.boards), nat.ptr(self.rowlen), self.P, self.R, self.stride,
-                 int(match), int(mismatch), int(gap), nat.ptr(self.sp), nat.ptr(self.em), nat.ptr(self.al),
-                 nat.ptr(self.max_al), nat.current_stream_ptr())
+        b = self.cur
+        nat.call("gad_fitness", nat.ptr(b.boards), nat.ptr(b.rowlen), self.n, self.R, self.stride,
+                 int(match), int(mismatch), int(gap), nat.ptr(b.sp), nat.ptr(b.em), nat.ptr(b.al),
+                 nat.ptr(self.max_al), self._stream())
+        self.evals += self.n
         return self.sp, self.em, self.al
+
+    def hof_update(self, mode: str):
+        """GA.update_hall_of_fame (GA.py:110-136) on device."""
+        ws = self._workspace()
+        b = self.cur
+        nat.call("gad_hof_update", nat.ptr(b.boards), nat.ptr(b.sp), nat.ptr(b.em), nat.ptr(b.al), self.n, self.R,
+                 self.stride, MODE_ID[mode], nat.ptr(self.hof_board), nat.ptr(self.hof), int(self.hof_valid),
+                 nat.ptr(ws), ws.numel(), self._stream())
+        self.hof_valid = True
+
+    def hof_numpy(self):
+        """(board uint8 [R, width], (index, sp, em, al)) of the hall of fame."""
+        rec = self.hof.cpu().numpy()
+        width = int(rec[4])
+        return self.hof_board[:, :width].cpu().numpy(), (int(rec[1]), int(rec[2]), int(rec[3]), width)
+
+    # ------------------------------------------------------------------ a9
+    def rank_order(self, mode: str, n: int):
+        """Device tensor with utils.get_index_of_the_best_fitted_individuals(scores, n)."""
+        ws = self._workspace()
+        b = self.cur
+        st = self._stream()
+        nat.call("gad_rank_keys", nat.ptr(b.sp), nat.ptr(b.em), nat.ptr(b.al), self.n, MODE_ID[mode], None,
+                 nat.ptr(self._keys), nat.ptr(ws), ws.numel(), st)
+        nat.call("gad_rank_order", nat.ptr(self._keys), self.n, nat.ptr(self._order), nat.ptr(ws), ws.numel(), st)
+        return self._order[:min(n, self.n)]
+
+    # ------------------------------------------------------------------ a10 / a11
+    def select_flags(self, mode: str, top_n: int):
+        """Survivor flags of GA.selection (top_n = -1: the Pareto front only). Returns (keep, count)."""
+        ws = self._workspace()
+        b = self.cur
+        nat.call("gad_select", nat.ptr(b.sp), nat.ptr(b.em), nat.ptr(b.al), self.n, MODE_ID[mode], int(top_n),
+                 nat.ptr(self._keep), nat.ptr(self._dst), nat.ptr(self._count), nat.ptr(ws), ws.numel(),
+                 self._stream())
+        return self._keep[:self.n], self._count
+
+    def select(self, mode: str, top_n: int) -> int:
+        """GA.py:232-259: keep the survivors, in original order. Returns their number (one 4-byte
+        device->host read: the crossover plan needs it on the host)."""
+        self.select_flags(mode, top_n)
+        if self.alt is None or self.alt.boards.shape != self.cur.boards.shape:
+            self.alt = _Buffer(self.capacity, self.R, self.stride, self.device)
+        s, d = self.cur, self.alt
+        nat.call("gad_compact", nat.ptr(s.boards), nat.ptr(s.rowlen), nat.ptr(s.sp), nat.ptr(s.em), nat.ptr(s.al),
+                 nat.ptr(self._keep), nat.ptr(self._dst), self.n, self.R, self.stride, nat.ptr(d.boards),
+                 nat.ptr(d.rowlen), nat.ptr(d.sp), nat.ptr(d.em), nat.ptr(d.al), self._stream())
+        self.cur, self.alt = d, s
+        self.n = int(self._count.item())
+        return self.n
+
+    # ------------------------------------------------------------------ a12 / a13
+    def crossover(self, plan: np.ndarray, kind: int = 0):
+        """Append len(plan) children built from (parent1, parent2, cut) triples (GA.py:296)."""
+        n_children = int(plan.shape[0])
+        if n_children == 0:
+            return
+        assert plan.dtype == np.int32 and plan.shape[1] == 3
+        self.ensure_capacity(self.n + n_children)
+        d_plan = torch.from_numpy(plan).to(self.device, non_blocking=False)
+        b = self.cur
+        nat.call("gad_crossover", nat.ptr(b.boards), nat.ptr(b.rowlen), self.n, nat.ptr(d_plan), n_children, self.R,
+                 self.stride, int(kind), self._stream())
+        self.n += n_children
+
+    # ------------------------------------------------------------------ a14-a18
+    def worst_tiles(self, idx, rw, cw, mode, match, mismatch, gap):
+        """Device int32 [M, 2] with (from_row, from_col) of every listed individual's worst tile."""
+        M = self.n if idx is None else int(idx.numel())
+        tile = torch.empty((M, 2), dtype=torch.int32, device=self.device)
+        b = self.cur
+        nat.call("gad_worst_tiles", nat.ptr(b.boards), nat.ptr(b.rowlen), self.R, self.stride, nat.ptr(idx), M,
+                 int(rw), int(cw), MODE_ID[mode], int(match), int(mismatch), int(gap), nat.ptr(tile), self._stream())
+        return tile
+
+    def mutate(self, qnet, idx, tile, max_value: float):
+        """GA.py:335-373 for the listed individuals with their tiles; boards grow in place."""
+        M = int(tile.shape[0])
+        if M == 0:
+            return
+        width = int(self.cur.rowlen[:self.n].max().item())
+        self.ensure_stride(width + (qnet.rows - 1) * qnet.cols)
+        self._status.zero_()
+        fw = ctypes.c_int64(0)
+        b = self.cur
+        nat.call("gad_mutate", qnet.handle, nat.ptr(b.boards), nat.ptr(b.rowlen), self.R, self.stride, nat.ptr(idx),
+                 nat.ptr(tile), M, float(max_value), nat.ptr(self._status), ctypes.byref(fw), self._stream())
+        self.forwards += fw.value
+        if int(self._status.item()) & 1:
+            raise nat.GadCapacityError("a mutated row outgrew the board stride")

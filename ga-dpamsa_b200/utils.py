@@ -100,3 +100,167 @@ def clean_unnecessary_gaps(aligned_sequence):
 def get_nucleotides_seqs(chromosome):
     """int codes -> strings (reference utils.py:464-467); pure formatting, stays on the host."""
     return ["".join(_LETTERS[v - 1] for v in sequence) for sequence in chromosome]
+
+
+def count_exact_columns(chromosome, from_row, to_row, from_column, to_column):
+    """Number of exact-match columns of a window (numerator of utils.py:128), device-counted."""
+    if to_column <= from_column:
+        return 0
+    if to_row <= from_row:
+        return to_column - from_column
+    return int(_window_score(chromosome, from_row, to_row, from_column, to_column)[1])
+
+
+# ----------------------------------------------------------------------------------------------
+# a15: tiling and the worst-fitted sub-board (reference utils.py:131-313)
+# ----------------------------------------------------------------------------------------------
+def is_overlap(range1, range2):
+    """reference utils.py:153-162 (half-open rectangles)."""
+    from_row1, to_row1, from_column1, to_column1 = range1
+    from_row2, to_row2, from_column2, to_column2 = range2
+    return (from_row1 < to_row2 and to_row1 > from_row2) and (from_column1 < to_column2 and to_column1 > from_column2)
+
+
+def check_overlap(new_range, used_ranges):
+    """reference utils.py:191-195"""
+    return any(is_overlap(new_range, r) for r in used_ranges)
+
+
+def get_all_different_sub_range(individual, m_prime=None, n_prime=None):
+    """The non-overlapping full tiles the reference's scan accepts (utils.py:230-252): exactly the
+    lattice of (m_prime, n_prime) tiles that fit, row-major. Defaults are read from config."""
+    m_prime = config.AGENT_WINDOW_ROW if m_prime is None else m_prime
+    n_prime = config.AGENT_WINDOW_COLUMN if n_prime is None else n_prime
+    m = len(individual)
+    n = min(len(genes) for genes in individual)
+    return [(i, i + m_prime, j, j + n_prime)
+            for i in range(0, m - m_prime + 1, m_prime)
+            for j in range(0, n - n_prime + 1, n_prime)]
+
+
+def calculate_worst_fitted_sub_board(individual, mode):
+    """(score, (from_row, to_row, from_column, to_column)) of the lowest-scoring tile (reference
+    utils.py:276-313). The tile is chosen by gad_worst_tiles on the device; the returned score is the
+    reference's first tuple element: the tile's SP ('sp' and 'cs' modes) or its normalised SP ('mo')."""
+    import torch
+    from population import DevicePopulation
+    rw, cw = int(config.AGENT_WINDOW_ROW), int(config.AGENT_WINDOW_COLUMN)
+    tiles = get_all_different_sub_range(individual, rw, cw)
+    if not tiles:
+        raise ValueError("min() arg is an empty sequence")
+    dev = DevicePopulation.from_lists([individual], device=config.DEVICE)
+    t = dev.worst_tiles(None, rw, cw, mode, int(config.MATCH_REWARD), int(config.MISMATCH_PENALTY),
+                        int(config.GAP_PENALTY)).cpu().numpy()[0]
+    torch.cuda.synchronize()
+    fr, fc = int(t[0]), int(t[1])
+    worst = (fr, fr + rw, fc, fc + cw)
+    sp = get_sum_of_pairs(individual, *worst)
+    if mode in ('sp', 'cs'):
+        return sp, worst
+    sps = [get_sum_of_pairs(individual, *tile) for tile in tiles]
+    lo, hi = min(sps), max(sps)
+    return ((sp - lo) / (hi - lo) if hi > lo else 0.5), worst
+
+
+# ----------------------------------------------------------------------------------------------
+# a9: ranking (reference utils.py:332-355)
+# ----------------------------------------------------------------------------------------------
+def get_index_of_the_best_fitted_individuals(population_scores, num_individuals):
+    """Indices of the best individuals: stable descending sort on the score ('sp'/'cs' tuples) or on
+    the sum of the min/max-normalised SP and CS ('mo' tuples). The keys are formed on the host with the
+    reference's own float expressions; the stable sort runs on the device (gad_rank_order)."""
+    import torch
+    n = len(population_scores)
+    if n == 0:
+        return []
+    nat.require_device()
+    if len(population_scores[0]) == 2:
+        keys = np.array([float(t[1]) for t in population_scores], dtype=np.float64)
+    else:
+        sps = [t[1] for t in population_scores]
+        css = [t[2] for t in population_scores]
+        lo_s, hi_s, lo_c, hi_c = min(sps), max(sps), min(css), max(css)
+        keys = np.array([((s - lo_s) / (hi_s - lo_s) if hi_s > lo_s else 0.5) +
+                         ((c - lo_c) / (hi_c - lo_c) if hi_c > lo_c else 0.5)
+                         for s, c in zip(sps, css)], dtype=np.float64)
+    dev = torch.device(config.DEVICE)
+    nbytes = ctypes.c_size_t(0)
+    nat.call("gad_workspace_bytes", n, ctypes.byref(nbytes))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    d_keys = torch.from_numpy(keys).to(dev)
+    d_order = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.call("gad_rank_order", d_keys.data_ptr(), n, d_order.data_ptr(), ws.data_ptr(), ws.numel(),
+                 nat.current_stream_ptr())
+    order = d_order.cpu().numpy()
+    return [population_scores[i][0] for i in order[:num_individuals]]
+
+
+# ----------------------------------------------------------------------------------------------
+# callers' side of the path: metrics, FASTA parsing, report/CSV plumbing (reference utils.py:475-807).
+# Host-side formatting only; the scores themselves come from the device functions above.
+# ----------------------------------------------------------------------------------------------
+def calculate_metrics(env):
+    """reference utils.py:500-513"""
+    alignment_length = len(env.aligned[0])
+    num_sequences = len(env.aligned)
+    sp_score = env.calc_score()
+    exact_matches = env.calc_exact_matched()
+    column_score = exact_matches / alignment_length
+    return {"AL": alignment_length, "QTY": num_sequences, "SP": sp_score, "EM": exact_matches, "CS": column_score}
+
+
+def parse_fasta_to_sequences(fasta_content):
+    """reference utils.py:543-560"""
+    sequences, current = [], []
+    for line in fasta_content.splitlines():
+        line = line.strip()
+        if line.startswith(">"):
+            if current:
+                sequences.append(''.join(current))
+                current = []
+        else:
+            current.append(line)
+    if current:
+        sequences.append(''.join(current))
+    return sequences
+
+
+def save_inference_csv(csv_data, tool_name, dataset_name):
+    """reference utils.py:733-748"""
+    import os
+    import pandas as pd
+    tool_csv_dir = os.path.join(config.CSV_PATH, tool_name)
+    os.makedirs(tool_csv_dir, exist_ok=True)
+    csv_file_path = os.path.join(tool_csv_dir, f"{dataset_name}_{tool_name}_results.csv")
+    if isinstance(csv_data, list):
+        columns = ["File Name", "Alignment Length (AL)", "Number of Sequences (QTY)", "Sum of Pairs (SP)",
+                   "Exact Matches (EM)", "Column Score (CS)"]
+        df = pd.DataFrame(csv_data, columns=columns)
+    else:
+        df = pd.read_csv(csv_data)
+    df.to_csv(csv_file_path, index=False)
+    return csv_file_path
+
+
+def run_ga_dpamsa_inference(mode, dataset, dataset_name, model_path):
+    """reference utils.py:773-780"""
+    import os
+    from mainGA import inference as ga_inference
+    ga_inference(mode=mode, dataset=dataset, model_path=model_path)
+    mode_tag = {"sp": "Max_SP", "cs": "Max_CS", "mo": "MO"}[mode]
+    return os.path.join(config.GA_DPAMSA_INF_CSV_PATH, f"{dataset_name}_{mode_tag}_GA_DPAMSA_results.csv")
+
+
+def _out_of_scope(name, where):
+    def stub(*_args, **_kwargs):
+        raise NotImplementedError("%s (reference %s) is outside the generation-loop scope of this build "
+                                  "(SURVEY.md section 2)" % (name, where))
+    stub.__name__ = name
+    return stub
+
+
+run_dpamsa_inference = _out_of_scope("run_dpamsa_inference", "utils.py:783-807")
+run_tool_and_generate_report = _out_of_scope("run_tool_and_generate_report", "utils.py:610-697")
+display_menu = _out_of_scope("display_menu", "utils.py:563-607")
+plot_metrics = _out_of_scope("plot_metrics", "utils.py:813-975")

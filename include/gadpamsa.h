@@ -86,6 +86,88 @@ int gad_window_score_host(const uint8_t *h_board, int R, int stride,
                           int from_row, int to_row, int from_col, int to_col,
                           int match, int mismatch, int gap, int64_t *sp, int32_t *em);
 
+/* ---- a9-a11, a8: ranking, selection, survivor compaction, hall of fame ----
+ * All take a caller-provided device workspace of gad_workspace_bytes(P) bytes (valid for every
+ * population size <= P). Score inputs are the int32 sp/em/al arrays gad_fitness writes. */
+int gad_workspace_bytes(int64_t P, size_t *bytes);
+
+/* The fp64 sort key of utils.get_index_of_the_best_fitted_individuals (utils.py:332-351):
+ * 'sp' -> sp, 'cs' -> em/al, 'mo' -> (sp-min)/(max-min) + (cs-min)/(max-min) (0.5 when flat).
+ * When d_hof (the int32[8] hall-of-fame record, see gad_hof_update) is not NULL its score is
+ * appended as element P, exactly like GA.py:127-132 - d_key then holds P+1 doubles. */
+int gad_rank_keys(const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, int64_t P, int mode,
+                  const int32_t *d_hof, double *d_key, void *d_ws, size_t ws_bytes, void *stream);
+
+/* Stable descending order of n keys (ties keep ascending index) = python sorted(..., reverse=True):
+ * d_order[:k] is the list utils.get_index_of_the_best_fitted_individuals(scores, k) returns. */
+int gad_rank_order(const double *d_key, int64_t n, int32_t *d_order, void *d_ws, size_t ws_bytes, void *stream);
+
+/* GA.selection's survivor set (GA.py:232-256; Pareto front GA.py:195-211 in O(P log P)):
+ * d_keep[p] = 1 for survivors, d_dst[p] = their slot after compaction in original order
+ * (GA.py:259), *d_count = number of survivors (may exceed top_n in 'mo' mode, like the reference). */
+int gad_select(const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, int64_t P, int mode, int64_t top_n,
+               uint8_t *d_keep, int32_t *d_dst, int32_t *d_count, void *d_ws, size_t ws_bytes, void *stream);
+
+/* Move the survivors (boards, row lengths, scores) to their slots in a second population buffer. */
+int gad_compact(const uint8_t *d_src_boards, const int32_t *d_src_rowlen, const int32_t *d_src_sp,
+                const int32_t *d_src_em, const int32_t *d_src_al, const uint8_t *d_keep, const int32_t *d_dst,
+                int64_t P, int R, int stride, uint8_t *d_dst_boards, int32_t *d_dst_rowlen, int32_t *d_dst_sp,
+                int32_t *d_dst_em, int32_t *d_dst_al, void *stream);
+
+/* GA.update_hall_of_fame (GA.py:110-136) without the population deep copy. d_hof is int32[8]:
+ * {valid, index, sp, em, al, 0, 0, 0}; d_hof_board is uint8[R][stride]. hof_valid = 0 on the first
+ * call (GA.py:110-115). On ties a population member replaces the hall of fame (lowest index). */
+int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al,
+                   int64_t P, int R, int stride, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
+                   void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- a12/a13: crossover --------------------------------------------------
+ * Children n_parents + c (c < n_children) of the same buffer are built from d_plan[c] =
+ * {parent1, parent2, cut}. kind 0 = horizontal (GA.py:296: rows [0,cut) of parent1, the rest of
+ * parent2); kind 1 = vertical (extension, no reference code: every row is parent1[:cut] + parent2[cut:]). */
+int gad_crossover(uint8_t *d_boards, int32_t *d_rowlen, int64_t n_parents, const int32_t *d_plan,
+                  int64_t n_children, int R, int stride, int kind, void *stream);
+
+/* CPython-compatible MT19937 replay (random.getstate()[1] = 624 words + position, in/out):
+ * the (parent1, parent2, cut) triples of GA.py:281-293 for n_children children. h_widths (one
+ * per parent) selects the vertical cut rule randint(1, min(w1,w2)-1); NULL = horizontal. */
+int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
+                               const int32_t *h_widths, int32_t *h_plan);
+
+/* GA.generate_population (GA.py:71-94) with the same replay: n_clone copies, then h_ngaps[r]
+ * gaps per row inserted one at a time at randint(0, len-1). Host buffers in the library layout. */
+int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen, int seq_stride,
+                           const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone, uint8_t *h_boards,
+                           int32_t *h_rowlen, int stride);
+
+/* ---- a15: worst-fitted sub-board of every mutating individual -------------
+ * utils.calculate_worst_fitted_sub_board (utils.py:276-313) over the implicit (rw, cw) tile lattice
+ * of utils.get_all_different_sub_range (utils.py:230-252). d_idx[m] (NULL = identity) names the
+ * individual; d_tile[m] = {from_row, from_col} of its first-minimum tile ({-1,-1}: no tile fits). */
+int gad_worst_tiles(const uint8_t *d_boards, const int32_t *d_rowlen, int R, int stride, const int32_t *d_idx,
+                    int64_t M, int rw, int cw, int mode, int match, int mismatch, int gap, int32_t *d_tile,
+                    void *stream);
+
+/* ---- a14, a16-a18: batched Q-network and environment episodes -------------
+ * gad_qnet holds the reference state_dict (DPAMSA/dqn.py:187-213; 16 fp32 tensors, order in
+ * csrc/qnet.cu) for an agent trained on rows x cols windows. Eval mode (no dropout). */
+typedef struct gad_qnet gad_qnet;
+int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int d_v, int h1, int h2,
+                    const float *const *h_weights);
+int gad_qnet_destroy(gad_qnet *q);
+int gad_qnet_dims(const gad_qnet *q, int *L, int *A);
+/* Net.forward (dqn.py:69-79) + argmax (dqn.py:153-154) for B states of L uint8 tokens each. */
+int gad_qnet_forward(gad_qnet *q, const uint8_t *d_states, int64_t B, float max_value, float *d_q,
+                     int32_t *d_action, void *stream);
+int gad_qnet_forward_host(gad_qnet *q, const uint8_t *h_states, int64_t B, float max_value, float *h_q,
+                          int32_t *h_action);
+/* GA.mutation's episode loop + Environment.padding + splice (GA.py:335-373) for M individuals.
+ * Requires max row length + (rows-1)*cols <= stride; otherwise bit 0 of *d_status is set and the
+ * board is left as it was. *h_forwards (optional) = lock-step forwards executed. Synchronises. */
+int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int R, int stride, const int32_t *d_idx,
+               const int32_t *d_tile, int64_t M, float max_value, int32_t *d_status, int64_t *h_forwards,
+               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "ga-dpamsa_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-os.environ.setdefault("GADPAMSA_PROJECT_ROOT", os.path.join(ROOT, "gpurun_out", "project_root"))
+os.environ.setdefault("GADPAMSA_PROJECT_ROOT", os.path.join("/tmp", "gadpamsa_project_root"))
 for p in (PKG, os.path.join(ROOT, "oracle"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)

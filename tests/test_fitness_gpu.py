@@ -161,7 +161,7 @@ def test_facade_free_functions(gpu):
         assert utils.get_sum_of_pairs(b, 0, 3, 0, 4) == O.sum_of_pairs(b, 0, 3, 0, 4, O.Weights(5, -3, -7))
     finally:
         config.MATCH_REWARD, config.MISMATCH_PENALTY, config.GAP_PENALTY = old
-    assert utils.get_nucleotides_seqs([[1, 2, 3, 5], [4, 3, 2, 1]]) == ["ATC-", "GCAT"]
+    assert utils.get_nucleotides_seqs([[1, 2, 3, 5], [4, 3, 2, 1]]) == ["ATC-", "GCTA"]
     assert utils.get_column_score([[1, 2, 3, 3]] * 3, 0, 3, 0, 4) == 1.0
 
 

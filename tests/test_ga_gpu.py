@@ -1,0 +1,457 @@
+"""The generation loop on the GPU (ranking, selection, hall of fame, crossover, tile search, Q-net,
+mutation, GA.run) through the C-ABI and the reference-shaped facade, against the oracle and the
+golden fixtures generated from the unmodified reference (oracle/make_golden.py). Integer, index and
+board results are bit-exact; Q-values follow the north star's 1e-3 relative tolerance."""
+import copy
+import fractions
+import os
+import random
+
+import numpy as np
+import pytest
+
+import ga_oracle as O
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+WEIGHTS = (4, -4, -4)
+
+
+@pytest.fixture(scope="module")
+def gpu(native_lib):
+    native_lib.require_device()
+    import torch
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture()
+def cfg():
+    """config knobs restored after the test."""
+    import config
+    names = ["AGENT_WINDOW_ROW", "AGENT_WINDOW_COLUMN", "GA_ITERATIONS", "POPULATION_SIZE", "CLONE_RATE", "GAP_RATE",
+             "SELECTION_RATE", "MUTATION_RATE", "MATCH_REWARD", "MISMATCH_PENALTY", "GAP_PENALTY", "CROSSOVER_KIND"]
+    saved = {n: getattr(config, n) for n in names}
+    yield config
+    for n, v in saved.items():
+        setattr(config, n, v)
+
+
+@pytest.fixture(scope="module")
+def weight_files(gpu):
+    """Substitute weights (oracle.synth_qnet_weights, the ones the golden traces were made with)
+    written in the reference's .pth layout under config.DPAMSA_WEIGHTS_PATH."""
+    import torch
+    import config
+    z = np.load(os.path.join(GOLDEN, "qnet_vectors.npz"))
+    seed = int(z["weight_seed"])
+    out = {}
+    os.makedirs(config.DPAMSA_WEIGHTS_PATH, exist_ok=True)
+    for rows, cols in ((3, 30), (6, 30), (2, 5)):
+        sd = O.synth_qnet_weights(rows, cols, seed)
+        name = "syn%dx%d" % (rows, cols)
+        torch.save({k: torch.from_numpy(v) for k, v in sd.items()},
+                   os.path.join(config.DPAMSA_WEIGHTS_PATH, name + ".pth"))
+        out[(rows, cols)] = (name, sd)
+    return out
+
+
+def tagged_board(i):
+    """A 2x4 board of valid codes that encodes the integer i (base 4)."""
+    digits = [1 + (i >> (2 * k)) % 4 for k in range(4)]
+    return [digits, digits[::-1]]
+
+
+def untag(board):
+    return sum((d - 1) << (2 * k) for k, d in enumerate(board[0][:4]))
+
+
+def scores_to_arrays(scores, mode):
+    n = len(scores)
+    sp = np.zeros(n, np.int32)
+    em = np.zeros(n, np.int32)
+    al = np.ones(n, np.int32)
+    for i, t in enumerate(scores):
+        cs = None
+        if len(t) == 3:
+            sp[i], cs = t[1], t[2]
+        elif mode == "sp":
+            sp[i] = t[1]
+        else:
+            cs = t[1]
+        if cs is not None:
+            fr = fractions.Fraction(cs).limit_denominator(1000)
+            assert fr.numerator / fr.denominator == cs
+            em[i], al[i] = fr.numerator, fr.denominator
+    return sp, em, al
+
+
+def device_population(gpu, n, scores=None, mode="sp"):
+    from population import DevicePopulation
+    dev = DevicePopulation.from_lists([tagged_board(i) for i in range(n)])
+    if scores is not None:
+        sp, em, al = scores_to_arrays(scores, mode)
+        dev.cur.sp[:n].copy_(gpu.from_numpy(sp))
+        dev.cur.em[:n].copy_(gpu.from_numpy(em))
+        dev.cur.al[:n].copy_(gpu.from_numpy(al))
+    return dev
+
+
+# ------------------------------------------------------------------------------------------- a9
+def test_rank_golden(gpu, primitives):
+    import utils
+    for rec in primitives["rank"]:
+        scores = [tuple(t) for t in rec["scores"]]
+        assert utils.get_index_of_the_best_fitted_individuals(scores, rec["n"]) == rec["out"]
+        mode = "mo" if len(scores[0]) == 3 else "sp"
+        dev = device_population(gpu, len(scores), scores, mode)
+        assert dev.rank_order(mode, rec["n"]).cpu().tolist() == rec["out"]
+
+
+def test_rank_large_random_against_oracle(gpu):
+    rng = random.Random(5)
+    n = 20000
+    scores = [(i, rng.randint(-40, 40) * 4, rng.randint(0, 63) / 63) for i in range(n)]
+    for mode, sc in (("sp", [(i, s) for i, s, _ in scores]), ("cs", [(i, c) for i, _, c in scores]), ("mo", scores)):
+        dev = device_population(gpu, n, sc, mode)
+        assert dev.rank_order(mode, 5000).cpu().tolist() == O.rank_best(sc, 5000)
+
+
+# ------------------------------------------------------------------------------------------- a10 / a11
+def test_selection_and_pareto_golden(gpu, primitives):
+    for rec in primitives["selection"]:
+        scores = [tuple(t) for t in rec["scores"]]
+        dev = device_population(gpu, rec["n"], scores, rec["mode"])
+        top_n = int(rec["n"] * rec["rate"])
+        n_keep = dev.select(rec["mode"], top_n)
+        assert [untag(b) for b in dev.to_lists()] == rec["keep"]
+        assert n_keep == len(rec["keep"])
+    for rec in primitives["pareto"]:
+        scores = [tuple(t) for t in rec["scores"]]
+        dev = device_population(gpu, len(scores), scores, "mo")
+        keep, _ = dev.select_flags("mo", -1)
+        assert np.nonzero(keep.cpu().numpy())[0].tolist() == rec["out"]
+
+
+@pytest.mark.parametrize("mode", ["sp", "cs", "mo"])
+def test_selection_large_random_against_oracle(gpu, mode):
+    rng = random.Random(17)
+    n = 6000
+    full = [(i, rng.randint(-12, 12) * 4, rng.randint(0, 20) / 21) for i in range(n)]
+    sc = full if mode == "mo" else [(i, s) for i, s, _ in full] if mode == "sp" else [(i, c) for i, _, c in full]
+    for rate in (0.5, 0.01, 0.9):
+        dev = device_population(gpu, n, sc, mode)
+        keep, count = dev.select_flags(mode, int(n * rate))
+        want = O.selection_keep(sc, mode, n, rate, fast=True)
+        assert np.nonzero(keep.cpu().numpy())[0].tolist() == sorted(want)
+        assert int(count.item()) == len(want)
+
+
+def test_compaction_keeps_boards_scores_and_order(gpu):
+    from population import DevicePopulation
+    rng = random.Random(3)
+    pop = [[[rng.choice([1, 2, 3, 4]) for _ in range(rng.randint(20, 70))] for _ in range(5)] for _ in range(300)]
+    for b in pop:
+        w = max(map(len, b))
+        for row in b:
+            row.extend([5] * (w - len(row)))
+    dev = DevicePopulation.from_lists(copy.deepcopy(pop))
+    dev.fitness(*WEIGHTS)
+    sp, em, al = [a.copy() for a in dev.scores_numpy()]
+    scores = [(i, int(sp[i])) for i in range(len(pop))]
+    keep = sorted(O.selection_keep(scores, "sp", len(pop), 0.3))
+    assert dev.select("sp", int(len(pop) * 0.3)) == len(keep)
+    cleaned = copy.deepcopy(pop)
+    O.fitness_scores(cleaned, "sp")
+    assert dev.to_lists() == [cleaned[i] for i in keep]
+    sp2, em2, al2 = dev.scores_numpy()
+    assert sp2.tolist() == sp[keep].tolist() and em2.tolist() == em[keep].tolist() and al2.tolist() == al[keep].tolist()
+
+
+# ------------------------------------------------------------------------------------------- a8
+def test_hall_of_fame_golden(gpu, primitives):
+    for rec in primitives["hof"]:
+        mode = rec["mode"]
+        n = len(rec["scores1"])
+        dev = device_population(gpu, n, [tuple(t) for t in rec["scores1"]], mode)
+        dev.hof_update(mode)
+        board, (idx, sp, em, al) = dev.hof_numpy()
+        assert idx == rec["first"][1][0] and untag(board.tolist()) == rec["first"][0][0][0] - 1
+        got = (idx, sp) if mode == "sp" else (idx, sp, em / al)
+        assert list(got) == rec["first"][1]
+        # second population: boards tagged 100+i in the golden record -> tag i+64 here
+        sp2, em2, al2 = scores_to_arrays([tuple(t) for t in rec["scores2"]], mode)
+        dev2_boards = [tagged_board(64 + i) for i in range(n)]
+        from population import pack_boards
+        b, r = pack_boards(dev2_boards, stride=dev.stride)
+        dev.cur.boards[:n].copy_(gpu.from_numpy(b))
+        dev.cur.sp[:n].copy_(gpu.from_numpy(sp2))
+        dev.cur.em[:n].copy_(gpu.from_numpy(em2))
+        dev.cur.al[:n].copy_(gpu.from_numpy(al2))
+        dev.hof_update(mode)
+        board, (idx, sp, em, al) = dev.hof_numpy()
+        want_board, want_score = rec["second"]
+        assert idx == want_score[0]
+        tag = want_board[0][0]                       # golden: i+1 (first population) or 100+i (second)
+        assert untag(board.tolist()) == (tag - 100 + 64 if tag >= 100 else tag - 1)
+        got = (idx, sp) if mode == "sp" else (idx, sp, em / al)
+        assert list(got) == want_score
+
+
+# ------------------------------------------------------------------------------------------- a3 / a12 / a13
+def test_population_and_crossover_rng_replay(gpu, primitives, cfg, native_lib):
+    """Same CPython `random` stream as the reference: populations, crossover children and the state of
+    the generator afterwards are identical."""
+    import GA as ga_mod
+    for rec in primitives["population"]:
+        cfg.POPULATION_SIZE = rec["P"]
+        cfg.CLONE_RATE, cfg.GAP_RATE = 0.25, 0.05
+        random.seed(rec["seed"])
+        g = ga_mod.GA(rec["seqs"], "sp")
+        g.generate_population()
+        assert g.population == rec["population"]
+        n_surv = rec["n_survivors"]
+        g.population = rec["population"][:n_surv]
+        dev = g._dev
+        plan = np.empty((rec["P"] - n_surv, 3), np.int32)
+        state, meta = ga_mod._mt_state()
+        native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, n_surv, dev.R, rec["P"] - n_surv, None,
+                        plan.ctypes.data)
+        ga_mod._mt_restore(state, meta)
+        dev.crossover(plan, 0)
+        assert g.population == rec["after_crossover"]
+        assert random.random() == rec["next_random"]
+
+
+def test_crossover_plan_matches_python_random(gpu, native_lib):
+    import GA as ga_mod
+    for seed, (n_par, rows, n_child) in enumerate([(2, 2, 50), (3, 6, 200), (1000, 20, 5000), (32768, 6, 32768)]):
+        random.seed(seed)
+        want = O.crossover_plan(n_par, rows, n_child)
+        after = random.random()
+        random.seed(seed)
+        plan = np.empty((n_child, 3), np.int32)
+        state, meta = ga_mod._mt_state()
+        native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, n_par, rows, n_child, None, plan.ctypes.data)
+        ga_mod._mt_restore(state, meta)
+        assert plan.tolist() == [list(t) for t in want]
+        assert random.random() == after
+    with pytest.raises(ValueError):
+        state, _ = ga_mod._mt_state()
+        native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, 1, 6, 4, None, plan.ctypes.data)
+
+
+def test_crossover_children_against_oracle(gpu):
+    from population import DevicePopulation
+    rng = random.Random(8)
+    parents = []
+    for _ in range(40):
+        w = rng.randint(5, 90)
+        parents.append([[rng.choice([1, 2, 3, 4, 5]) for _ in range(w)] for _ in range(7)])
+    for kind in (0, 1):
+        plan = []
+        for _ in range(300):
+            a, b = rng.sample(range(40), 2)
+            hi = 6 if kind == 0 else min(len(parents[a][0]), len(parents[b][0])) - 1
+            plan.append((a, b, rng.randint(1, hi)))
+        dev = DevicePopulation.from_lists(copy.deepcopy(parents), capacity=400)
+        dev.crossover(np.array(plan, np.int32), kind)
+        child = O.horizontal_child if kind == 0 else O.vertical_child
+        want = parents + [child(parents[a], parents[b], c) for a, b, c in plan]
+        assert dev.to_lists() == want
+        # the children obey the layout invariant: a fitness pass gives the oracle's result
+        dev.fitness(*WEIGHTS)
+        ref = copy.deepcopy(want)
+        sc = O.fitness_scores(ref, "mo")
+        assert dev.to_lists() == ref
+        assert dev.scores_numpy()[0].tolist() == [s for _, s, _ in sc]
+
+
+# ------------------------------------------------------------------------------------------- a15
+def test_worst_tile_golden(gpu, primitives, cfg):
+    import utils
+    for rec in primitives["worst"]:
+        cfg.AGENT_WINDOW_ROW, cfg.AGENT_WINDOW_COLUMN = rec["rw"], rec["cw"]
+        score, tile = utils.calculate_worst_fitted_sub_board(rec["board"], rec["mode"])
+        assert list(tile) == rec["tile"]
+        assert score == rec["score"]
+    for rec in primitives["tiles"]:
+        board = [[1] * rec["W"] for _ in range(rec["R"])]
+        assert [list(t) for t in utils.get_all_different_sub_range(board, rec["rw"], rec["cw"])] == rec["out"]
+
+
+def test_worst_tiles_population_against_oracle(gpu):
+    from population import DevicePopulation
+    rng = random.Random(12)
+    for R, W, rw, cw in ((6, 63, 3, 30), (6, 63, 6, 30), (20, 210, 3, 30), (7, 59, 3, 30)):
+        pop = [[[rng.choice([1, 2, 3, 4, 5, 1, 2]) for _ in range(W)] for _ in range(R)] for _ in range(120)]
+        dev = DevicePopulation.from_lists(pop)
+        for mode in ("sp", "cs", "mo"):
+            for w in (WEIGHTS, (5, -3, -7)):
+                got = dev.worst_tiles(None, rw, cw, mode, *w).cpu().numpy()
+                for p, board in enumerate(pop):
+                    _, t = O.worst_tile(board, mode, rw, cw, O.Weights(*w))
+                    assert (got[p, 0], got[p, 1]) == (t[0], t[2])
+
+
+# ------------------------------------------------------------------------------------------- a16-a18
+def test_qnet_golden_vectors(gpu, weight_files):
+    """Q-values of the reference Net (eval mode) on recorded states: 1e-3 relative (plus a floor of
+    1e-5 * max_value for Q near 0) and identical greedy actions."""
+    from DPAMSA.dqn import load_qnet
+    z = np.load(os.path.join(GOLDEN, "qnet_vectors.npz"))
+    for (rows, cols), (name, sd) in weight_files.items():
+        tag = "%dx%d" % (rows, cols)
+        states, q_ref = z["states_" + tag], z["q_" + tag]
+        max_value = cols * rows * (rows - 1) / 2 * 4
+        net = load_qnet(name, rows, cols)
+        q, a = net.forward(states.astype(np.uint8), max_value)
+        assert np.all(np.abs(q - q_ref) <= 1e-3 * np.abs(q_ref) + 1e-5 * max_value), np.abs(q - q_ref).max()
+        assert np.array_equal(a, q_ref.argmax(1))
+        q64 = O.qnet_forward(sd, states, max_value)
+        assert np.all(np.abs(q - q64) <= 1e-3 * np.abs(q64) + 1e-5 * max_value)
+
+
+def test_dqn_and_environment_facade(gpu, weight_files, primitives):
+    from DPAMSA.dqn import DQN
+    from DPAMSA.env import Environment
+    name, sd = weight_files[(2, 5)]
+    env = Environment([[1, 2, 3, 4, 1], [2, 2, 3, 1, 1]], convert_data=False)
+    agent = DQN(env.action_number, env.row, env.max_len, env.max_len * env.max_reward)
+    agent.load(name)
+    oenv = O.Env([[1, 2, 3, 4, 1], [2, 2, 3, 1, 1]])
+    state = env.reset()
+    assert state == oenv.reset()
+    while True:
+        a = agent.predict(state)
+        want = O.greedy_action(O.qnet_forward(sd, [state], env.max_len * env.max_reward, np.float32)[0])
+        assert a.shape == (1,) and int(a[0]) == want
+        r, state, done = env.step(a)
+        r2, s2, d2 = oenv.step(want)
+        assert (r, state, done) == (r2, s2, d2)
+        if done == 0:
+            break
+    env.padding()
+    oenv.padding()
+    assert env.aligned == oenv.aligned
+    for rec in primitives["env"]:
+        env = Environment(copy.deepcopy(rec["data"]), convert_data=False)
+        assert env.max_reward == rec["max_reward"] and env.action_number == rec["action_number"]
+        assert env.reset() == rec["steps"][0]["state"]
+        for st in rec["steps"][1:]:
+            r, s, d = env.step(st["action"])
+            assert (r, s, d) == (st["reward"], st["state"], st["done"])
+            assert env.aligned == st["aligned"]
+        env.padding()
+        assert env.aligned == rec["padded"]
+    with pytest.raises(FileNotFoundError):
+        DQN(7, 3, 30, 360.0).load("no_such_model")
+
+
+@pytest.mark.parametrize("rows,cols,R,W", [(3, 30, 6, 63), (6, 30, 6, 64), (3, 30, 7, 95), (2, 5, 5, 23)])
+def test_mutation_against_oracle(gpu, weight_files, rows, cols, R, W):
+    """Batched device episodes + padding + splice == the oracle's per-individual GA.py:335-373."""
+    from DPAMSA.dqn import load_qnet
+    from population import DevicePopulation
+    name, sd = weight_files[(rows, cols)]
+    net = load_qnet(name, rows, cols)
+    rng = random.Random(rows * 100 + W)
+    pop = [[[rng.choice([1, 2, 3, 4, 5, 1, 2, 3, 4]) for _ in range(W)] for _ in range(R)] for _ in range(24)]
+    dev = DevicePopulation.from_lists(copy.deepcopy(pop))
+    gpu_idx = gpu.tensor([3, 0, 7, 23, 11, 12, 5], dtype=gpu.int32, device="cuda")
+    tile = dev.worst_tiles(gpu_idx, rows, cols, "sp", *WEIGHTS)
+    max_value = cols * rows * (rows - 1) / 2 * 4
+    dev.mutate(net, gpu_idx, tile, max_value)
+    want = copy.deepcopy(pop)
+    for i in gpu_idx.cpu().tolist():
+        _, t = O.worst_tile(want[i], "sp", rows, cols)
+        O.mutate_board(want[i], t, sd, qdtype=np.float32)
+    assert dev.to_lists() == want
+    dev.fitness(*WEIGHTS)
+    sc = O.fitness_scores(want, "mo")
+    assert dev.to_lists() == want
+    assert dev.scores_numpy()[0].tolist() == [s for _, s, _ in sc]
+
+
+# ------------------------------------------------------------------------------------------- a19: whole runs
+def run_facade(tr, cfg, model):
+    import GA as ga_mod
+    for k, v in tr["knobs"].items():
+        setattr(cfg, k, v)
+    random.seed(tr["seed"])
+    g = ga_mod.GA(tr["seqs"], tr["mode"])
+    log = []
+    inner = g.calculate_fitness_score
+
+    def logged():
+        inner()
+        hof = g.hall_of_fame
+        log.append({"scores": [list(s) for s in g.population_score], "hof": O.decode(hof[0]),
+                    "hof_score": list(hof[1])})
+    g.calculate_fitness_score = logged
+    out = g.run(model)
+    return out, log, g
+
+
+def test_ga_run_reproduces_reference_traces(gpu, ga_traces, weight_files, cfg):
+    """GA.run through the facade == the unmodified reference's recorded per-pass scores, hall of fame
+    and final alignment, for every recorded (mode, seed, knobs) - population generation, mutation with
+    greedy Q-net actions, selection and crossover included."""
+    done = 0
+    for tr in ga_traces["traces"]:
+        kb = tr["knobs"]
+        name, _ = weight_files[(kb["AGENT_WINDOW_ROW"], kb["AGENT_WINDOW_COLUMN"])]
+        out, log, _ = run_facade(tr, cfg, name)
+        assert len(log) == len(tr["passes"])
+        for k, (mine, ref) in enumerate(zip(log, tr["passes"])):
+            assert mine["scores"] == ref["scores"], (tr["mode"], tr["seed"], k)
+            assert mine["hof"] == ref["hof"] and mine["hof_score"] == ref["hof_score"], (tr["mode"], tr["seed"], k)
+        assert out == tr["result"]
+        done += 1
+    assert done >= 20
+
+
+def test_ga_run_against_oracle_larger_population(gpu, weight_files, cfg, datasets_json):
+    """P=256 on a 6x60 set, all three modes, against the oracle's whole loop (too slow for the golden file)."""
+    name, sd = weight_files[(3, 30)]
+    seqs = datasets_json["synthetic_dataset_6x60bp"]["test2"]
+    for mode in ("sp", "cs", "mo"):
+        knobs = {"AGENT_WINDOW_ROW": 3, "AGENT_WINDOW_COLUMN": 30, "GA_ITERATIONS": 2, "POPULATION_SIZE": 256,
+                 "CLONE_RATE": 0.25, "GAP_RATE": 0.05, "SELECTION_RATE": 0.5, "MUTATION_RATE": 0.1}
+        tr = {"knobs": knobs, "seed": 11, "seqs": seqs, "mode": mode}
+        out, log, _ = run_facade(tr, cfg, name)
+        random.seed(11)
+        olog = []
+        oout, _ = O.ga_run(seqs, mode, sd, O.Knobs(**knobs), log=olog, fast_pareto=True)
+        assert len(log) == len(olog)
+        for mine, ref in zip(log, olog):
+            assert mine["scores"] == [list(s) for s in ref[1]]
+            assert mine["hof"] == ref[2] and mine["hof_score"] == list(ref[3])
+        assert out == oout
+
+
+def test_run_validation_errors(gpu, weight_files, cfg):
+    import GA as ga_mod
+    name, _ = weight_files[(3, 30)]
+    cfg.POPULATION_SIZE = 6
+    cfg.AGENT_WINDOW_ROW, cfg.AGENT_WINDOW_COLUMN = 3, 30
+    with pytest.raises(ValueError):
+        ga_mod.GA(["ACGT" * 10, "ACGA" * 10], "sp").run(name)            # 2 rows < window rows
+    with pytest.raises(ValueError):
+        ga_mod.GA(["ACGTACGT", "ACGAACGT", "ACGAACGA"], "sp").run(name)   # 8 columns < window columns
+    with pytest.raises(KeyError):
+        ga_mod.GA(["ACGN" * 10] * 3, "sp").run(name)                      # unknown nucleotide (GA.py:79)
+
+
+def test_vertical_crossover_run(gpu, weight_files, cfg, datasets_json):
+    """Vertical crossover is an extension without reference code (parity unpinned): the run must keep
+    the population size and every child must be a column-wise recombination of two survivors."""
+    import GA as ga_mod
+    name, _ = weight_files[(3, 30)]
+    cfg.POPULATION_SIZE, cfg.GA_ITERATIONS, cfg.CROSSOVER_KIND = 40, 1, "vertical"
+    random.seed(2)
+    g = ga_mod.GA(datasets_json["dataset1_6x30bp"]["test0"], "sp")
+    out = g.run(name)
+    assert len(g.population) == 40 and len(out) == 6
+    assert len({len(r) for r in out}) == 1
