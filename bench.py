@@ -219,6 +219,172 @@ def cpu_c_port(boards, rowlen, threads, min_seconds=2.0):
     return done / elapsed, done, elapsed
 
 
+
+# ------------------------------------------------------------------------------------------------
+# whole generations (GA.run's loop body, reference GA.py:494-526) through the facade
+# ------------------------------------------------------------------------------------------------
+AGENTS = {"c2": (3, 30), "c3": (6, 30), "c4": (3, 30)}          # BASELINE configs: trained window per workload
+QNET_FLOPS = {(3, 30): 26.8e6, (6, 30): 63.9e6}                 # reference Net.forward per state
+
+
+def synth_weight_file(rows, cols, seed=7):
+    """Random-init weights in the reference state_dict layout (DPAMSA/dqn.py:54-63; the pretrained
+    files are not in the reference checkout). Returns the model name for DQN.load."""
+    import torch
+    import config
+    rng = np.random.default_rng(seed)
+    L, A, d, dk, h1, h2 = rows * (cols + 1), 2 ** rows - 1, 64, 164, 1028, 512
+    def lin(o, i):
+        b = 1.0 / np.sqrt(i)
+        return rng.uniform(-b, b, size=(o, i)).astype(np.float32)
+    pos = np.arange(L, dtype=np.float64)[:, None] / np.power(10000.0, 2 * (np.arange(d) // 2) / d)
+    pos[:, 0::2] = np.sin(pos[:, 0::2])
+    pos[:, 1::2] = np.cos(pos[:, 1::2])
+    emb = rng.standard_normal((6, d)).astype(np.float32)
+    emb[0] = 0
+    sd = {
+        "encoder.src_word_emb.weight": emb, "encoder.position_enc.pos_table": pos.astype(np.float32)[None],
+        "encoder.layer_norm.weight": np.ones(d, np.float32), "encoder.layer_norm.bias": np.zeros(d, np.float32),
+        "encoder.self_attention.w_qs.weight": lin(dk, d), "encoder.self_attention.w_ks.weight": lin(dk, d),
+        "encoder.self_attention.w_vs.weight": lin(dk, d), "encoder.self_attention.fc.weight": lin(d, dk),
+        "encoder.self_attention.layer_norm.weight": np.ones(d, np.float32),
+        "encoder.self_attention.layer_norm.bias": np.zeros(d, np.float32),
+        "l1.weight": lin(h1, L * d), "l1.bias": lin(1, L * d)[0, :h1].copy(), "l2.weight": lin(h2, h1),
+        "l2.bias": lin(1, h1)[0, :h2].copy(), "l3.weight": lin(A, h2), "l3.bias": lin(1, h2)[0, :A].copy(),
+    }
+    name = "bench_%dx%d" % (rows, cols)
+    os.makedirs(config.DPAMSA_WEIGHTS_PATH, exist_ok=True)
+    torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, os.path.join(config.DPAMSA_WEIGHTS_PATH, name + ".pth"))
+    return name, sd
+
+
+def seq_strings(rows, cols, seed):
+    return ["".join("ATCG-"[v - 1] for v in row) for row in synth_sequences(rows, cols, seed)]
+
+
+def measure_generations(workload, n_gen, n_warm):
+    """Generations/s of the facade's loop body (mutation -> fitness -> selection -> crossover, each with the
+    reference's fitness re-evaluations) on one GPU, with a per-phase breakdown."""
+    import random
+    import torch
+    import config
+    import GA as ga_mod
+    rows, cols, P, mode, _ = WORKLOADS[workload]
+    rw, cw = AGENTS[workload]
+    saved = {k: getattr(config, k) for k in ("POPULATION_SIZE", "AGENT_WINDOW_ROW", "AGENT_WINDOW_COLUMN", "GA_ITERATIONS")}
+    config.POPULATION_SIZE, config.AGENT_WINDOW_ROW, config.AGENT_WINDOW_COLUMN = P, rw, cw
+    try:
+        model, _ = synth_weight_file(rw, cw)
+        random.seed(20251019)
+        g = ga_mod.GA(seq_strings(rows, cols, 20251019), mode)
+        t0 = time.perf_counter()
+        g.generate_population()
+        torch.cuda.synchronize()
+        t_pop = time.perf_counter() - t0
+        g.calculate_fitness_score()
+        phases = {"mutation": 0.0, "fitness": 0.0, "selection": 0.0, "crossover": 0.0}
+        evals = forwards = episodes = 0
+        total = 0.0
+        for it in range(n_warm + n_gen):
+            dev = g._dev
+            e0, f0 = dev.evals, dev.forwards
+            stamps = []
+            for name, fn in (("mutation", lambda: g.mutation(model)), ("fitness", g.calculate_fitness_score),
+                             ("selection", g.selection), ("crossover", g.horizontal_crossover)):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                stamps.append((name, time.perf_counter() - t0))
+            if it >= n_warm:
+                for name, dt in stamps:
+                    phases[name] += dt
+                    total += dt
+                evals += g._dev.evals - e0
+                forwards += g._dev.forwards - f0
+                episodes += round(P * config.MUTATION_RATE)
+        hof = g.hall_of_fame
+        flops = QNET_FLOPS.get((rw, cw))
+        return {
+            "value": n_gen / total, "unit": "generations/s", "generations": n_gen, "warmup": n_warm,
+            "ms_per_generation": 1e3 * total / n_gen,
+            "phase_ms": {k: 1e3 * v / n_gen for k, v in phases.items()},
+            "fitness_evals_per_generation": evals / n_gen, "episodes_per_generation": episodes / n_gen,
+            "lockstep_forwards_per_generation": forwards / n_gen,
+            "population_generation_s": t_pop, "agent_window": [rw, cw], "population": P, "mode": mode,
+            "hall_of_fame_score": list(hof[1]) if hof else None,
+            "reference_net_flops_per_state": flops,
+        }
+    finally:
+        for k, v in saved.items():
+            setattr(config, k, v)
+
+
+def cpu_generation_port(workload, cores, n_mut_per_core=1):
+    """The reference's per-generation CPU cost from bounded samples of the oracle port: fitness passes at
+    the measured python-port rate plus round(P*MUTATION_RATE) episodes at the measured per-individual
+    mutation time (the reference's own torch CPU ops in eval mode, one thread per process, agent
+    hoisted out of the per-individual loop - the reference re-creates and re-loads it every time,
+    GA.py:354-355, which is not counted), spread over `cores`."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import multiprocessing as mp
+    rows, cols, P, mode, _ = WORKLOADS[workload]
+    rw, cw = AGENTS[workload]
+    boards, rowlen = synth_population(rows, cols, 4096, 20251019)
+    n_sample = python_sample_size(rows, cols, 4096, cores)
+    pool = python_pool(cores)
+    cpu_python_port(boards, rowlen, mode, min(64 * cores, 4096), cores, pool)
+    fit_rate, _, _ = cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
+    jobs = [(workload, 1000 + i, n_mut_per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    res = pool.map(_mutation_worker, jobs) if pool is not None else [_mutation_worker(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+    per_ind = sum(r[0] for r in res) / sum(r[1] for r in res)
+    steps = sum(r[2] for r in res) / sum(r[1] for r in res)
+    M = round(P * 0.25)
+    S = P // 2
+    gen_s = (2 * P + S) / fit_rate + M * per_ind / cores
+    return {"value": 1.0 / gen_s, "unit": "generations/s", "cores": cores, "kind": "port",
+            "fitness_evals_per_s": fit_rate, "mutation_s_per_individual_1core": per_ind,
+            "episode_steps_mean": steps,
+            "sample": "%d fitness evals and %d mutation episodes timed (%.1f s wall), extrapolated linearly to "
+                      "(2P+S)=%d evals + %d episodes on %d processes" % (n_sample, cores * n_mut_per_core, wall,
+                                                                         2 * P + S, M, cores)}
+
+
+def _mutation_worker(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import random
+    import ga_oracle as O
+    workload, seed, n = args
+    rows, cols, P, mode, _ = WORKLOADS[workload]
+    rw, cw = AGENTS[workload]
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import torch
+    sd = O.synth_qnet_weights(rw, cw, 7)
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    forward = lambda states, max_value: O.qnet_forward_torch(sd_t, states, max_value)
+    rng = random.Random(seed)
+    seqs = seq_strings(rows, cols, 20251019)
+    pop = O.generate_population(seqs, n + 1, 0.0, 0.05, rng)[:n]
+    O.fitness_scores(pop, mode)
+    t0 = time.perf_counter()
+    steps = 0
+    for b in pop:
+        _, tile = O.worst_tile(b, mode, rw, cw)
+        trace = []
+        O.mutate_board(b, tile, sd, trace=trace, forward=forward)
+        steps += len(trace)
+    return time.perf_counter() - t0, n, steps
+
+
 # ------------------------------------------------------------------------------------------------
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -228,6 +394,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--generations", type=int, default=2, help="timed whole generations (0 = skip)")
+    ap.add_argument("--generation-warmup", type=int, default=1)
     return ap.parse_args()
 
 
@@ -266,6 +434,10 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.generations > 0:
+        line["generation"] = {"cpu_baseline": cpu_generation_port(args.workload, cores)}
+        line["generation"]["value"] = line["generation"]["cpu_baseline"]["value"]
+        line["generation"]["unit"] = "generations/s"
     print(json.dumps(line), flush=True)
 
 
@@ -399,6 +571,12 @@ def main():
         "launch_ms": {"median": statistics.median(per_launch_ms), "max": max(per_launch_ms)},
     }
 
+    # ---------------- whole generations (N=1; the sharded loop is measured by --gpus N via the GA facade) ----
+    if world == 1 and args.generations > 0:
+        del replicas, pristine_b, pristine_r
+        torch.cuda.empty_cache()
+        line["generation"] = measure_generations(args.workload, args.generations, args.generation_warmup)
+
     # ---------------- CPU baselines on rank 0 at N=1 ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -414,6 +592,8 @@ def main():
                                 "sample": "%d boards in %.2f s on %d processes" % (py_n, py_dt, cores)}
         line["cpu_baseline_c_openmp"] = {"value": c_rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                          "sample": "%d evals in %.2f s, oracle/ga_oracle.c" % (c_n, c_dt)}
+        if args.generations > 0:
+            line["generation"]["cpu_baseline"] = cpu_generation_port(args.workload, cores)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

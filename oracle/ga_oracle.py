@@ -479,20 +479,49 @@ def qnet_forward(sd, states, max_value, dtype=np.float64):
     return np.tanh(h) * dtype(max_value)
 
 
+def qnet_forward_torch(sd_t, states, max_value):
+    """The same forward with the torch CPU ops the reference itself executes (dqn.py:69-79,
+    models.py:87-95,190-207,241-249), eval mode, fp32.  ``sd_t``: state_dict of torch tensors.
+    This is the reference's real CPU cost model (bench.py's mutation baseline); results agree with
+    ``qnet_forward`` to fp32 rounding."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        tok = torch.as_tensor(np.asarray(states), dtype=torch.long)
+        L = tok.shape[1]
+        x = F.embedding(tok, sd_t["encoder.src_word_emb.weight"], padding_idx=0)
+        x = x + sd_t["encoder.position_enc.pos_table"][:, :L]
+        x = F.layer_norm(x, (x.shape[-1],), sd_t["encoder.layer_norm.weight"], sd_t["encoder.layer_norm.bias"], 1e-6)
+        q = F.linear(x, sd_t["encoder.self_attention.w_qs.weight"])
+        k = F.linear(x, sd_t["encoder.self_attention.w_ks.weight"])
+        v = F.linear(x, sd_t["encoder.self_attention.w_vs.weight"])
+        att = torch.matmul(q / (q.shape[-1] ** 0.5), k.transpose(1, 2))
+        att = att.masked_fill((tok != 0).unsqueeze(-2) == 0, -1e9)
+        att = F.softmax(att, dim=-1)
+        o = F.linear(torch.matmul(att, v), sd_t["encoder.self_attention.fc.weight"]) + x
+        o = F.layer_norm(o, (o.shape[-1],), sd_t["encoder.self_attention.layer_norm.weight"],
+                         sd_t["encoder.self_attention.layer_norm.bias"], 1e-6)
+        h = F.leaky_relu(F.linear(o.reshape(o.shape[0], -1), sd_t["l1.weight"], sd_t["l1.bias"]))
+        h = F.leaky_relu(F.linear(h, sd_t["l2.weight"], sd_t["l2.bias"]))
+        h = torch.tanh(F.linear(h, sd_t["l3.weight"], sd_t["l3.bias"]))
+        return torch.mul(h, max_value).numpy()
+
+
 def greedy_action(qvalues):
     """dqn.py:153-154 - argmax, first index on ties."""
     return int(np.argmax(qvalues))
 
 
-def mutate_board(board, tile, sd, w=DEFAULT_W, qdtype=np.float32, trace=None):
-    """GA.py:335-373 for one individual, eval-mode agent.  In place."""
+def mutate_board(board, tile, sd, w=DEFAULT_W, qdtype=np.float32, trace=None, forward=None):
+    """GA.py:335-373 for one individual, eval-mode agent.  In place.  ``forward(states, max_value)``
+    replaces the numpy forward (e.g. ``qnet_forward_torch`` bound to torch weights)."""
     fr, tr, fc, tc = tile
     sub = [row[fc:tc] for row in board[fr:tr]]
     env = Env(sub, w)
     max_value = env.max_len * env.max_reward                     # GA.py:354
     state = env.reset()
     while True:
-        q = qnet_forward(sd, [state], max_value, dtype=qdtype)[0]
+        q = (forward([state], max_value) if forward else qnet_forward(sd, [state], max_value, dtype=qdtype))[0]
         a = greedy_action(q)
         if trace is not None:
             trace.append((list(state), a, q))
