@@ -1,0 +1,389 @@
+// l1 of the Q-network on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   C[M][N] = leaky_relu( (A . W^T) * 2^-s + bias ),   A = Z (encoder output), W = l1.weight (dqn.py:57,73)
+//
+// Precision: the north star needs greedy-action parity with the fp32 reference, which bf16/fp16 inputs
+// (2^-9 / 2^-11 per operand) cannot give. Both operands are therefore split into two fp16 terms,
+// x = hi + lo (W pre-scaled by 2^s so that lo stays normal), and the product is evaluated as
+// hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM - 2^-22 per operand, i.e. fp32-class - as ONE
+// k-loop over three (A-segment, W-segment) pairs of the same tiles:
+//     A' = [Zh | Zl]  (M x 2K fp16)       W' = [Wh | Wl]  (Npad x 2K fp16)
+//     segments: (Zh,Wh) (Zl,Wh) (Zh,Wl)
+//
+// Structure (one CTA per SM, persistent over 128 x BN output tiles):
+//     warp 0   TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem stages, mbarrier expect_tx
+//     warp 1   MMA issuer     one elected lane issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16), commits
+//                             to the stage's "empty" barrier and, per tile, to the accumulator's "full" barrier
+//     warps 2-9 epilogue      tcgen05.ld 32x32b from their TMEM lane quarter and column half into fp32 registers
+//                             per chunk; after the last chunk scale + bias + LeakyReLU and store
+// Accumulation: tcgen05 adds each K=16 product block into the fp32 TMEM accumulator with truncation, a
+// bias that grows linearly with the number of accumulations (measured: 1e-4 relative after the 2232
+// MMAs of one 6x30 tile, 50x worse than fp32). The k-loop is therefore cut into chunks of CHUNK_KB
+// k-blocks (32 MMAs): each chunk accumulates into one of two TMEM buffers (2 x 256 columns) from zero
+// and the epilogue warps add the finished chunk into fp32 registers with round-to-nearest while the
+// next chunk runs in the other buffer - the same promotion DeepGEMM applies to FP8 on Hopper.
+#include "gad_common.cuh"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "gemm_tc.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                      // 64 fp16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int ACC_COLS = 256;               // TMEM columns per accumulator buffer
+constexpr int TMEM_COLS = 512;
+constexpr int CHUNK_KB = 8;                 // k-blocks (of 64) per TMEM accumulation chunk = 32 MMAs
+constexpr int EPI_WARPS = 8;                // 2 per TMEM lane quarter, each owning half of the tile's columns
+
+template <int BN> struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (220 * 1024) / STAGE_BYTES > 6 ? 6 : (220 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment (BN multiple of 8)");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 28)) __trap();            // a lost arrival must fail loudly, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in smem written by TMA with 128-byte swizzle: rows of 128 bytes, 8-row atoms of
+// 1024 bytes (stride byte offset), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address        bits [0,14)
+    d |= (uint64_t)0 << 16;                             // leading byte offset  bits [16,30) (unused: swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version   bits [46,48)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B         bits [61,64)
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n)
+{
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const float *__restrict__ bias, float out_scale, float *__restrict__ C, int ldc,
+                      const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky)
+{
+    using C_ = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C_::STAGES * C_::STAGE_BYTES);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C_::STAGES;
+    const uint32_t tfull0 = empty0 + 8 * C_::STAGES, tempty0 = tfull0 + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * C_::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long M = m_ptr ? (long long)*m_ptr : m_fixed;
+    const int tiles_n = (N + BN - 1) / BN;
+    const long long tiles = ((M + BM - 1) / BM) * tiles_n;
+    const int kblocks = K / BK;                          // per segment
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C_::STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull0 + 8 * s, 1);
+            mbar_init(tempty0 + 8 * s, EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                     // TMEM allocation (whole warp), 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int m_blk = (int)(t / tiles_n), n_blk = (int)(t % tiles_n);
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int a_off = seg == 1 ? K : 0, b_off = seg == 2 ? K : 0;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
+                        mbar_expect_tx(full0 + 8 * stage, C_::STAGE_BYTES);
+                        tma_load_2d(sa, &map_a, full0 + 8 * stage, a_off + kb * BK, m_blk * BM);
+                        tma_load_2d(sb, &map_b, full0 + 8 * stage, b_off + kb * BK, n_blk * BN);
+                        if (++stage == C_::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            long long chunk = 0;                                                  // running chunk counter (buffer = chunk & 1)
+            const int total_kb = 3 * kblocks;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+                for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK_KB, ++chunk) {
+                    const int as = (int)(chunk & 1);
+                    mbar_wait(tempty0 + 8 * as, (uint32_t)((chunk >> 1) & 1) ^ 1);    // epilogue has drained this buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                    const int kb1 = kb0 + CHUNK_KB < total_kb ? kb0 + CHUNK_KB : total_kb;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
+                            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || k != 0);
+                        }
+                        umma_commit(empty0 + 8 * stage);                          // frees the smem stage when the MMAs retire
+                        if (++stage == C_::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(tfull0 + 8 * as);                                 // chunk ready for the epilogue
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: warps 2..9; TMEM lane quarter = warp & 3, column half = (warp-2) >> 2 =====
+        constexpr int HALF = BN / 2;                       // columns per epilogue warp
+        constexpr int NLD = HALF / 8;                      // x8 loads per chunk
+        static_assert(HALF % 8 == 0, "BN/2 must be a multiple of 8");
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const int total_kb = 3 * kblocks;
+        long long chunk = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int m_blk = (int)(t / tiles_n), n_blk = (int)(t % tiles_n);
+            float acc[HALF];
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+            for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK_KB, ++chunk) {
+                const int as = (int)(chunk & 1);
+                mbar_wait(tfull0 + 8 * as, (uint32_t)((chunk >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_COLS + half * HALF;
+#pragma unroll
+                for (int g = 0; g < NLD; ++g) {
+                    uint32_t r[8];
+                    tmem_ld8(taddr + 8 * g, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[8 * g + u] += __uint_as_float(r[u]);       // fp32 RN promotion
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+            }
+            const long long row = (long long)m_blk * BM + quarter * 32 + lane;
+            const int n0 = n_blk * BN + half * HALF;
+            if (row < M) {
+                float *dst = C + (size_t)row * ldc + n0;
+#pragma unroll
+                for (int j = 0; j < HALF; j += 4) {
+                    float4 v;
+                    float *pv = reinterpret_cast<float *>(&v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float x = 0.f;
+                        if (n0 + j + u < N) {
+                            x = fmaf(acc[j + u], out_scale, bias[n0 + j + u]);
+                            if (leaky) x = x > 0.f ? x : 0.01f * x;
+                        }
+                        pv[u] = x;
+                    }
+                    if (n0 + j + 3 < N) {
+                        *reinterpret_cast<float4 *>(dst + j) = v;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (n0 + j + u < N) dst[j + u] = pv[u];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// fp32 weights [N][K] -> fp16 [Npad][2K] = (hi | lo) of w * 2^s; rows >= N are zero
+__global__ void split_weights_kernel(const float *__restrict__ W, int N, int Npad, int K, float scale, __half *__restrict__ out)
+{
+    const long long total = (long long)Npad * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / K;
+        const int k = (int)(i - n * K);
+        const float w = n < N ? W[i] * scale : 0.f;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        out[(size_t)n * 2 * K + k] = hi;
+        out[(size_t)n * 2 * K + K + k] = lo;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(CUtensorMap *map, const void *base, long long rows, long long cols, int box_rows)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GAD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        GAD_REQUIRE(p && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        gad_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box=%dx%d)", (int)rc, rows, cols,
+                      BK, box_rows);
+        return GAD_ECUDA;
+    }
+    return GAD_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host interface used by qnet.cu
+// ---------------------------------------------------------------------------------------------
+int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K)
+{
+    GAD_REQUIRE(K % BK == 0, "tcgen05 layer: K=%d must be a multiple of %d", K, BK);
+    L->N = N;
+    L->K = K;
+    L->BN = TC_BN;
+    L->Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
+    float mx = 0.f;
+    for (size_t i = 0; i < (size_t)N * K; ++i) mx = fmaxf(mx, fabsf(h_W[i]));
+    int s = 0;
+    if (mx > 0.f) s = (int)floorf(log2f(32768.f / mx));
+    if (s > 60) s = 60;
+    if (s < -60) s = -60;
+    L->scale = ldexpf(1.f, s);
+    L->inv_scale = ldexpf(1.f, -s);
+    GAD_CUDA(cudaMalloc((void **)&L->W2, (size_t)L->Npad * 2 * K * sizeof(__half)));
+    split_weights_kernel<<<GAD_NUM_SMS * 8, 256>>>(d_W, N, L->Npad, K, L->scale, (__half *)L->W2);
+    GAD_LAUNCH_CHECK();
+    GAD_CUDA(cudaDeviceSynchronize());
+    int rc = encode_map((CUtensorMap *)L->map_b, L->W2, L->Npad, 2ll * K, TC_BN);
+    if (rc) return rc;
+    GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<TC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<TC_BN>::SMEM));
+    return GAD_OK;
+}
+
+void tc_layer_free(TcLayer *L)
+{
+    if (L->W2) cudaFree(L->W2);
+    L->W2 = nullptr;
+}
+
+int tc_layer_bind_a(TcLayer *L, const void *d_A2, long long rows)
+{
+    return encode_map((CUtensorMap *)L->map_a, d_A2, rows, 2ll * L->K, BM);
+}
+
+int tc_layer_run(const TcLayer *L, const float *d_bias, float *d_C, int ldc, const int32_t *d_m, long long m_max,
+                 int leaky, cudaStream_t st)
+{
+    const long long tiles = ((m_max + BM - 1) / BM) * ((L->N + TC_BN - 1) / TC_BN);
+    if (tiles == 0) return GAD_OK;
+    const unsigned grid = (unsigned)(tiles < GAD_NUM_SMS ? tiles : GAD_NUM_SMS);
+    gemm_split_f16_kernel<TC_BN><<<grid, 64 + 32 * EPI_WARPS, Cfg<TC_BN>::SMEM, st>>>(*(const CUtensorMap *)L->map_a,
+                                                                       *(const CUtensorMap *)L->map_b, d_bias,
+                                                                       L->inv_scale, d_C, ldc, d_m, m_max, L->N, L->K,
+                                                                       leaky);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}

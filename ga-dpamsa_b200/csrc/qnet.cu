@@ -18,8 +18,11 @@
 //   * episodes run in lock-step on device with an active list that shrinks as episodes finish; the
 //     host only polls the active count.
 #include "gad_common.cuh"
+#include "gemm_tc.cuh"
 
+#include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -35,6 +38,8 @@ struct gad_qnet {
     long long cap = 0;
     uint8_t *tok = nullptr;
     float *Z = nullptr, *H1 = nullptr, *H2 = nullptr, *Q = nullptr;
+    __half *Z2 = nullptr;            // (hi | lo) fp16 split of Z, [cap][2K]: A operand of the tcgen05 l1
+    TcLayer *tc1 = nullptr;          // NULL = fp32 SIMT l1 (GAD_QNET_SIMT=1)
     int32_t *act = nullptr;
     // episode state for `ecap` episodes
     long long ecap = 0;
@@ -85,7 +90,8 @@ __device__ __forceinline__ int build_tokens(uint8_t *tok, const uint8_t *sub, co
 
 __global__ void __launch_bounds__(256)
 encode_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
-              const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout)
+              const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
+              __half *__restrict__ Z2out)
 {
     extern __shared__ float smem[];
     const int L = net.L;
@@ -181,9 +187,19 @@ encode_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int3
                 float v = d0 * d0 + d1 * d1;
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
                 const float rstd = rsqrtf(v * (1.f / QN_D) + 1e-6f);       // LayerNorm(eps=1e-6), models.py:166
-                float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D;
-                z[lane] = d0 * rstd * g0 + be0;
-                z[lane + 32] = d1 * rstd * g1 + be1;
+                const float z0 = d0 * rstd * g0 + be0, z1 = d1 * rstd * g1 + be1;
+                if (Z2out) {                                   // x = hi + lo in fp16 for the tensor-core l1
+                    __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D, *zl = zh + net.K;
+                    const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
+                    zh[lane] = h0;
+                    zh[lane + 32] = h1;
+                    zl[lane] = __float2half_rn(z0 - __half2float(h0));
+                    zl[lane + 32] = __float2half_rn(z1 - __half2float(h1));
+                } else {
+                    float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D;
+                    z[lane] = z0;
+                    z[lane + 32] = z1;
+                }
             }
             __syncwarp();
         }
@@ -464,12 +480,17 @@ int upload(float **dst, const float *src, size_t n)
 int ensure_states(gad_qnet *q, long long B)
 {
     if (B <= q->cap) return GAD_OK;
-    cudaFree(q->tok); cudaFree(q->Z); cudaFree(q->H1); cudaFree(q->H2); cudaFree(q->Q); cudaFree(q->act);
-    q->tok = nullptr; q->Z = q->H1 = q->H2 = q->Q = nullptr; q->act = nullptr;
+    cudaFree(q->tok); cudaFree(q->Z); cudaFree(q->Z2); cudaFree(q->H1); cudaFree(q->H2); cudaFree(q->Q); cudaFree(q->act);
+    q->tok = nullptr; q->Z = q->H1 = q->H2 = q->Q = nullptr; q->act = nullptr; q->Z2 = nullptr;
     q->cap = 0;
     int rc;
     if ((rc = dev_alloc(&q->tok, (size_t)B * q->L))) return rc;
-    if ((rc = dev_alloc(&q->Z, (size_t)B * q->K))) return rc;
+    if (q->tc1) {
+        const long long rows = (B + 127) / 128 * 128;      // whole TMA boxes stay inside the allocation
+        if ((rc = dev_alloc(&q->Z2, (size_t)rows * 2 * q->K))) return rc;
+        GAD_CUDA(cudaMemset(q->Z2, 0, (size_t)rows * 2 * q->K * sizeof(__half)));
+        if ((rc = tc_layer_bind_a(q->tc1, q->Z2, rows))) return rc;
+    } else if ((rc = dev_alloc(&q->Z, (size_t)B * q->K))) return rc;
     if ((rc = dev_alloc(&q->H1, (size_t)B * q->h1))) return rc;
     if ((rc = dev_alloc(&q->H2, (size_t)B * q->h2))) return rc;
     if ((rc = dev_alloc(&q->Q, (size_t)B * q->A))) return rc;
@@ -510,11 +531,16 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
     if (smem > 48 * 1024)
         GAD_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     long long grid = n_max < (long long)GAD_NUM_SMS * 16 ? n_max : (long long)GAD_NUM_SMS * 16;
-    encode_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z);
+    encode_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
     GAD_LAUNCH_CHECK();
     const unsigned mt = (unsigned)((n_max + GM_BM - 1) / GM_BM);
-    dense_kernel<<<dim3((q->h1 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->Z, q->W1, q->b1, q->H1, n_ptr, n_max, q->h1,
-                                                                        q->K, 1);
+    if (q->tc1) {
+        int rc = tc_layer_run(q->tc1, q->b1, q->H1, q->h1, n_ptr, n_max, 1, st);
+        if (rc) return rc;
+    } else {
+        dense_kernel<<<dim3((q->h1 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->Z, q->W1, q->b1, q->H1, n_ptr, n_max,
+                                                                            q->h1, q->K, 1);
+    }
     dense_kernel<<<dim3((q->h2 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->H1, q->W2, q->b2, q->H2, n_ptr, n_max, q->h2,
                                                                         q->h1, 1);
     head_step_kernel<<<(unsigned)((n_max + 7) / 8), 256, 0, st>>>(*q, q->H2, n_ptr, n_max, max_value, Qout, act_out,
@@ -617,6 +643,11 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
     up(&q->b2, h_weights[13], h2);
     up(&q->W3, h_weights[14], (size_t)q->A * h2);
     up(&q->b3, h_weights[15], q->A);
+    const char *simt = getenv("GAD_QNET_SIMT");
+    if (!rc && !(simt && simt[0] == '1')) {                 // l1 on tcgen05 (default); GAD_QNET_SIMT=1 keeps the fp32 SIMT tiles
+        q->tc1 = new TcLayer();
+        rc = tc_layer_init(q->tc1, q->W1, h_weights[10], h1, q->K);
+    }
     if (!rc) rc = dev_alloc(&q->counts, 2);
     if (!rc && cudaMallocHost((void **)&q->h_count, 2 * sizeof(int32_t)) != cudaSuccess) {
         gad_set_error("gad_qnet_create: cudaMallocHost failed");
@@ -635,6 +666,11 @@ extern "C" int gad_qnet_destroy(gad_qnet *q)
     if (!q) return GAD_OK;
     float *f[] = {q->X, q->T, q->VF, q->ln2_g, q->ln2_b, q->W1, q->b1, q->W2, q->b2, q->W3, q->b3, q->Z, q->H1, q->H2, q->Q};
     for (float *p : f) cudaFree(p);
+    cudaFree(q->Z2);
+    if (q->tc1) {
+        tc_layer_free(q->tc1);
+        delete q->tc1;
+    }
     cudaFree(q->tok); cudaFree(q->act); cudaFree(q->sub); cudaFree(q->heads); cudaFree(q->aligned);
     cudaFree(q->steps); cudaFree(q->list0); cudaFree(q->list1); cudaFree(q->counts);
     if (q->h_count) cudaFreeHost(q->h_count);

@@ -315,6 +315,28 @@ def test_qnet_golden_vectors(gpu, weight_files):
         assert np.all(np.abs(q - q64) <= 1e-3 * np.abs(q64) + 1e-5 * max_value)
 
 
+def test_qnet_tensor_core_l1_against_fp32_tiles(gpu, weight_files, monkeypatch):
+    """The tcgen05 split-fp16 l1 (hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM) agrees with the fp32
+    SIMT tiles to fp32 rounding on every recorded state, for every batch size class (partial tiles)."""
+    from DPAMSA.dqn import QNet
+    z = np.load(os.path.join(GOLDEN, "qnet_vectors.npz"))
+    for (rows, cols), (name, sd) in weight_files.items():
+        states = z["states_%dx%d" % (rows, cols)].astype(np.uint8)
+        max_value = cols * rows * (rows - 1) / 2 * 4
+        monkeypatch.setenv("GAD_QNET_SIMT", "1")
+        q_simt, a_simt = QNet(sd, rows, cols).forward(states, max_value)
+        monkeypatch.setenv("GAD_QNET_SIMT", "0")
+        net = QNet(sd, rows, cols)
+        for n in (1, 3, len(states)):
+            q_tc, a_tc = net.forward(states[:n], max_value)
+            assert np.all(np.abs(q_tc - q_simt[:n]) <= 2e-5 * np.abs(q_simt[:n]) + 1e-6 * max_value), \
+                np.abs(q_tc - q_simt[:n]).max()
+            assert np.array_equal(a_tc, a_simt[:n])
+        big = np.concatenate([states] * (300 // len(states) + 1))[:300]          # 3 M-tiles, the last one partial
+        q_big, _ = net.forward(big, max_value)
+        assert np.array_equal(q_big[:len(states)], net.forward(states, max_value)[0])
+
+
 def test_dqn_and_environment_facade(gpu, weight_files, primitives):
     from DPAMSA.dqn import DQN
     from DPAMSA.env import Environment
