@@ -152,8 +152,9 @@ class GA:
             self._dev.hof_valid = False
 
     # ------------------------------------------------------------------ a3
-    def generate_population(self):
-        """GA.py:71-94 through the CPython-compatible MT19937 replay (same draws as the reference)."""
+    def _generate_host(self):
+        """GA.py:71-94 through the CPython-compatible MT19937 replay (same draws as the reference):
+        host arrays (boards uint8 [P,R,stride], rowlen int32 [P,R])."""
         nat.require_device()
         seqs = [[nucleotides_map[nuc] for nuc in seq] for seq in self.sequences]      # KeyError like GA.py:79
         R = len(seqs)
@@ -174,10 +175,11 @@ class GA:
         nat.call("gad_mt_population_host", state.ctypes.data, seq_arr.ctypes.data, seqlen.ctypes.data, cstride,
                  ngaps.ctypes.data, R, P, n_clone, boards.ctypes.data, rowlen.ctypes.data, stride)
         _mt_restore(state, meta)
-        hof_keep = self._dev
-        self._dev = None
-        self._adopt(boards, rowlen)
-        del hof_keep
+        return boards, rowlen
+
+    def generate_population(self):
+        """GA.py:71-94: n_clone exact copies, then gap-inserted individuals; uploaded to the device."""
+        self._adopt(*self._generate_host())
 
     # ------------------------------------------------------------------ a4 + a8
     def update_hall_of_fame(self):

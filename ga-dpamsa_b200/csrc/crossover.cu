@@ -13,8 +13,8 @@ namespace {
 // kind 1 (vertical, not in the reference code - supplement table A5): every row keeps parent1's
 // first `cut` cells and continues with parent2's cells from `cut` on.
 __global__ void __launch_bounds__(256)
-crossover_kernel(uint8_t *boards, int32_t *rowlen, long long n_parents,
-                 const int32_t *__restrict__ plan, long long n_children, int R, int stride, int kind)
+crossover_kernel(const uint8_t *src_boards, const int32_t *src_rowlen, uint8_t *boards, int32_t *rowlen,
+                 long long n_parents, const int32_t *__restrict__ plan, long long n_children, int R, int stride, int kind)
 {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -25,13 +25,13 @@ crossover_kernel(uint8_t *boards, int32_t *rowlen, long long n_parents,
         const int r = (int)(u - c * R);
         const int p1 = plan[3 * c + 0], p2 = plan[3 * c + 1], cut = plan[3 * c + 2];
         // parents are rectangular here (selection's fitness pass has just cleaned them)
-        const int w1 = rowlen[(size_t)p1 * R + r], w2 = rowlen[(size_t)p2 * R + r];
+        const int w1 = src_rowlen[(size_t)p1 * R + r], w2 = src_rowlen[(size_t)p2 * R + r];
         const int wmax = max(w1, w2);
         const int n16 = min(stride >> 4, (wmax + 15) >> 4);
         const long long child = n_parents + c;
         uint4 *d4 = reinterpret_cast<uint4 *>(boards + ((size_t)child * R + r) * stride);
-        const uint4 *a4 = reinterpret_cast<const uint4 *>(boards + ((size_t)p1 * R + r) * stride);
-        const uint4 *b4 = reinterpret_cast<const uint4 *>(boards + ((size_t)p2 * R + r) * stride);
+        const uint4 *a4 = reinterpret_cast<const uint4 *>(src_boards + ((size_t)p1 * R + r) * stride);
+        const uint4 *b4 = reinterpret_cast<const uint4 *>(src_boards + ((size_t)p2 * R + r) * stride);
         int len;
         if (kind == 0) {
             const bool first = r < cut;
@@ -96,8 +96,31 @@ extern "C" int gad_crossover(uint8_t *d_boards, int32_t *d_rowlen, int64_t n_par
     long long blocks = (units + 7) / 8;
     const long long cap = (long long)GAD_NUM_SMS * 8 * 4;
     if (blocks > cap) blocks = cap;
-    crossover_kernel<<<(unsigned)blocks, 256, 0, gad_stream(stream)>>>(d_boards, d_rowlen, n_parents, d_plan,
-                                                                        n_children, R, stride, kind);
+    crossover_kernel<<<(unsigned)blocks, 256, 0, gad_stream(stream)>>>(d_boards, d_rowlen, d_boards, d_rowlen, n_parents,
+                                                                        d_plan, n_children, R, stride, kind);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// Sharded form: parents come from a separate (all-gathered) survivor buffer, children are written to
+// slots [dst_first, dst_first + n_children) of this rank's population buffer.
+extern "C" int gad_crossover_from(const uint8_t *d_src_boards, const int32_t *d_src_rowlen, uint8_t *d_dst_boards,
+                                  int32_t *d_dst_rowlen, int64_t dst_first, const int32_t *d_plan, int64_t n_children,
+                                  int R, int stride, int kind, void *stream)
+{
+    GAD_REQUIRE(d_src_boards && d_src_rowlen && d_dst_boards && d_dst_rowlen && (d_plan || n_children == 0),
+                "gad_crossover_from: null device pointer");
+    GAD_REQUIRE(dst_first >= 0 && n_children >= 0 && R >= 1 && stride >= 16 && stride % 16 == 0,
+                "gad_crossover_from: bad shape");
+    GAD_REQUIRE(kind == 0 || kind == 1, "gad_crossover_from: kind must be 0 (horizontal) or 1 (vertical)");
+    if (n_children == 0) return GAD_OK;
+    const long long units = (long long)n_children * R;
+    long long blocks = (units + 7) / 8;
+    const long long cap = (long long)GAD_NUM_SMS * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    crossover_kernel<<<(unsigned)blocks, 256, 0, gad_stream(stream)>>>(d_src_boards, d_src_rowlen, d_dst_boards,
+                                                                        d_dst_rowlen, dst_first, d_plan, n_children, R,
+                                                                        stride, kind);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -93,7 +93,7 @@ encode_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int3
               const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
               __half *__restrict__ Z2out)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int L = net.L;
     const int nw = blockDim.x >> 5;
     float *Pw = smem;                                         // [nw][L][ENC_QT]
@@ -202,6 +202,193 @@ encode_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int3
                 }
             }
             __syncwarp();
+        }
+    }
+}
+
+// Tiled encoder (the one that runs for the reference's window sizes): one CTA per state.
+//   stage 0  tokens, the list of valid (unmasked) keys, and their VF rows -> shared memory
+//   per block of ENC_RB query rows:
+//     stage A  one warp per row: logits gathered from T, fp32 softmax numerators e[k][row] -> shared
+//              (transposed, so stage B reads them as the A operand), row sums kept
+//     stage B  [ENC_RB x nk] . [nk x 64] register-tiled product (6 rows x 4 channels per thread,
+//              24 FMA per 4 shared loads), then /sum + residual + LayerNorm and the store
+// Masked keys contribute exp(-1e9 - max) == 0 in the reference; they are simply not in the key list.
+template <int RB> struct EncTile {
+    static constexpr int THREADS = RB / 96 * 256;          // 6 rows x 4 channels per thread in stage B
+    static constexpr int PS = RB + 2;                      // row stride of the transposed numerators (even)
+};
+
+template <int RB>
+__global__ void __launch_bounds__(EncTile<RB>::THREADS)
+encode_tiled_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
+                    const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
+                    __half *__restrict__ Z2out)
+{
+    constexpr int PS = EncTile<RB>::PS;
+    constexpr int NW = EncTile<RB>::THREADS / 32;
+    extern __shared__ __align__(16) float smem[];
+    const int L = net.L;
+    float *VFs = smem;                                   // [L][64]
+    float *Pt = VFs + (size_t)L * QN_D;                  // [L][PS]
+    float *rsum = Pt + (size_t)L * PS;                   // [RB]
+    int *kj = reinterpret_cast<int *>(rsum + RB);        // [L] valid key positions
+    int *koff = kj + L;                                  // [L] tok[j] * L + j of every valid key
+    uint8_t *tok = reinterpret_cast<uint8_t *>(koff + L);  // [L]
+    __shared__ int s_nk;
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = lane & 15, ty = warp * 2 + (lane >> 4);          // stage-B tile: rows ty*6.., channels tx*4..
+
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();
+        if (tok_in) {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
+            __syncthreads();
+        } else {
+            const int e = active[row];
+            build_tokens(tok, net.sub + (size_t)e * net.rows * net.cols, net.heads + (size_t)e * net.rows, net.rows,
+                         net.cols, L);
+        }
+        if (warp == 0) {                                 // ordered list of unmasked keys
+            int base = 0;
+            for (int j0 = 0; j0 < L; j0 += 32) {
+                const int j = j0 + lane;
+                const bool v = j < L && tok[j] != 0;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, v);
+                if (v) kj[base + __popc(m & ((1u << lane) - 1u))] = j;
+                base += __popc(m);
+            }
+            if (lane == 0) s_nk = base;
+        }
+        __syncthreads();
+        int nk = s_nk;
+        const bool all_masked = nk == 0;                 // softmax over all -1e9 is uniform (never an environment state)
+        if (all_masked) {
+            for (int j = threadIdx.x; j < L; j += blockDim.x) kj[j] = j;
+            nk = L;
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < nk * (QN_D / 4); i += blockDim.x) {
+            const int k = i >> 4, c4 = i & 15;
+            const int j = kj[k];
+            reinterpret_cast<float4 *>(VFs)[i] =
+                __ldg(reinterpret_cast<const float4 *>(net.VF + ((size_t)tok[j] * L + j) * QN_D) + c4);
+        }
+        for (int k = threadIdx.x; k < nk; k += blockDim.x) {          // offset of key k inside a row of T
+            const int j = kj[k];
+            koff[k] = tok[j] * L + j;
+        }
+        for (int rb = 0; rb < L; rb += RB) {
+            __syncthreads();
+            // ---- stage A: one warp per pair of rows; a lane keeps logits k = lane + 32u in registers (all loads of
+            // the pair are issued before the first use), softmax numerators go to shared memory transposed
+            constexpr int U = RB / 32;
+            for (int r0 = 2 * warp; r0 < RB; r0 += 2 * NW) {
+                float sv[2][U];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = rb + r0 + h;
+                    const bool live = i < L;
+                    const int ii = live ? i : 0;
+                    const float *trow = net.T + ((size_t)tok[ii] * L + ii) * (QN_VOCAB * L);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = lane + 32 * u;
+                        float v = -INFINITY;
+                        if (live && k < nk) v = all_masked ? -1e9f : __ldg(trow + koff[k]);
+                        sv[h][u] = v;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = r0 + h;
+                    if (rb + r >= L) {                   // rows beyond the state: stage B multiplies zeros
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (lane + 32 * u < nk) Pt[(lane + 32 * u) * PS + r] = 0.f;
+                        if (lane == 0) rsum[r] = 1.f;
+                        continue;
+                    }
+                    float mx = sv[h][0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u) mx = fmaxf(mx, sv[h][u]);
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+                    float sum = 0.f;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = lane + 32 * u;
+                        if (k < nk) {
+                            const float ev = expf(sv[h][u] - mx);
+                            Pt[k * PS + r] = ev;
+                            sum += ev;
+                        }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                    if (lane == 0) rsum[r] = sum;
+                }
+            }
+            __syncthreads();
+            // ---- stage B
+            float acc[6][4];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+            const float *pp = Pt + ty * 6;
+            const float *vp = VFs + tx * 4;
+#pragma unroll 4
+            for (int k = 0; k < nk; ++k) {
+                const float2 p01 = *reinterpret_cast<const float2 *>(pp + k * PS);
+                const float2 p23 = *reinterpret_cast<const float2 *>(pp + k * PS + 2);
+                const float2 p45 = *reinterpret_cast<const float2 *>(pp + k * PS + 4);
+                const float4 v = *reinterpret_cast<const float4 *>(vp + k * QN_D);
+                const float p[6] = {p01.x, p01.y, p23.x, p23.y, p45.x, p45.y};
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    acc[a][0] = fmaf(p[a], v.x, acc[a][0]);
+                    acc[a][1] = fmaf(p[a], v.y, acc[a][1]);
+                    acc[a][2] = fmaf(p[a], v.z, acc[a][2]);
+                    acc[a][3] = fmaf(p[a], v.w, acc[a][3]);
+                }
+            }
+            const float4 g = *reinterpret_cast<const float4 *>(net.ln2_g + tx * 4);
+            const float4 be = *reinterpret_cast<const float4 *>(net.ln2_b + tx * 4);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const int r = ty * 6 + a, i = rb + r;
+                // all 16 lanes of the half-warp share the row: the guard is uniform across the shuffles below
+                const bool live = i < L;
+                const int ii = live ? i : L - 1;
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(net.X + ((size_t)tok[ii] * L + ii) * QN_D) + tx);
+                const float inv = 1.f / rsum[r];
+                const float y0 = fmaf(acc[a][0], inv, x.x), y1 = fmaf(acc[a][1], inv, x.y);
+                const float y2 = fmaf(acc[a][2], inv, x.z), y3 = fmaf(acc[a][3], inv, x.w);
+                float sm = (y0 + y1) + (y2 + y3);
+                for (int o = 8; o > 0; o >>= 1) sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o);
+                const float mu = sm * (1.f / QN_D);
+                const float d0 = y0 - mu, d1 = y1 - mu, d2 = y2 - mu, d3 = y3 - mu;
+                float vr = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+                for (int o = 8; o > 0; o >>= 1) vr += __shfl_xor_sync(0xFFFFFFFFu, vr, o);
+                const float rstd = rsqrtf(vr * (1.f / QN_D) + 1e-6f);          // LayerNorm(eps=1e-6), models.py:166
+                const float z[4] = {d0 * rstd * g.x + be.x, d1 * rstd * g.y + be.y, d2 * rstd * g.z + be.z,
+                                    d3 * rstd * g.w + be.w};
+                if (!live) continue;
+                if (Z2out) {                                                   // x = hi + lo in fp16 for the tensor-core l1
+                    __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D + tx * 4, *zl = zh + net.K;
+                    __half h[4], l[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        h[b] = __float2half_rn(z[b]);
+                        l[b] = __float2half_rn(z[b] - __half2float(h[b]));
+                    }
+                    *reinterpret_cast<uint2 *>(zh) = *reinterpret_cast<const uint2 *>(h);
+                    *reinterpret_cast<uint2 *>(zl) = *reinterpret_cast<const uint2 *>(l);
+                } else {
+                    *reinterpret_cast<float4 *>(Zout + (size_t)row * net.K + (size_t)i * QN_D + tx * 4) =
+                        make_float4(z[0], z[1], z[2], z[3]);
+                }
+            }
         }
     }
 }
@@ -519,19 +706,48 @@ int ensure_episodes(gad_qnet *q, long long M)
 
 int encode_smem_bytes(int L, int warps) { return warps * L * ENC_QT * (int)sizeof(float) + ((L + 15) & ~15); }
 
+int encode_tiled_smem_bytes(int L, int RB)
+{
+    return (L * QN_D + L * (RB + 2) + RB + 2 * L) * (int)sizeof(float) + ((L + 15) & ~15);
+}
+
+template <int RB>
+int launch_encode_tiled(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const int32_t *n_ptr,
+                        long long n_max, cudaStream_t st)
+{
+    const int bytes = encode_tiled_smem_bytes(q->L, RB);
+    if (bytes > 48 * 1024)
+        GAD_CUDA(cudaFuncSetAttribute(encode_tiled_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    long long per_sm = (220 * 1024) / bytes;
+    const long long by_threads = 2048 / EncTile<RB>::THREADS;
+    if (per_sm > by_threads) per_sm = by_threads;
+    const long long grid = n_max < (long long)GAD_NUM_SMS * per_sm ? n_max : (long long)GAD_NUM_SMS * per_sm;
+    encode_tiled_kernel<RB><<<(unsigned)grid, EncTile<RB>::THREADS, bytes, st>>>(*q, tok_in, active, n_ptr, n_max,
+                                                                                 q->Z, q->Z2);
+    return GAD_OK;
+}
+
 // one forward over `n` rows (device count in n_ptr, or n_fixed): tokens/episodes -> H2, then the head kernel
 int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const int32_t *n_ptr, long long n_max,
                    float max_value, float *Qout, int32_t *act_out, int32_t *next_active, int32_t *next_count,
                    cudaStream_t st)
 {
-    int warps = 8;
-    while (warps > 1 && encode_smem_bytes(q->L, warps) > 200 * 1024) warps >>= 1;
-    const int smem = encode_smem_bytes(q->L, warps);
-    GAD_REQUIRE(smem <= 227 * 1024, "agent window too large for the encoder kernel (L=%d)", q->L);
-    if (smem > 48 * 1024)
-        GAD_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    long long grid = n_max < (long long)GAD_NUM_SMS * 16 ? n_max : (long long)GAD_NUM_SMS * 16;
-    encode_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
+    if (q->L <= 96 && encode_tiled_smem_bytes(q->L, 96) <= 220 * 1024) {
+        int rc = launch_encode_tiled<96>(q, tok_in, active, n_ptr, n_max, st);
+        if (rc) return rc;
+    } else if (q->L <= 192 && encode_tiled_smem_bytes(q->L, 192) <= 220 * 1024) {
+        int rc = launch_encode_tiled<192>(q, tok_in, active, n_ptr, n_max, st);
+        if (rc) return rc;
+    } else {                                             // very large agent windows: warp-per-row fallback
+        int warps = 8;
+        while (warps > 1 && encode_smem_bytes(q->L, warps) > 200 * 1024) warps >>= 1;
+        const int smem = encode_smem_bytes(q->L, warps);
+        GAD_REQUIRE(smem <= 227 * 1024, "agent window too large for the encoder kernel (L=%d)", q->L);
+        if (smem > 48 * 1024)
+            GAD_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        long long grid = n_max < (long long)GAD_NUM_SMS * 16 ? n_max : (long long)GAD_NUM_SMS * 16;
+        encode_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
+    }
     GAD_LAUNCH_CHECK();
     const unsigned mt = (unsigned)((n_max + GM_BM - 1) / GM_BM);
     if (q->tc1) {

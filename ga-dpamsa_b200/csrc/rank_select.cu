@@ -452,7 +452,10 @@ __global__ void hof_commit_kernel(const uint8_t *__restrict__ boards, const int 
 
 inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+__global__ void copy_winner_kernel(const Stats *st, int32_t *out) { *out = st->winner; }
+
 }  // namespace
+
 
 // =============================================================================================
 // C ABI
@@ -561,6 +564,31 @@ extern "C" int gad_compact(const uint8_t *d_src_boards, const int32_t *d_src_row
                                                                       d_src_al, d_keep, d_dst, P, R, stride,
                                                                       d_dst_boards, d_dst_rowlen, d_dst_sp, d_dst_em,
                                                                       d_dst_al);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// Index of the best element of population (+ hall-of-fame record as element P) - the decision of
+// GA.update_hall_of_fame without the board copy (used when the boards are sharded over several GPUs).
+extern "C" int gad_hof_argbest(const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, int64_t P, int mode,
+                               const int32_t *d_hof, int32_t *d_winner, void *d_ws, size_t ws_bytes, void *stream)
+{
+    GAD_REQUIRE(d_sp && d_em && d_al && d_winner, "gad_hof_argbest: null device pointer");
+    GAD_REQUIRE(mode >= GAD_MODE_SP && mode <= GAD_MODE_MO, "gad_hof_argbest: unknown mode %d", mode);
+    GAD_REQUIRE(P >= 1, "gad_hof_argbest: empty population");
+    Workspace w;
+    int rc = open_workspace(w, d_ws, ws_bytes, P + 1, "gad_hof_argbest");
+    if (rc) return rc;
+    cudaStream_t st = gad_stream(stream);
+    double *key = reinterpret_cast<double *>(w.k0);
+    const long long n = P + (d_hof ? 1 : 0);
+    if ((rc = compute_keys(d_sp, d_em, d_al, d_hof, P, mode, key, w, st))) return rc;
+    GAD_CUDA(cudaMemsetAsync(&w.stats->ticket, 0, sizeof(unsigned), st));
+    unsigned blocks = blocks_for(n, 256 * 4);
+    if (blocks > (unsigned)kArgBlocks) blocks = kArgBlocks;
+    if (blocks < 1) blocks = 1;
+    argbest_kernel<<<blocks, 256, 0, st>>>(key, n, w.part_key, w.part_idx, w.stats);
+    copy_winner_kernel<<<1, 1, 0, st>>>(w.stats, d_winner);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -279,12 +279,47 @@ class DevicePopulation:
                  int(rw), int(cw), MODE_ID[mode], int(match), int(mismatch), int(gap), nat.ptr(tile), self._stream())
         return tile
 
-    def mutate(self, qnet, idx, tile, max_value: float):
+    def compact_with(self, keep: torch.Tensor):
+        """Keep the local boards flagged in `keep` (bool [n]), in order (sharded selection)."""
+        self._workspace()
+        n = self.n
+        k8 = keep.to(torch.uint8).contiguous()
+        dst = (torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - keep.to(torch.int32)).contiguous()
+        if self.alt is None or self.alt.boards.shape != self.cur.boards.shape:
+            self.alt = _Buffer(self.capacity, self.R, self.stride, self.device)
+        s, d = self.cur, self.alt
+        nat.call("gad_compact", nat.ptr(s.boards), nat.ptr(s.rowlen), nat.ptr(s.sp), nat.ptr(s.em), nat.ptr(s.al),
+                 nat.ptr(k8), nat.ptr(dst), n, self.R, self.stride, nat.ptr(d.boards), nat.ptr(d.rowlen),
+                 nat.ptr(d.sp), nat.ptr(d.em), nat.ptr(d.al), self._stream())
+        self.cur, self.alt = d, s
+        self.n = int(keep.sum().item())
+
+    def crossover_from(self, src_boards, src_rowlen, pos, plan: np.ndarray, kind: int = 0):
+        """Append children whose parents are rows of an all-gathered survivor buffer; `plan` holds
+        logical parent indices, `pos` maps a logical index to its row in `src_boards`."""
+        n_children = int(plan.shape[0])
+        if n_children == 0:
+            return
+        assert src_boards.shape[1] == self.R and src_boards.shape[2] == self.stride, "ranks disagree on the board stride"
+        self.ensure_capacity(self.n + n_children)
+        d_plan = torch.from_numpy(np.ascontiguousarray(plan)).to(self.device)
+        d_plan[:, 0] = pos[d_plan[:, 0].long()].to(torch.int32)
+        d_plan[:, 1] = pos[d_plan[:, 1].long()].to(torch.int32)
+        d_plan = d_plan.contiguous()
+        src_boards, src_rowlen = src_boards.contiguous(), src_rowlen.contiguous()
+        b = self.cur
+        nat.call("gad_crossover_from", nat.ptr(src_boards), nat.ptr(src_rowlen), nat.ptr(b.boards), nat.ptr(b.rowlen),
+                 self.n, nat.ptr(d_plan), n_children, self.R, self.stride, int(kind), self._stream())
+        torch.cuda.current_stream().synchronize()          # src buffers are temporaries of the caller
+        self.n += n_children
+
+    def mutate(self, qnet, idx, tile, max_value: float, width=None):
         """GA.py:335-373 for the listed individuals with their tiles; boards grow in place."""
         M = int(tile.shape[0])
         if M == 0:
             return
-        width = int(self.cur.rowlen[:self.n].max().item())
+        if width is None:
+            width = int(self.cur.rowlen[:self.n].max().item())
         self.ensure_stride(width + (qnet.rows - 1) * qnet.cols)
         self._status.zero_()
         fw = ctypes.c_int64(0)
@@ -294,3 +329,47 @@ class DevicePopulation:
         self.forwards += fw.value
         if int(self._status.item()) & 1:
             raise nat.GadCapacityError("a mutated row outgrew the board stride")
+
+
+class Ranker:
+    """Ranking / selection / hall-of-fame decisions on explicit score tensors (used on the all-gathered
+    global scores of a sharded population)."""
+
+    def __init__(self, capacity: int, device):
+        self.capacity = capacity
+        self.device = device
+        nbytes = ctypes.c_size_t(0)
+        nat.call("gad_workspace_bytes", capacity, ctypes.byref(nbytes))
+        self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        self.keys = torch.empty(capacity + 1, dtype=torch.float64, device=device)
+        self.order = torch.empty(capacity + 1, dtype=torch.int32, device=device)
+        self.keep = torch.empty(capacity, dtype=torch.uint8, device=device)
+        self.dst = torch.empty(capacity, dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.winner = torch.zeros(1, dtype=torch.int32, device=device)
+        self.hof = torch.zeros(8, dtype=torch.int32, device=device)
+
+    def rank_order(self, scores, n, mode, k):
+        sp, em, al = scores
+        st = nat.current_stream_ptr()
+        nat.call("gad_rank_keys", nat.ptr(sp), nat.ptr(em), nat.ptr(al), n, MODE_ID[mode], None, nat.ptr(self.keys),
+                 nat.ptr(self.ws), self.ws.numel(), st)
+        nat.call("gad_rank_order", nat.ptr(self.keys), n, nat.ptr(self.order), nat.ptr(self.ws), self.ws.numel(), st)
+        return self.order[:min(k, n)]
+
+    def select_flags(self, scores, n, mode, top_n):
+        sp, em, al = scores
+        nat.call("gad_select", nat.ptr(sp), nat.ptr(em), nat.ptr(al), n, MODE_ID[mode], int(top_n), nat.ptr(self.keep),
+                 nat.ptr(self.dst), nat.ptr(self.count), nat.ptr(self.ws), self.ws.numel(), nat.current_stream_ptr())
+        return self.keep[:n], self.dst[:n], int(self.count.item())
+
+    def argbest(self, scores, n, mode, hof_score):
+        sp, em, al = scores
+        hof_ptr = None
+        if hof_score is not None:
+            self.hof.copy_(torch.tensor([1, hof_score[0], hof_score[1], hof_score[2], hof_score[3], 0, 0, 0],
+                                        dtype=torch.int32))
+            hof_ptr = nat.ptr(self.hof)
+        nat.call("gad_hof_argbest", nat.ptr(sp), nat.ptr(em), nat.ptr(al), n, MODE_ID[mode], hof_ptr,
+                 nat.ptr(self.winner), nat.ptr(self.ws), self.ws.numel(), nat.current_stream_ptr())
+        return int(self.winner.item())

@@ -1,0 +1,298 @@
+"""The generation loop with the population sharded over the GPUs of one box (one process per GPU,
+``torch.distributed``; NCCL on GPUs, gloo in the CPU tests of the host logic).
+
+Every individual carries its *logical* index - the position it has in the reference's single list
+(GA.py:54) - so all order-dependent decisions (stable sorts, first-maximum ties, survivors "in original
+order", crossover parents) are taken on score arrays arranged by logical index and are bit-identical
+to a single-GPU run for any world size. Physical placement is free: survivors stay on the rank that
+owns them, children are dealt out to refill every rank to its share.
+
+Per fitness pass : one all-gather of (sp, em, al, logical index) - 16 bytes per individual - and, when
+                   the hall of fame changes, one broadcast of the winner's board from its owner.
+Per generation   : one all-gather of the survivors' boards ("elite" exchange) so that each rank can
+                   build its children from any pair of parents.
+Fitness, tile search, Q-net episodes, compaction and crossover itself run locally with no collective.
+
+The algorithm is written against a small backend interface so that the exchange logic can be
+exercised on CPU (tests/test_sharded_cpu.py plugs the oracle in); ``DeviceBackend`` is the product.
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import config
+
+nucleotides_map = {'A': 1, 'T': 2, 'C': 3, 'G': 4, 'a': 1, 't': 2, 'c': 3, 'g': 4, '-': 5}
+
+
+def shard_bounds(total: int, world: int):
+    """Contiguous shares of `total` items: the first total % world ranks get one more."""
+    base, extra = divmod(total, world)
+    lo = [r * base + min(r, extra) for r in range(world + 1)]
+    return lo
+
+
+class ShardedGA:
+    """Same phases and results as ``GA`` (GA.py:38-545) over a sharded population."""
+
+    def __init__(self, sequences, mode, backend, group=None):
+        self.sequences = sequences
+        self.mode = mode
+        self.backend = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.population_size = config.POPULATION_SIZE
+        self.current_iteration = 0
+        self.n_global = 0
+        self.gidx = None             # logical index of every local individual (tensor on backend.device)
+        self.g_scores = None         # (sp, em, al) int32 tensors arranged by logical index
+        self.owner = None            # rank that owns each logical index
+        self.hof_board = None        # replicated on every rank: (boards uint8 [R, w] tensor)
+        self.hof_score = None        # (logical index, sp, em, al)
+        self.comm_bytes = 0          # bytes this rank received through collectives
+
+    # ------------------------------------------------------------------ collectives
+    def _all_gather_padded(self, t: torch.Tensor, counts):
+        """All-gather of per-rank tensors whose first dimension differs: pad to the largest, gather,
+        return the concatenation of the valid parts in rank order."""
+        if self.world == 1:
+            return t
+        mx = max(counts)
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(out, pad, group=self.group)
+        self.comm_bytes += pad.numel() * pad.element_size() * (self.world - 1)
+        return torch.cat([o[:c] for o, c in zip(out, counts)])
+
+    def _counts(self, n_local: int):
+        if self.world == 1:
+            return [n_local]
+        t = torch.tensor([n_local], dtype=torch.int64, device=self.backend.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return [int(o.item()) for o in out]
+
+    # ------------------------------------------------------------------ a3
+    def generate_population(self):
+        """Every rank replays the same `random` stream (GA.py:71-94) and keeps its slice."""
+        boards, rowlen = self.backend.generate_full_population(self.sequences, self.population_size)
+        P = boards.shape[0]
+        lo = shard_bounds(P, self.world)
+        a, b = lo[self.rank], lo[self.rank + 1]
+        self.backend.adopt(boards[a:b], rowlen[a:b], capacity=max(b - a, lo[1] - lo[0]))
+        self.gidx = torch.arange(a, b, dtype=torch.int64, device=self.backend.device)
+        self.n_global = P
+
+    # ------------------------------------------------------------------ a4 + a8
+    def calculate_fitness_score(self):
+        sp, em, al = self.backend.fitness()                       # local, no collective
+        counts = self._counts(int(self.gidx.numel()))
+        packed = torch.stack((sp.to(torch.int64), em.to(torch.int64), al.to(torch.int64), self.gidx), dim=1)
+        allp = self._all_gather_padded(packed, counts)
+        n = self.n_global
+        g = allp[:, 3]
+        dev = self.backend.device
+        self.g_scores = tuple(torch.zeros(n, dtype=torch.int32, device=dev).index_copy_(0, g, allp[:, k].to(torch.int32))
+                              for k in range(3))
+        owner_of_pos = torch.repeat_interleave(torch.arange(self.world, device=dev),
+                                               torch.tensor(counts, device=dev))
+        self.owner = torch.zeros(n, dtype=torch.int64, device=dev).index_copy_(0, g, owner_of_pos)
+        self.update_hall_of_fame()
+
+    def update_hall_of_fame(self):
+        """GA.py:110-136 on the gathered scores; the winner's board is broadcast by its owner."""
+        n = self.n_global
+        w = self.backend.hof_argbest(self.g_scores, n, self.mode, self.hof_score)
+        if w >= n:                                               # the old hall of fame keeps its place
+            self.hof_score = (n,) + tuple(self.hof_score[1:])
+            return
+        owner = int(self.owner[w].item())
+        sp, em, al = (int(t[w].item()) for t in self.g_scores)
+        if owner == self.rank:
+            local = int((self.gidx == w).nonzero()[0].item())
+            board = self.backend.board(local, al)
+        else:
+            board = torch.empty((self.backend.R, al), dtype=torch.uint8, device=self.backend.device)
+        if self.world > 1:
+            dist.broadcast(board, src=owner, group=self.group)
+            self.comm_bytes += board.numel()
+        self.hof_board = board
+        self.hof_score = (w, sp, em, al)
+
+    @property
+    def hall_of_fame(self):
+        if self.hof_board is None:
+            return []
+        idx, sp, em, al = self.hof_score
+        cs = em / al if al > 0 else 0
+        score = (idx, sp, cs) if self.mode == 'mo' else (idx, sp if self.mode == 'sp' else cs)
+        return ([row.tolist() for row in self.hof_board.cpu().numpy()], score)
+
+    @property
+    def population_score(self):
+        sp, em, al = (t.cpu().numpy() for t in self.g_scores)
+        out = []
+        for i in range(self.n_global):
+            cs = int(em[i]) / int(al[i]) if al[i] > 0 else 0
+            out.append((i, int(sp[i]), cs) if self.mode == 'mo' else (i, int(sp[i]) if self.mode == 'sp' else cs))
+        return out
+
+    # ------------------------------------------------------------------ a10
+    def selection(self):
+        """GA.py:232-260: the survivor set is decided on the global scores; every rank compacts its own."""
+        top_n = int(self.population_size * config.SELECTION_RATE)
+        keep, dst, count = self.backend.select_flags(self.g_scores, self.n_global, self.mode, top_n)
+        local_keep = keep[self.gidx].to(torch.bool)
+        self.backend.compact(local_keep)
+        self.gidx = dst[self.gidx][local_keep].to(torch.int64)
+        self.n_global = count
+        self.calculate_fitness_score()
+
+    # ------------------------------------------------------------------ a12
+    def horizontal_crossover(self):
+        """GA.py:281-301: one shared plan; survivors' boards all-gathered; each rank builds its block of
+        children (logical indices S + block) so that it ends up with its share of the population."""
+        P = int(config.POPULATION_SIZE)
+        S = self.n_global
+        n_children = P - S
+        if n_children > 0:
+            plan = self.backend.crossover_plan(S, n_children)            # identical on every rank
+            counts = self._counts(int(self.gidx.numel()))
+            lo = shard_bounds(P, self.world)
+            need = [max(0, (lo[r + 1] - lo[r]) - counts[r]) for r in range(self.world)]
+            assert sum(need) == n_children, (need, n_children)
+            first = sum(need[:self.rank])
+            mine = plan[first:first + need[self.rank]]
+            boards, rowlen = self.backend.survivors()
+            all_boards = self._all_gather_padded(boards, counts)
+            all_rowlen = self._all_gather_padded(rowlen, counts)
+            all_gidx = self._all_gather_padded(self.gidx, counts)
+            pos = torch.zeros(S, dtype=torch.int64, device=self.backend.device)
+            pos.index_copy_(0, all_gidx, torch.arange(S, device=self.backend.device))
+            self.backend.crossover_from(all_boards, all_rowlen, pos, mine)
+            kids = torch.arange(S + first, S + first + need[self.rank], dtype=torch.int64, device=self.backend.device)
+            self.gidx = torch.cat((self.gidx, kids))
+            self.n_global = P
+        self.calculate_fitness_score()
+
+    # ------------------------------------------------------------------ a14
+    def mutation(self, model_path):
+        n = min(round(config.POPULATION_SIZE * config.MUTATION_RATE), self.n_global)
+        if n <= 0:
+            return
+        order = self.backend.rank_order(self.g_scores, self.n_global, self.mode, n)      # logical indices
+        chosen = torch.zeros(self.n_global, dtype=torch.bool, device=self.backend.device)
+        chosen[order.to(torch.int64)] = True
+        local = chosen[self.gidx].nonzero().flatten().to(torch.int32)
+        # the stride must grow identically on every rank (the survivor all-gather needs equal strides)
+        self.backend.mutate(local, model_path, self.mode, int(self.g_scores[2].max().item()))
+
+    # ------------------------------------------------------------------ a19
+    def run(self, model_path, debug_mode=False):
+        self.generate_population()
+        self.calculate_fitness_score()
+        self.backend.validate_window()
+        for _ in range(config.GA_ITERATIONS):
+            self.current_iteration += 1
+            self.mutation(model_path)
+            self.calculate_fitness_score()
+            self.selection()
+            self.horizontal_crossover()
+        best, _ = self.hall_of_fame
+        return ["".join("ATCG-"[v - 1] for v in row) for row in best]
+
+
+class DeviceBackend:
+    """The product backend: libgadpamsa kernels on this rank's GPU."""
+
+    def __init__(self, device=None):
+        import _native as nat
+        nat.require_device()
+        self.nat = nat
+        self.device = torch.device(device or config.DEVICE)
+        torch.cuda.set_device(self.device)
+        self.pop = None
+        self.R = 0
+        self._rank_tmp = None
+
+    # -- population ---------------------------------------------------------------------------
+    def generate_full_population(self, sequences, P):
+        import GA as ga_mod
+        g = ga_mod.GA.__new__(ga_mod.GA)
+        g.sequences, g.mode, g.population_size, g._dev = sequences, 'sp', P, None
+        g._device = self.device
+        return g._generate_host()
+
+    def adopt(self, boards, rowlen, capacity):
+        from population import DevicePopulation
+        extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
+        stride = -(-(boards.shape[2] + extra) // 16) * 16
+        wide = np.full((boards.shape[0], boards.shape[1], stride), 5, dtype=np.uint8)
+        wide[:, :, :boards.shape[2]] = boards
+        self.pop = DevicePopulation.from_numpy(wide, np.ascontiguousarray(rowlen), device=self.device,
+                                               capacity=max(capacity, 1))
+        self.R = self.pop.R
+
+    def board(self, local, width):
+        return self.pop.cur.boards[local, :, :width].contiguous()
+
+    def survivors(self):
+        p = self.pop
+        return p.cur.boards[:p.n], p.cur.rowlen[:p.n]
+
+    def validate_window(self):
+        if config.AGENT_WINDOW_ROW > self.R:
+            raise ValueError("AGENT_WINDOW_ROW is larger than the sequence count.")
+
+    # -- phases -------------------------------------------------------------------------------
+    def _weights(self):
+        return int(config.MATCH_REWARD), int(config.MISMATCH_PENALTY), int(config.GAP_PENALTY)
+
+    def fitness(self):
+        return self.pop.fitness(*self._weights())
+
+    def _ranker(self, n):
+        from population import Ranker
+        if self._rank_tmp is None or self._rank_tmp.capacity < n:
+            self._rank_tmp = Ranker(max(n, int(config.POPULATION_SIZE)), self.device)
+        return self._rank_tmp
+
+    def hof_argbest(self, scores, n, mode, hof_score):
+        return self._ranker(n).argbest(scores, n, mode, hof_score)
+
+    def select_flags(self, scores, n, mode, top_n):
+        return self._ranker(n).select_flags(scores, n, mode, top_n)
+
+    def rank_order(self, scores, n, mode, k):
+        return self._ranker(n).rank_order(scores, n, mode, k)
+
+    def compact(self, local_keep):
+        self.pop.compact_with(local_keep)
+
+    def crossover_plan(self, n_parents, n_children):
+        import GA as ga_mod
+        plan = np.empty((n_children, 3), dtype=np.int32)
+        state, meta = ga_mod._mt_state()
+        self.nat.call("gad_mt_crossover_plan_host", state.ctypes.data, n_parents, self.R, n_children, None,
+                      plan.ctypes.data)
+        ga_mod._mt_restore(state, meta)
+        return plan
+
+    def crossover_from(self, all_boards, all_rowlen, pos, plan):
+        self.pop.crossover_from(all_boards, all_rowlen, pos, plan)
+
+    def mutate(self, local_idx, model_path, mode, global_width):
+        from DPAMSA import dqn as _dqn
+        rw, cw = int(config.AGENT_WINDOW_ROW), int(config.AGENT_WINDOW_COLUMN)
+        self.pop.ensure_stride(global_width + (rw - 1) * cw)
+        if local_idx.numel() == 0:
+            return
+        qnet = _dqn.load_qnet(model_path, rw, cw)
+        tile = self.pop.worst_tiles(local_idx, rw, cw, mode, *self._weights())
+        self.pop.mutate(qnet, local_idx, tile, cw * (rw * (rw - 1) / 2 * config.MATCH_REWARD), width=global_width)

@@ -121,12 +121,24 @@ int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, const int32_t *
                    int64_t P, int R, int stride, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
                    void *d_ws, size_t ws_bytes, void *stream);
 
+/* The decision of gad_hof_update alone: *d_winner = index of the best of population + hall of fame
+ * (P = the hall of fame keeps its place). Used when the boards are sharded over several GPUs and
+ * the winner's board has to be fetched from its owner. */
+int gad_hof_argbest(const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, int64_t P, int mode,
+                    const int32_t *d_hof, int32_t *d_winner, void *d_ws, size_t ws_bytes, void *stream);
+
 /* ---- a12/a13: crossover --------------------------------------------------
  * Children n_parents + c (c < n_children) of the same buffer are built from d_plan[c] =
  * {parent1, parent2, cut}. kind 0 = horizontal (GA.py:296: rows [0,cut) of parent1, the rest of
  * parent2); kind 1 = vertical (extension, no reference code: every row is parent1[:cut] + parent2[cut:]). */
 int gad_crossover(uint8_t *d_boards, int32_t *d_rowlen, int64_t n_parents, const int32_t *d_plan,
                   int64_t n_children, int R, int stride, int kind, void *stream);
+
+/* Sharded form of gad_crossover: parents are rows of a separate (all-gathered) survivor buffer,
+ * children go to slots [dst_first, dst_first + n_children) of this rank's population buffer. */
+int gad_crossover_from(const uint8_t *d_src_boards, const int32_t *d_src_rowlen, uint8_t *d_dst_boards,
+                       int32_t *d_dst_rowlen, int64_t dst_first, const int32_t *d_plan, int64_t n_children, int R,
+                       int stride, int kind, void *stream);
 
 /* CPython-compatible MT19937 replay (random.getstate()[1] = 624 words + position, in/out):
  * the (parent1, parent2, cut) triples of GA.py:281-293 for n_children children. h_widths (one
