@@ -479,3 +479,30 @@ def test_vertical_crossover_run(gpu, weight_files, cfg, datasets_json):
     out = g.run(name)
     assert len(g.population) == 40 and len(out) == 6
     assert len({len(r) for r in out}) == 1
+
+
+# ------------------------------------------------------------------------------------------- multi-GPU (section 8(e))
+def _run_sharded_check(world):
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = os.path.join(ROOT, "scripts", "sharded_check.py")
+    if world == 1:
+        cmd = [sys.executable, script]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), script]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert "SHARDED-OK world=%d" % world in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])
+
+
+def test_sharded_loop_single_rank_reproduces_reference_traces(gpu):
+    """The sharded code path (logical indices, gathered-score ranking, gad_crossover_from) with one rank."""
+    _run_sharded_check(1)
+
+
+def test_sharded_loop_two_gpus_reproduces_reference_traces(gpu):
+    """Two ranks over NCCL: same per-pass scores, hall of fame and result as the reference for every trace."""
+    if gpu.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run_sharded_check(2)
