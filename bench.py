@@ -227,7 +227,7 @@ AGENTS = {"c2": (3, 30), "c3": (6, 30), "c4": (3, 30)}          # BASELINE confi
 QNET_FLOPS = {(3, 30): 26.8e6, (6, 30): 63.9e6}                 # reference Net.forward per state
 
 
-def synth_weight_file(rows, cols, seed=7):
+def synth_weight_file(rows, cols, seed=7, tag=""):
     """Random-init weights in the reference state_dict layout (DPAMSA/dqn.py:54-63; the pretrained
     files are not in the reference checkout). Returns the model name for DQN.load."""
     import torch
@@ -252,7 +252,7 @@ def synth_weight_file(rows, cols, seed=7):
         "l1.weight": lin(h1, L * d), "l1.bias": lin(1, L * d)[0, :h1].copy(), "l2.weight": lin(h2, h1),
         "l2.bias": lin(1, h1)[0, :h2].copy(), "l3.weight": lin(A, h2), "l3.bias": lin(1, h2)[0, :A].copy(),
     }
-    name = "bench_%dx%d" % (rows, cols)
+    name = "bench_%dx%d%s" % (rows, cols, tag)
     os.makedirs(config.DPAMSA_WEIGHTS_PATH, exist_ok=True)
     torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, os.path.join(config.DPAMSA_WEIGHTS_PATH, name + ".pth"))
     return name, sd
@@ -262,62 +262,118 @@ def seq_strings(rows, cols, seed):
     return ["".join("ATCG-"[v - 1] for v in row) for row in synth_sequences(rows, cols, seed)]
 
 
-def measure_generations(workload, n_gen, n_warm):
-    """Generations/s of the facade's loop body (mutation -> fitness -> selection -> crossover, each with the
-    reference's fitness re-evaluations) on one GPU, with a per-phase breakdown."""
+def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
+    """Generations/s of the loop body (mutation -> fitness -> selection -> crossover, each with the
+    reference's fitness re-evaluations), with a per-phase breakdown. One GPU: through the GA facade.
+    N GPUs: sharded.ShardedGA over NCCL, population = N x the workload's population (weak scaling),
+    phases bracketed by barriers, time = max over ranks."""
     import random
     import torch
+    import torch.distributed as dist
     import config
-    import GA as ga_mod
     rows, cols, P, mode, _ = WORKLOADS[workload]
+    P_total = P * world
     rw, cw = AGENTS[workload]
     saved = {k: getattr(config, k) for k in ("POPULATION_SIZE", "AGENT_WINDOW_ROW", "AGENT_WINDOW_COLUMN", "GA_ITERATIONS")}
-    config.POPULATION_SIZE, config.AGENT_WINDOW_ROW, config.AGENT_WINDOW_COLUMN = P, rw, cw
+    config.POPULATION_SIZE, config.AGENT_WINDOW_ROW, config.AGENT_WINDOW_COLUMN = P_total, rw, cw
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
     try:
-        model, _ = synth_weight_file(rw, cw)
+        model, _ = synth_weight_file(rw, cw, tag="_r%d" % rank)
         random.seed(20251019)
-        g = ga_mod.GA(seq_strings(rows, cols, 20251019), mode)
+        seqs = seq_strings(rows, cols, 20251019)
+        if world == 1:
+            import GA as ga_mod
+            g = ga_mod.GA(seqs, mode)
+            counters = lambda: (g._dev.evals, g._dev.forwards)
+        else:
+            import sharded
+            g = sharded.ShardedGA(seqs, mode, sharded.DeviceBackend(config.DEVICE))
+            counters = lambda: (g.backend.pop.evals, g.backend.pop.forwards)
         t0 = time.perf_counter()
         g.generate_population()
-        torch.cuda.synchronize()
+        sync()
         t_pop = time.perf_counter() - t0
         g.calculate_fitness_score()
         phases = {"mutation": 0.0, "fitness": 0.0, "selection": 0.0, "crossover": 0.0}
         evals = forwards = episodes = 0
         total = 0.0
         for it in range(n_warm + n_gen):
-            dev = g._dev
-            e0, f0 = dev.evals, dev.forwards
+            e0, f0 = counters()
             stamps = []
             for name, fn in (("mutation", lambda: g.mutation(model)), ("fitness", g.calculate_fitness_score),
                              ("selection", g.selection), ("crossover", g.horizontal_crossover)):
-                torch.cuda.synchronize()
+                sync()
                 t0 = time.perf_counter()
                 fn()
-                torch.cuda.synchronize()
+                sync()
                 stamps.append((name, time.perf_counter() - t0))
             if it >= n_warm:
                 for name, dt in stamps:
                     phases[name] += dt
                     total += dt
-                evals += g._dev.evals - e0
-                forwards += g._dev.forwards - f0
-                episodes += round(P * config.MUTATION_RATE)
+                e1, f1 = counters()
+                evals += e1 - e0
+                forwards += f1 - f0
+                episodes += round(P_total * config.MUTATION_RATE)
+        if world > 1:
+            t = torch.tensor([total] + [phases[k] for k in sorted(phases)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t[0])
+            phases = {k: float(v) for k, v in zip(sorted(phases), t[1:])}
+            c = torch.tensor([evals], dtype=torch.float64, device="cuda")
+            dist.all_reduce(c)
+            evals = float(c[0])
         hof = g.hall_of_fame
-        flops = QNET_FLOPS.get((rw, cw))
-        return {
+        tensor = None
+        if rank == 0:
+            tensor = l1_tensor_roofline(model, rw, cw, min(32768, round(P_total * config.MUTATION_RATE)))
+        out = {
             "value": n_gen / total, "unit": "generations/s", "generations": n_gen, "warmup": n_warm,
             "ms_per_generation": 1e3 * total / n_gen,
             "phase_ms": {k: 1e3 * v / n_gen for k, v in phases.items()},
             "fitness_evals_per_generation": evals / n_gen, "episodes_per_generation": episodes / n_gen,
             "lockstep_forwards_per_generation": forwards / n_gen,
-            "population_generation_s": t_pop, "agent_window": [rw, cw], "population": P, "mode": mode,
+            "population_generation_s": t_pop, "agent_window": [rw, cw], "population": P_total, "mode": mode,
             "hall_of_fame_score": list(hof[1]) if hof else None,
-            "reference_net_flops_per_state": flops,
+            "reference_net_flops_per_state": QNET_FLOPS.get((rw, cw)),
+            "individuals_per_s": P_total * n_gen / total,
+            "roofline": tensor,
         }
+        if world > 1:
+            out["collective_bytes_received_per_generation_rank0"] = g.comm_bytes / (n_warm + n_gen)
+            out["parallelism"] = ("population sharded by logical index over %d ranks; per fitness pass an NCCL all-gather "
+                                  "of 32 B/individual, per generation an all-gather of the survivors' boards" % world)
+        return out
     finally:
         for k, v in saved.items():
             setattr(config, k, v)
+
+
+def l1_tensor_roofline(model, rw, cw, M):
+    """The Q-net's l1 GEMM (tcgen05, gemm_tc.cu) timed alone with CUDA events at the mutation batch size."""
+    import ctypes
+    import _native as nat
+    from DPAMSA import dqn
+    net = dqn.load_qnet(model, rw, cw)
+    ms = ctypes.c_float(0)
+    fl = ctypes.c_double(0)
+    nat.call("gad_qnet_time_l1", net.handle, int(M), 10, ctypes.byref(ms), ctypes.byref(fl), nat.current_stream_ptr())
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(path):
+        with open(path) as fh:
+            peak, src = float(json.load(fh)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
+    achieved = fl.value / (ms.value * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_split_f16_kernel<208> (Q-net l1, tcgen05 kind::f16)", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel_ms": ms.value, "rows": int(M),
+            "flops_per_launch": fl.value, "peak_source": src,
+            "note": "executed FLOPs: three fp16 passes (hi.hi + lo.hi + hi.lo) give fp32-class accuracy; the "
+                    "single-pass-equivalent (algorithmic 2*M*K*N) rate is one third of `achieved`"}
 
 
 def cpu_generation_port(workload, cores, n_mut_per_core=1):
@@ -572,10 +628,12 @@ def main():
     }
 
     # ---------------- whole generations (N=1; the sharded loop is measured by --gpus N via the GA facade) ----
-    if world == 1 and args.generations > 0:
+    if args.generations > 0:
         del replicas, pristine_b, pristine_r
         torch.cuda.empty_cache()
-        line["generation"] = measure_generations(args.workload, args.generations, args.generation_warmup)
+        import config
+        config.DEVICE = "cuda:%d" % local_rank
+        line["generation"] = measure_generations(args.workload, args.generations, args.generation_warmup, world, rank)
 
     # ---------------- CPU baselines on rank 0 at N=1 ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -61,6 +61,8 @@ SIGNATURES = {
     "gad_qnet_dims": (c_int, [c_vp, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "gad_qnet_forward": (c_int, [c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_vp, c_vp]),
     "gad_qnet_forward_host": (c_int, [c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_vp]),
+    "gad_qnet_time_l1": (c_int, [c_vp, c_i64, c_int, ctypes.POINTER(ctypes.c_float),
+                                 ctypes.POINTER(ctypes.c_double), c_vp]),
     "gad_mutate": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_i64p, c_vp]),
 }
 

@@ -992,3 +992,33 @@ extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int
     if (h_forwards) *h_forwards = forwards;
     return GAD_OK;
 }
+
+// Timing hook for bench.py's tensor roofline: the l1 tcgen05 GEMM alone over M rows of the current
+// activation buffer, `reps` back-to-back launches between CUDA events on `stream`. Synchronises.
+extern "C" int gad_qnet_time_l1(gad_qnet *q, int64_t M, int reps, float *ms_per_launch, double *flops_per_launch,
+                                void *stream)
+{
+    GAD_REQUIRE(q && ms_per_launch && flops_per_launch && M >= 1 && M <= kMaxBatch && reps >= 1, "gad_qnet_time_l1: bad argument");
+    GAD_REQUIRE(q->tc1, "gad_qnet_time_l1: the tensor-core l1 is disabled (GAD_QNET_SIMT=1)");
+    int rc = ensure_states(q, M);
+    if (rc) return rc;
+    cudaStream_t st = gad_stream(stream);
+    GAD_CUDA(cudaMemsetAsync(q->Z2, 0x3c, (size_t)M * 2 * q->K * sizeof(__half), st));      // finite fp16 values
+    cudaEvent_t e0, e1;
+    GAD_CUDA(cudaEventCreate(&e0));
+    GAD_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i)
+        if ((rc = tc_layer_run(q->tc1, q->b1, q->H1, q->h1, nullptr, M, 1, st))) return rc;
+    GAD_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; ++i)
+        if ((rc = tc_layer_run(q->tc1, q->b1, q->H1, q->h1, nullptr, M, 1, st))) return rc;
+    GAD_CUDA(cudaEventRecord(e1, st));
+    GAD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GAD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / reps;
+    *flops_per_launch = 3.0 * 2.0 * (double)M * (double)q->K * (double)q->h1;      // three fp16 passes (hi.hi, lo.hi, hi.lo)
+    return GAD_OK;
+}

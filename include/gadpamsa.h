@@ -173,6 +173,10 @@ int gad_qnet_forward(gad_qnet *q, const uint8_t *d_states, int64_t B, float max_
                      int32_t *d_action, void *stream);
 int gad_qnet_forward_host(gad_qnet *q, const uint8_t *h_states, int64_t B, float max_value, float *h_q,
                           int32_t *h_action);
+/* Measurement hook (bench.py): the l1 tensor-core GEMM alone over M rows, `reps` launches between
+ * CUDA events. *flops_per_launch counts the three fp16 passes actually executed. Synchronises. */
+int gad_qnet_time_l1(gad_qnet *q, int64_t M, int reps, float *ms_per_launch, double *flops_per_launch,
+                     void *stream);
 /* GA.mutation's episode loop + Environment.padding + splice (GA.py:335-373) for M individuals.
  * Requires max row length + (rows-1)*cols <= stride; otherwise bit 0 of *d_status is set and the
  * board is left as it was. *h_forwards (optional) = lock-step forwards executed. Synchronises. */
