@@ -60,6 +60,42 @@ __device__ __forceinline__ void count_word(const uint8_t *__restrict__ board, in
     for (; r < R; ++r) colcounts_add(cc, col[(size_t)r * wstride], first);
 }
 
+// counts of the 16 columns of unit `u` (one uint4 = 4 words) over rows [0, R); words at or beyond
+// `nwords` are outside the board (their bytes may be stale) and get an empty valid mask
+__device__ __forceinline__ void count_unit(const uint8_t *__restrict__ board, int R, int stride, int u, int nwords,
+                                           ColCounts (&cc)[4], uint32_t (&valid)[4])
+{
+    const uint4 *col = reinterpret_cast<const uint4 *>(board) + u;
+    const int ustride = stride >> 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        colcounts_clear(cc[k]);
+        valid[k] = 4 * u + k < nwords ? GAD_MSB4 : 0u;
+    }
+    const uint4 first = col[0];
+    int r = 0;
+    for (; r + 4 <= R; r += 4) {                          // 4 independent 16-byte loads in flight per lane
+        uint4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = col[(size_t)(r + i) * ustride];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            colcounts_add(cc[0], x[i].x, first.x);
+            colcounts_add(cc[1], x[i].y, first.y);
+            colcounts_add(cc[2], x[i].z, first.z);
+            colcounts_add(cc[3], x[i].w, first.w);
+        }
+    }
+    for (; r < R; ++r) {
+        const uint4 x0 = col[(size_t)r * ustride];
+        colcounts_add(cc[0], x0.x, first.x);
+        colcounts_add(cc[1], x0.y, first.y);
+        colcounts_add(cc[2], x0.z, first.z);
+        colcounts_add(cc[3], x0.w, first.w);
+    }
+}
+
+// GS lanes own one board; lane l owns the 16-byte units l, l+GS, ... of every row.
 template <int GS>
 __global__ void __launch_bounds__(256)
 fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long long P, int R, int stride,
@@ -87,13 +123,16 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
         w = group_max<GS>(w, gmask);
         wmin = -group_max<GS>(-wmin, gmask);
         const int nwords = (w + 3) >> 2;
+        const int nunits = (nwords + 3) >> 2;
 
         BoardSums bs;
         boardsums_clear(bs);
-        for (int j = gl; j < nwords; j += GS) {
-            ColCounts cc;
-            count_word(board, R, stride, j, cc);
-            boardsums_fold(bs, cc, GAD_MSB4, false);
+        for (int u = gl; u < nunits; u += GS) {
+            ColCounts cc[4];
+            uint32_t valid[4];
+            count_unit(board, R, stride, u, nwords, cc, valid);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) boardsums_fold(bs, cc[k], valid[k], false);
         }
         bs.q2 = group_sum<GS>(bs.q2, gmask);
         bs.s1 = group_sum<GS>(bs.s1, gmask);
@@ -103,20 +142,22 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
         const int nk = (int)bs.kept;
 
         if (nk != w) {
-            // utils.py:408-428: drop every all-gap column, keep the order. In place: chunk by
-            // chunk, each row's words are read by the whole group before any lane stores, and
-            // stores only land at or left of the columns just read.
+            // utils.py:408-428: drop every all-gap column, keep the order. In place: chunk by chunk, each
+            // row's units are read by the whole group before any lane stores, and stores only land at or
+            // left of the columns just read.
             int base = 0;
-            const int nchunks = (nwords + GS - 1) / GS;
+            const int nchunks = (nunits + GS - 1) / GS;
             for (int ch = 0; ch < nchunks; ++ch) {
-                const int j = ch * GS + gl;
-                uint32_t keep = 0u;
-                if (j < nwords) {
-                    ColCounts cc;
-                    count_word(board, R, stride, j, cc);
-                    keep = nonzero_lanes(cc.c1 + cc.c2 + cc.c3 + cc.c4);
+                const int u = ch * GS + gl;
+                uint32_t keep[4] = {0u, 0u, 0u, 0u};
+                if (u < nunits) {
+                    ColCounts cc[4];
+                    uint32_t valid[4];
+                    count_unit(board, R, stride, u, nwords, cc, valid);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) keep[k] = nonzero_lanes(cc[k].c1 + cc[k].c2 + cc[k].c3 + cc[k].c4) & valid[k];
                 }
-                const int mine = __popc(keep);
+                const int mine = __popc(keep[0]) + __popc(keep[1]) + __popc(keep[2]) + __popc(keep[3]);
                 int incl = mine;                                  // inclusive scan inside the group
 #pragma unroll
                 for (int o = 1; o < GS; o <<= 1) {
@@ -127,13 +168,16 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
                 const int dst0 = base + incl - mine;
                 for (int r = 0; r < R; ++r) {
                     uint8_t *row = board + (size_t)r * stride;
-                    uint32_t x = 0u;
-                    if (j < nwords) x = reinterpret_cast<const uint32_t *>(row)[j];
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (u < nunits) x = reinterpret_cast<const uint4 *>(row)[u];
                     __syncwarp(gmask);
+                    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
                     int d = dst0;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (keep & (0x80u << (8 * b))) row[d++] = (uint8_t)(x >> (8 * b));
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (keep[k] & (0x80u << (8 * b))) row[d++] = (uint8_t)(xs[k] >> (8 * b));
                     __syncwarp(gmask);
                 }
                 base += total;
@@ -213,9 +257,9 @@ int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int str
 
 }  // namespace
 
-extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int match,
-                           int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al, int32_t *d_max_al,
-                           void *stream)
+extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
+                           int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
+                           int32_t *d_max_al, void *stream)
 {
     GAD_REQUIRE(P >= 0 && R >= 1 && R <= 255, "gad_fitness: need P >= 0 and 1 <= R <= 255 (got P=%lld R=%d)",
                 (long long)P, R);
@@ -225,11 +269,18 @@ extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int 
     GAD_REQUIRE(d_boards && d_rowlen && d_sp && d_em && d_al, "gad_fitness: null device pointer");
     if (P == 0) return GAD_OK;
     cudaStream_t st = gad_stream(stream);
-    const int words = stride / 4;
-    if (words <= 4) return launch_fitness<4>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, d_max_al, st);
-    if (words <= 8) return launch_fitness<8>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, d_max_al, st);
-    if (words <= 16) return launch_fitness<16>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, d_max_al, st);
-    return launch_fitness<32>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, d_max_al, st);
+    if (d_max_al) GAD_CUDA(cudaMemsetAsync(d_max_al, 0, sizeof(int32_t), st));
+    // lanes per board from the expected width (a performance hint only: wider boards take more trips)
+    int width = width_hint > 0 && width_hint < stride ? width_hint : stride;
+    const int units = (width + 15) / 16;
+#define GAD_FIT(GS) launch_fitness<GS>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, d_max_al, st)
+    if (units <= 1) return GAD_FIT(1);
+    if (units <= 2) return GAD_FIT(2);
+    if (units <= 4) return GAD_FIT(4);
+    if (units <= 8) return GAD_FIT(8);
+    if (units <= 16) return GAD_FIT(16);
+    return GAD_FIT(32);
+#undef GAD_FIT
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,8 +322,8 @@ extern "C" int gad_fitness_host(uint8_t *h_boards, int32_t *h_rowlen, int64_t P,
     int32_t *d_sp = (int32_t *)s.d_scores, *d_em = d_sp + P, *d_al = d_em + P;
     GAD_CUDA(cudaMemcpyAsync(s.d_boards, h_boards, nb, cudaMemcpyHostToDevice, s.stream));
     GAD_CUDA(cudaMemcpyAsync(s.d_rowlen, h_rowlen, nr, cudaMemcpyHostToDevice, s.stream));
-    rc = gad_fitness((uint8_t *)s.d_boards, (int32_t *)s.d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al,
-                     nullptr, s.stream);
+    rc = gad_fitness((uint8_t *)s.d_boards, (int32_t *)s.d_rowlen, P, R, stride, 0, match, mismatch, gap, d_sp, d_em,
+                     d_al, nullptr, s.stream);
     if (rc) return rc;
     GAD_CUDA(cudaMemcpyAsync(h_sp, d_sp, ns, cudaMemcpyDeviceToHost, s.stream));
     GAD_CUDA(cudaMemcpyAsync(h_em, d_em, ns, cudaMemcpyDeviceToHost, s.stream));

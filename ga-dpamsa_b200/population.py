@@ -95,6 +95,7 @@ class DevicePopulation:
         self._dst = None
         self._count = torch.zeros(1, dtype=torch.int32, device=dev)
         self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.width_hint = 0                      # expected board width (lanes per board in the fitness pass)
         self.evals = 0                           # boards scored so far (reference-equivalent accounting)
         self.forwards = 0                        # lock-step Q-net forwards so far
 
@@ -103,12 +104,14 @@ class DevicePopulation:
     def from_lists(cls, population, device="cuda", stride=None, extra_capacity=0, capacity=None):
         nat.require_device()
         boards, rowlen = pack_boards(population, stride, extra_capacity)
-        return cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity)
+        return cls.from_numpy(boards, rowlen, device, capacity)
 
     @classmethod
     def from_numpy(cls, boards: np.ndarray, rowlen: np.ndarray, device="cuda", capacity=None):
         nat.require_device()
-        return cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity)
+        pop = cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity)
+        pop.width_hint = int(rowlen.max()) if rowlen.size else 0
+        return pop
 
     def to_numpy(self):
         return self.cur.boards[:self.n].cpu().numpy(), self.cur.rowlen[:self.n].cpu().numpy()
@@ -196,12 +199,10 @@ class DevicePopulation:
     def fitness(self, match: int, mismatch: int, gap: int):
         """One fused pad+clean+SP+EM pass over the live boards (GA.py:156-178). Asynchronous on the
         current stream; results land in self.sp / self.em / self.al (int32 device tensors)."""
-        nat.require_device()
-        self.max_al.zero_()
         b = self.cur
         nat.call("gad_fitness", nat.ptr(b.boards), nat.ptr(b.rowlen), self.n, self.R, self.stride,
-                 int(match), int(mismatch), int(gap), nat.ptr(b.sp), nat.ptr(b.em), nat.ptr(b.al),
-                 nat.ptr(self.max_al), self._stream())
+                 int(self.width_hint), int(match), int(mismatch), int(gap), nat.ptr(b.sp), nat.ptr(b.em),
+                 nat.ptr(b.al), nat.ptr(self.max_al), self._stream())
         self.evals += self.n
         return self.sp, self.em, self.al
 
@@ -252,7 +253,9 @@ class DevicePopulation:
                  nat.ptr(self._keep), nat.ptr(self._dst), self.n, self.R, self.stride, nat.ptr(d.boards),
                  nat.ptr(d.rowlen), nat.ptr(d.sp), nat.ptr(d.em), nat.ptr(d.al), self._stream())
         self.cur, self.alt = d, s
-        self.n = int(self._count.item())
+        both = torch.stack((self._count[0], self.max_al[0])).cpu()       # one small read: survivor count + widest board
+        self.n = int(both[0])
+        self.width_hint = int(both[1])
         return self.n
 
     # ------------------------------------------------------------------ a12 / a13
@@ -321,6 +324,7 @@ class DevicePopulation:
         if width is None:
             width = int(self.cur.rowlen[:self.n].max().item())
         self.ensure_stride(width + (qnet.rows - 1) * qnet.cols)
+        self.width_hint = width + qnet.cols              # mutated boards are wider until the next pass cleans them
         self._status.zero_()
         fw = ctypes.c_int64(0)
         b = self.cur

@@ -84,9 +84,12 @@ class ShardedGA:
         boards, rowlen = self.backend.generate_full_population(self.sequences, self.population_size)
         P = boards.shape[0]
         lo = shard_bounds(P, self.world)
-        a, b = lo[self.rank], lo[self.rank + 1]
-        self.backend.adopt(boards[a:b], rowlen[a:b], capacity=max(b - a, lo[1] - lo[0]))
-        self.gidx = torch.arange(a, b, dtype=torch.int64, device=self.backend.device)
+        # interleaved placement (individual i -> rank i % world): the clones - the first CLONE_RATE of the
+        # list and usually the best scored, hence the first to be mutated - spread evenly over the ranks
+        mine = np.arange(self.rank, P, self.world)
+        self.backend.adopt(np.ascontiguousarray(boards[mine]), np.ascontiguousarray(rowlen[mine]),
+                           capacity=lo[1] - lo[0])
+        self.gidx = torch.from_numpy(mine).to(self.backend.device, torch.int64)
         self.n_global = P
 
     # ------------------------------------------------------------------ a4 + a8

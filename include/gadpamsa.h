@@ -66,9 +66,10 @@ int gad_stream_sync(void *stream);                         /* synchronises */
  * Outputs (device, int32[P]): sp = sum-of-pairs, em = exact-match columns,
  * al = alignment length after cleaning; the facade forms CS = em / al as a
  * Python float so it is bit-identical to utils.py:128.
- * d_max_al (optional, device int32[1], caller zero-initialises) receives
- * max(al) by atomicMax. Requires R <= 255. */
-int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride,
+ * d_max_al (optional, device int32[1], zeroed by the call) receives
+ * max(al) by atomicMax. width_hint (0 = unknown) is the expected board width: it only selects how
+ * many lanes share a board, any width up to `stride` stays correct. Requires R <= 255. */
+int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
                 int match, int mismatch, int gap,
                 int32_t *d_sp, int32_t *d_em, int32_t *d_al, int32_t *d_max_al, void *stream);
 

@@ -40,8 +40,8 @@ def test_library_has_sm100a_code(native_lib):
 def test_argument_errors_without_gpu(native_lib):
     """Validation happens before any CUDA call, so it is testable on the CPU box."""
     lib = native_lib.lib()
-    rc = lib.gad_fitness(None, None, 4, 0, 16, 4, -4, -4, None, None, None, None, None)
+    rc = lib.gad_fitness(None, None, 4, 0, 16, 0, 4, -4, -4, None, None, None, None, None)
     assert rc == native_lib.GAD_EINVAL
     assert b"R" in lib.gad_last_error()
-    rc = lib.gad_fitness(None, None, 4, 3, 10, 4, -4, -4, None, None, None, None, None)
+    rc = lib.gad_fitness(None, None, 4, 3, 10, 0, 4, -4, -4, None, None, None, None, None)
     assert rc == native_lib.GAD_EINVAL and b"stride" in lib.gad_last_error()
