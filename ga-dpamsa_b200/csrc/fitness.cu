@@ -62,6 +62,7 @@ __device__ __forceinline__ void count_word(const uint8_t *__restrict__ board, in
 
 // counts of the 16 columns of unit `u` (one uint4 = 4 words) over rows [0, R); words at or beyond
 // `nwords` are outside the board (their bytes may be stale) and get an empty valid mask
+template <bool PAIRED>
 __device__ __forceinline__ void count_unit(const uint8_t *__restrict__ board, int R, int stride, int u, int nwords,
                                            ColCounts (&cc)[4], uint32_t (&valid)[4])
 {
@@ -73,20 +74,62 @@ __device__ __forceinline__ void count_unit(const uint8_t *__restrict__ board, in
         valid[k] = 4 * u + k < nwords ? GAD_MSB4 : 0u;
     }
     const uint4 first = col[0];
-    int r = 0;
+    if constexpr (!PAIRED) {                              // few rows: plain byte counters, fewer registers
+        int r = 0;
+        for (; r + 2 <= R; r += 2) {
+            const uint4 x0 = col[(size_t)r * ustride], x1 = col[(size_t)(r + 1) * ustride];
+            colcounts_add(cc[0], x0.x, first.x);
+            colcounts_add(cc[1], x0.y, first.y);
+            colcounts_add(cc[2], x0.z, first.z);
+            colcounts_add(cc[3], x0.w, first.w);
+            colcounts_add(cc[0], x1.x, first.x);
+            colcounts_add(cc[1], x1.y, first.y);
+            colcounts_add(cc[2], x1.z, first.z);
+            colcounts_add(cc[3], x1.w, first.w);
+        }
+        if (r < R) {
+            const uint4 x0 = col[(size_t)r * ustride];
+            colcounts_add(cc[0], x0.x, first.x);
+            colcounts_add(cc[1], x0.y, first.y);
+            colcounts_add(cc[2], x0.z, first.z);
+            colcounts_add(cc[3], x0.w, first.w);
+        }
+        return;
+    }
+    const uint32_t f2[4] = {first.x * 17u, first.y * 17u, first.z * 17u, first.w * 17u};   // first row in both nibbles
+    ColCounts nn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) colcounts_clear(nn[k]);
+    int r = 0, pairs = 0;
     for (; r + 4 <= R; r += 4) {                          // 4 independent 16-byte loads in flight per lane
         uint4 x[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[i] = col[(size_t)(r + i) * ustride];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            colcounts_add(cc[0], x[i].x, first.x);
-            colcounts_add(cc[1], x[i].y, first.y);
-            colcounts_add(cc[2], x[i].z, first.z);
-            colcounts_add(cc[3], x[i].w, first.w);
+        for (int i = 0; i < 4; i += 2) {
+            colcounts_add2(nn[0], x[i].x, x[i + 1].x, f2[0]);
+            colcounts_add2(nn[1], x[i].y, x[i + 1].y, f2[1]);
+            colcounts_add2(nn[2], x[i].z, x[i + 1].z, f2[2]);
+            colcounts_add2(nn[3], x[i].w, x[i + 1].w, f2[3]);
+        }
+        pairs += 2;
+        if (pairs >= 14) {                                // 4-bit counters hold at most 15
+#pragma unroll
+            for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
+            pairs = 0;
         }
     }
-    for (; r < R; ++r) {
+    if (r + 2 <= R) {
+        const uint4 x0 = col[(size_t)r * ustride], x1 = col[(size_t)(r + 1) * ustride];
+        colcounts_add2(nn[0], x0.x, x1.x, f2[0]);
+        colcounts_add2(nn[1], x0.y, x1.y, f2[1]);
+        colcounts_add2(nn[2], x0.z, x1.z, f2[2]);
+        colcounts_add2(nn[3], x0.w, x1.w, f2[3]);
+        r += 2;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
+    if (r < R) {
         const uint4 x0 = col[(size_t)r * ustride];
         colcounts_add(cc[0], x0.x, first.x);
         colcounts_add(cc[1], x0.y, first.y);
@@ -96,8 +139,8 @@ __device__ __forceinline__ void count_unit(const uint8_t *__restrict__ board, in
 }
 
 // GS lanes own one board; lane l owns the 16-byte units l, l+GS, ... of every row.
-template <int GS>
-__global__ void __launch_bounds__(256)
+template <int GS, bool PAIRED>
+__global__ void __launch_bounds__(256, 3)
 fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long long P, int R, int stride,
                int match, int mismatch, int gap, int32_t *__restrict__ sp, int32_t *__restrict__ em,
                int32_t *__restrict__ al, int32_t *__restrict__ max_al)
@@ -130,7 +173,7 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
         for (int u = gl; u < nunits; u += GS) {
             ColCounts cc[4];
             uint32_t valid[4];
-            count_unit(board, R, stride, u, nwords, cc, valid);
+            count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
 #pragma unroll
             for (int k = 0; k < 4; ++k) boardsums_fold(bs, cc[k], valid[k], false);
         }
@@ -153,7 +196,7 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
                 if (u < nunits) {
                     ColCounts cc[4];
                     uint32_t valid[4];
-                    count_unit(board, R, stride, u, nwords, cc, valid);
+                    count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) keep[k] = nonzero_lanes(cc[k].c1 + cc[k].c2 + cc[k].c3 + cc[k].c4) & valid[k];
                 }
@@ -249,8 +292,12 @@ int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int str
     long long blocks = (P + groups_per_block - 1) / groups_per_block;
     const long long cap = (long long)GAD_NUM_SMS * 8 * 4;          // 8 resident CTAs/SM, <=4 passes each
     if (blocks > cap) blocks = cap;
-    fitness_kernel<GS><<<(unsigned)blocks, threads, 0, st>>>(boards, rowlen, P, R, stride, match, mismatch, gap, sp,
-                                                              em, al, max_al);
+    if (R >= 8)
+        fitness_kernel<GS, true><<<(unsigned)blocks, threads, 0, st>>>(boards, rowlen, P, R, stride, match, mismatch,
+                                                                        gap, sp, em, al, max_al);
+    else
+        fitness_kernel<GS, false><<<(unsigned)blocks, threads, 0, st>>>(boards, rowlen, P, R, stride, match, mismatch,
+                                                                         gap, sp, em, al, max_al);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -68,6 +68,37 @@ __device__ __forceinline__ void colcounts_add(ColCounts &c, uint32_t x, uint32_t
     c.diff |= x ^ x_first;
 }
 
+// Two rows at once: z = xa | xb << 4 puts the 3-bit codes of row a in the low and of row b in the high
+// nibble of every byte, so one LOP3 per symbol yields the indicators of both rows (bits 0 and 4) and
+// the accumulators become pairs of 4-bit counters (at most 15 row pairs between two flushes).
+#define GAD_LSN8 0x11111111u
+#define GAD_NIB4 0x0F0F0F0Fu
+
+__device__ __forceinline__ void colcounts_add2(ColCounts &n, uint32_t xa, uint32_t xb, uint32_t first2)
+{
+    const uint32_t z = xb * 16u + xa;
+    const uint32_t b0 = z & GAD_LSN8;
+    const uint32_t b1 = (z >> 1) & GAD_LSN8;
+    const uint32_t b2 = (z >> 2) & GAD_LSN8;
+    n.c1 += b0 & ~b1 & ~b2;
+    n.c2 += b1 & ~b0;
+    n.c3 += b0 & b1;
+    n.c4 += b2 & ~b0;
+    n.diff |= z ^ first2;
+}
+
+// fold the nibble-pair counters of an epoch into the byte counters
+__device__ __forceinline__ void colcounts_flush2(ColCounts &c, ColCounts &n)
+{
+    c.c1 += (n.c1 & GAD_NIB4) + ((n.c1 >> 4) & GAD_NIB4);
+    c.c2 += (n.c2 & GAD_NIB4) + ((n.c2 >> 4) & GAD_NIB4);
+    c.c3 += (n.c3 & GAD_NIB4) + ((n.c3 >> 4) & GAD_NIB4);
+    c.c4 += (n.c4 & GAD_NIB4) + ((n.c4 >> 4) & GAD_NIB4);
+    c.diff |= (n.diff | (n.diff >> 4)) & GAD_NIB4;
+    n.c1 = n.c2 = n.c3 = n.c4 = 0u;
+    n.diff = 0u;
+}
+
 // bit 7 of every byte lane that is non-zero (exact per lane, lanes may hold up to 255)
 __device__ __forceinline__ uint32_t nonzero_lanes(uint32_t v)
 {
