@@ -506,3 +506,42 @@ def test_sharded_loop_two_gpus_reproduces_reference_traces(gpu):
     if gpu.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     _run_sharded_check(2)
+
+
+# ------------------------------------------------------------------------------------------- callers (section 8(f) rank 2)
+def test_inference_driver_writes_reference_report_format(gpu, weight_files, cfg, datasets_json, tmp_path):
+    """mainGA.inference over a dataset module: the report blocks parse with the golden-report parser and
+    their SP / EM / AL recompute from the alignment with the oracle (the 1340-record format)."""
+    import types
+    import mainGA
+    name, sd = weight_files[(3, 30)]
+    sets = datasets_json["dataset1_6x30bp"]
+    mod = types.SimpleNamespace(file_name="unit_6x30bp.py", datasets=list(sets)[:3], **{k: sets[k] for k in list(sets)[:3]})
+    cfg.POPULATION_SIZE, cfg.GA_ITERATIONS = 8, 2
+    cfg.AGENT_WINDOW_ROW, cfg.AGENT_WINDOW_COLUMN = 3, 30
+    for mode in ("sp", "mo"):
+        random.seed(1)
+        report, csv_path = mainGA.inference(mode, mod, model_path=name)
+        blocks = open(report).read().split("File: ")[1:]
+        assert len(blocks) == 3
+        for blk, key in zip(blocks, mod.datasets):
+            lines = blk.strip("\n").split("\n")
+            assert lines[0] == key
+            head = dict(ln.rsplit(":", 1) for ln in lines[1:6])
+            rows = [ln.strip() for ln in lines[lines.index("Alignment:") + 1:] if ln.strip()]
+            board = O.encode(rows)
+            R, W = len(board), len(board[0])
+            assert int(head["Number of Sequences (QTY)"]) == R == 6
+            assert int(head["Alignment Length (AL)"]) == W
+            assert int(head["Sum of Pairs (SP)"]) == O.sum_of_pairs(board, 0, R, 0, W)
+            assert int(head["Exact Matches (EM)"]) == O.exact_columns(board, 0, R, 0, W)
+            assert head["Column Score (CS)"].strip() == "%.3f" % O.column_score(board, 0, R, 0, W)
+            assert [r.replace("-", "") for r in rows] == [s.replace("-", "") for s in sets[key]]   # residues preserved
+        assert len(open(csv_path).read().strip().split("\n")) == 4
+    # the oracle's loop gives the same winning alignment for the first set
+    random.seed(1)
+    kb = O.Knobs(POPULATION_SIZE=8, GA_ITERATIONS=2)
+    want, _ = O.ga_run(sets[mod.datasets[0]], "sp", sd, kb)
+    random.seed(1)
+    import GA as ga_mod
+    assert ga_mod.GA(sets[mod.datasets[0]], "sp").run(name) == want
