@@ -33,6 +33,8 @@ struct gad_qnet {
     int rows, cols, L, A, K, h1, h2;
     // parameters / folded tables (device, fp32)
     float *X = nullptr, *T = nullptr, *VF = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    __half *VFh = nullptr, *VFl = nullptr;   // VF * 2^sv split into fp16 hi + lo (encode_mma_kernel's B operand)
+    float vf_inv_scale = 1.f;
     float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *W3 = nullptr, *b3 = nullptr;
     // activation scratch for `cap` states
     long long cap = 0;
@@ -393,6 +395,230 @@ encode_tiled_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, cons
     }
 }
 
+// Encoder on the warp-level tensor-core path (mma.sync m16n8k16, fp16 in / fp32 accumulate). One CTA of 8
+// warps per state, two CTAs per SM so that one CTA's logit gathers overlap the other's MMAs.
+//   per block of 64 query rows:
+//     stage A  as above, but the softmax numerators are stored as fp16 hi + lo (E = Eh + El), row-major
+//     stage B  Y[64 x 64] = E[64 x nk] . V[nk x 64] with V = Vh + Vl (pre-split, pre-scaled by 2^sv at load
+//              time): three MMAs per tile (Eh.Vh + El.Vh + Eh.Vl) - fp32-class accuracy, ~36 MMAs deep
+//     stage C  /sum, * 2^-sv, + residual, LayerNorm, store (hi | lo fp16 for the tcgen05 l1, or fp32)
+#define EM_RB 64
+#define EM_KP 200          // row stride of E in halves (400 B: conflict-free ldmatrix rows)
+#define EM_VP 72           // row stride of V in halves (144 B)
+#define EM_YP 66           // row stride of the fp32 staging tile
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2)
+encode_mma_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
+                  const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
+                  __half *__restrict__ Z2out)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int L = net.L;
+    const int LK = (L + 15) & ~15;                                   // keys padded to the MMA k-step
+    __half *Vh = reinterpret_cast<__half *>(smem);                   // [LK][EM_VP]
+    __half *Vl = Vh + (size_t)LK * EM_VP;
+    __half *Eh = Vl + (size_t)LK * EM_VP;                            // [EM_RB][EM_KP]
+    __half *El = Eh + (size_t)EM_RB * EM_KP;
+    float *rsum = reinterpret_cast<float *>(El + (size_t)EM_RB * EM_KP);   // [EM_RB]
+    int *kj = reinterpret_cast<int *>(rsum + EM_RB);                 // [L]
+    int *koff = kj + L;                                              // [L]
+    uint8_t *tok = reinterpret_cast<uint8_t *>(koff + L);            // [L]
+    float *Ybuf = reinterpret_cast<float *>(Eh);                     // [EM_RB][EM_YP], aliases Eh/El after stage B
+    __shared__ int s_nk;
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = 8;
+    const float vscale_inv = net.vf_inv_scale;
+
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();
+        if (tok_in) {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
+            __syncthreads();
+        } else {
+            const int e = active[row];
+            build_tokens(tok, net.sub + (size_t)e * net.rows * net.cols, net.heads + (size_t)e * net.rows, net.rows,
+                         net.cols, L);
+        }
+        if (warp == 0) {                                 // ordered list of unmasked keys
+            int base = 0;
+            for (int j0 = 0; j0 < L; j0 += 32) {
+                const int j = j0 + lane;
+                const bool v = j < L && tok[j] != 0;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, v);
+                if (v) kj[base + __popc(m & ((1u << lane) - 1u))] = j;
+                base += __popc(m);
+            }
+            if (lane == 0) s_nk = base;
+        }
+        __syncthreads();
+        int nk = s_nk;
+        const bool all_masked = nk == 0;                 // softmax over all -1e9 is uniform (never an environment state)
+        if (all_masked) {
+            for (int j = threadIdx.x; j < L; j += blockDim.x) kj[j] = j;
+            nk = L;
+            __syncthreads();
+        }
+        const int nk16 = (nk + 15) & ~15;
+        for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+            const int j = kj[k];
+            koff[k] = tok[j] * L + j;
+        }
+        // V rows of the valid keys (pre-split fp16 tables, 16 bytes per lane), zero rows up to the k-step
+        for (int i = threadIdx.x; i < nk16 * 8; i += blockDim.x) {
+            const int k = i >> 3, c8 = i & 7;
+            uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+            if (k < nk) {
+                const int j = kj[k];
+                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c8 * 8;
+                vh = __ldg(reinterpret_cast<const uint4 *>(net.VFh + src));
+                vl = __ldg(reinterpret_cast<const uint4 *>(net.VFl + src));
+            }
+            *reinterpret_cast<uint4 *>(Vh + (size_t)k * EM_VP + c8 * 8) = vh;
+            *reinterpret_cast<uint4 *>(Vl + (size_t)k * EM_VP + c8 * 8) = vl;
+        }
+        for (int rb = 0; rb < L; rb += EM_RB) {
+            __syncthreads();
+            // ---- stage A: softmax numerators of 64 rows, one warp per pair of rows, logits in registers
+            constexpr int U = 6;                         // keys per lane: up to 192
+            for (int r0 = 2 * warp; r0 < EM_RB; r0 += 2 * NW) {
+                float sv[2][U];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = rb + r0 + h;
+                    const bool live = i < L;
+                    const int ii = live ? i : 0;
+                    const float *trow = net.T + ((size_t)tok[ii] * L + ii) * (QN_VOCAB * L);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = lane + 32 * u;
+                        float v = -INFINITY;
+                        if (live && k < nk) v = all_masked ? -1e9f : __ldg(trow + koff[k]);
+                        sv[h][u] = v;
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = r0 + h;
+                    const bool live = rb + r < L;
+                    float mx = sv[h][0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u) mx = fmaxf(mx, sv[h][u]);
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+                    float sum = 0.f;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = lane + 32 * u;
+                        if (k < nk16) {
+                            float ev = 0.f;
+                            if (live && k < nk) ev = expf(sv[h][u] - mx);
+                            const __half hi = __float2half_rn(ev);
+                            Eh[r * EM_KP + k] = hi;
+                            El[r * EM_KP + k] = __float2half_rn(ev - __half2float(hi));
+                            sum += ev;
+                        }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                    if (lane == 0) rsum[r] = live ? sum : 1.f;
+                }
+            }
+            __syncthreads();
+            // ---- stage B: warp (mt, nh) owns rows 16*mt.., channels 32*nh.. : 4 n-tiles, 3 MMAs each per k-step
+            const int mt = warp & 3, nh = warp >> 2;
+            float acc[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+            const uint32_t a_off = (uint32_t)(((mt * 16 + (lane & 15)) * EM_KP + (lane >> 4) * 8) * 2);
+            const uint32_t b_off = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * EM_VP + nh * 32 + (lane >> 4) * 8) * 2);
+            const uint32_t eh0 = (uint32_t)__cvta_generic_to_shared(Eh) + a_off;
+            const uint32_t el0 = (uint32_t)__cvta_generic_to_shared(El) + a_off;
+            const uint32_t vh0 = (uint32_t)__cvta_generic_to_shared(Vh) + b_off;
+            const uint32_t vl0 = (uint32_t)__cvta_generic_to_shared(Vl) + b_off;
+            for (int k0 = 0; k0 < nk16; k0 += 16) {
+                uint32_t ah[4], al[4], bh[2][4], bl[2][4];
+                ldsm_x4(ah, eh0 + k0 * 2);
+                ldsm_x4(al, el0 + k0 * 2);
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {         // two n-tiles (16 channels) per ldmatrix.x4.trans
+                    ldsm_x4_trans(bh[pr], vh0 + (k0 * EM_VP + pr * 16) * 2);
+                    ldsm_x4_trans(bl[pr], vl0 + (k0 * EM_VP + pr * 16) * 2);
+                }
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float (&d)[4] = acc[pr * 2 + q];
+                        mma_16816(d, al, bh[pr][2 * q], bh[pr][2 * q + 1]);
+                        mma_16816(d, ah, bl[pr][2 * q], bl[pr][2 * q + 1]);
+                        mma_16816(d, ah, bh[pr][2 * q], bh[pr][2 * q + 1]);
+                    }
+            }
+            __syncthreads();                             // every warp is done reading E: reuse it as the fp32 staging tile
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int c = nh * 32 + t * 8 + (lane & 3) * 2;
+                const int r = mt * 16 + (lane >> 2);
+                *reinterpret_cast<float2 *>(Ybuf + r * EM_YP + c) = make_float2(acc[t][0], acc[t][1]);
+                *reinterpret_cast<float2 *>(Ybuf + (r + 8) * EM_YP + c) = make_float2(acc[t][2], acc[t][3]);
+            }
+            __syncthreads();
+            // ---- stage C: one warp per row, two channels per lane
+            const float2 g = *reinterpret_cast<const float2 *>(net.ln2_g + 2 * lane);
+            const float2 be = *reinterpret_cast<const float2 *>(net.ln2_b + 2 * lane);
+            for (int r = warp; r < EM_RB; r += NW) {
+                const int i = rb + r;
+                if (i >= L) break;
+                const float2 a = *reinterpret_cast<const float2 *>(Ybuf + r * EM_YP + 2 * lane);
+                const float2 x = __ldg(reinterpret_cast<const float2 *>(net.X + ((size_t)tok[i] * L + i) * QN_D) + lane);
+                const float inv = vscale_inv / rsum[r];
+                const float y0 = fmaf(a.x, inv, x.x), y1 = fmaf(a.y, inv, x.y);
+                float sm = y0 + y1;
+                for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o);
+                const float mu = sm * (1.f / QN_D);
+                const float d0 = y0 - mu, d1 = y1 - mu;
+                float vr = d0 * d0 + d1 * d1;
+                for (int o = 16; o > 0; o >>= 1) vr += __shfl_xor_sync(0xFFFFFFFFu, vr, o);
+                const float rstd = rsqrtf(vr * (1.f / QN_D) + 1e-6f);          // LayerNorm(eps=1e-6), models.py:166
+                const float z0 = d0 * rstd * g.x + be.x, z1 = d1 * rstd * g.y + be.y;
+                if (Z2out) {
+                    __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D + 2 * lane, *zl = zh + net.K;
+                    const __half h0 = __float2half_rn(z0), h1 = __float2half_rn(z1);
+                    *reinterpret_cast<__half2 *>(zh) = __halves2half2(h0, h1);
+                    *reinterpret_cast<__half2 *>(zl) =
+                        __halves2half2(__float2half_rn(z0 - __half2float(h0)), __float2half_rn(z1 - __half2float(h1)));
+                } else {
+                    *reinterpret_cast<float2 *>(Zout + (size_t)row * net.K + (size_t)i * QN_D + 2 * lane) = make_float2(z0, z1);
+                }
+            }
+        }
+    }
+}
+
+int encode_mma_smem_bytes(int L)
+{
+    const int LK = (L + 15) & ~15;
+    return 2 * LK * EM_VP * 2 + 2 * EM_RB * EM_KP * 2 + EM_RB * 4 + 2 * L * 4 + ((L + 15) & ~15);
+}
+
 // ---------------------------------------------------------------------------------------------
 // dense layers: C[M][N] = leaky_relu(A[M][K] . W[N][K]^T + b), fp32 SIMT tiles 128x128x16
 // ---------------------------------------------------------------------------------------------
@@ -732,7 +958,14 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
                    float max_value, float *Qout, int32_t *act_out, int32_t *next_active, int32_t *next_count,
                    cudaStream_t st)
 {
-    if (q->L <= 96 && encode_tiled_smem_bytes(q->L, 96) <= 220 * 1024) {
+    const char *enc = getenv("GAD_QNET_ENCODER");      // "simt" keeps the fp32 register-tiled encoder (A/B testing)
+    if (q->L <= 192 && !(enc && enc[0] == 's')) {
+        const int bytes = encode_mma_smem_bytes(q->L);
+        if (bytes > 48 * 1024)
+            GAD_CUDA(cudaFuncSetAttribute(encode_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        const long long grid = n_max < (long long)GAD_NUM_SMS * 2 ? n_max : (long long)GAD_NUM_SMS * 2;
+        encode_mma_kernel<<<(unsigned)grid, 256, bytes, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
+    } else if (q->L <= 96 && encode_tiled_smem_bytes(q->L, 96) <= 220 * 1024) {
         int rc = launch_encode_tiled<96>(q, tok_in, active, n_ptr, n_max, st);
         if (rc) return rc;
     } else if (q->L <= 192 && encode_tiled_smem_bytes(q->L, 192) <= 220 * 1024) {
@@ -851,6 +1084,26 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
     up(&q->X, Xf.data(), Xf.size());
     up(&q->T, Tf.data(), Tf.size());
     up(&q->VF, VFf.data(), VFf.size());
+    {
+        float mx = 0.f;
+        for (float v : VFf) mx = fmaxf(mx, fabsf(v));
+        int sv = mx > 0.f ? (int)floorf(log2f(16384.f / mx)) : 0;
+        sv = sv > 40 ? 40 : (sv < -40 ? -40 : sv);
+        q->vf_inv_scale = ldexpf(1.f, -sv);
+        std::vector<__half> vh(VFf.size()), vl(VFf.size());
+        for (size_t i = 0; i < VFf.size(); ++i) {
+            const float v = ldexpf(VFf[i], sv);
+            vh[i] = __float2half_rn(v);
+            vl[i] = __float2half_rn(v - __half2float(vh[i]));
+        }
+        if (!rc) rc = dev_alloc(&q->VFh, vh.size());
+        if (!rc) rc = dev_alloc(&q->VFl, vl.size());
+        if (!rc && (cudaMemcpy(q->VFh, vh.data(), vh.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(q->VFl, vl.data(), vl.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)) {
+            gad_set_error("gad_qnet_create: upload of the split VF tables failed");
+            rc = GAD_ECUDA;
+        }
+    }
     up(&q->ln2_g, h_weights[8], QN_D);
     up(&q->ln2_b, h_weights[9], QN_D);
     up(&q->W1, h_weights[10], (size_t)h1 * q->K);
@@ -883,6 +1136,8 @@ extern "C" int gad_qnet_destroy(gad_qnet *q)
     float *f[] = {q->X, q->T, q->VF, q->ln2_g, q->ln2_b, q->W1, q->b1, q->W2, q->b2, q->W3, q->b3, q->Z, q->H1, q->H2, q->Q};
     for (float *p : f) cudaFree(p);
     cudaFree(q->Z2);
+    cudaFree(q->VFh);
+    cudaFree(q->VFl);
     if (q->tc1) {
         tc_layer_free(q->tc1);
         delete q->tc1;
