@@ -124,10 +124,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, bool SPLIT_OUT>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const float *__restrict__ bias, float out_scale, float *__restrict__ C, int ldc,
+                      const float *__restrict__ bias, float out_scale, void *__restrict__ Cout, int ldc, int lo_offset,
                       const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky)
 {
     using C_ = Cfg<BN>;
@@ -257,26 +257,47 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const long long row = (long long)m_blk * BM + quarter * 32 + lane;
             const int n0 = n_blk * BN + half * HALF;
             if (row < M) {
-                float *dst = C + (size_t)row * ldc + n0;
 #pragma unroll
-                for (int j = 0; j < HALF; j += 4) {
-                    float4 v;
-                    float *pv = reinterpret_cast<float *>(&v);
+                for (int j = 0; j < HALF; j += 8) {
+                    float x[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float x = 0.f;
+                    for (int u = 0; u < 8; ++u) {
+                        x[u] = 0.f;
                         if (n0 + j + u < N) {
-                            x = fmaf(acc[j + u], out_scale, bias[n0 + j + u]);
-                            if (leaky) x = x > 0.f ? x : 0.01f * x;
+                            x[u] = fmaf(acc[j + u], out_scale, bias[n0 + j + u]);
+                            if (leaky) x[u] = x[u] > 0.f ? x[u] : 0.01f * x[u];
                         }
-                        pv[u] = x;
                     }
-                    if (n0 + j + 3 < N) {
-                        *reinterpret_cast<float4 *>(dst + j) = v;
-                    } else {
+                    if (n0 + j >= N) continue;
+                    if constexpr (SPLIT_OUT) {           // (hi | lo) fp16 activations of the next layer
+                        __half *dh = reinterpret_cast<__half *>(Cout) + (size_t)row * ldc + n0 + j;
+                        __half hi[8], lo[8];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (n0 + j + u < N) dst[j + u] = pv[u];
+                        for (int u = 0; u < 8; ++u) {
+                            hi[u] = __float2half_rn(x[u]);
+                            lo[u] = __float2half_rn(x[u] - __half2float(hi[u]));
+                        }
+                        if (n0 + j + 7 < N) {
+                            *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(hi);
+                            *reinterpret_cast<uint4 *>(dh + lo_offset) = *reinterpret_cast<const uint4 *>(lo);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (n0 + j + u < N) {
+                                    dh[u] = hi[u];
+                                    dh[lo_offset + u] = lo[u];
+                                }
+                        }
+                    } else {
+                        float *dst = reinterpret_cast<float *>(Cout) + (size_t)row * ldc + n0 + j;
+                        if (n0 + j + 7 < N && (ldc & 3) == 0) {
+                            *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                            *reinterpret_cast<float4 *>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (n0 + j + u < N) dst[u] = x[u];
+                        }
                     }
                 }
             }
@@ -288,18 +309,19 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
 }
 
-// fp32 weights [N][K] -> fp16 [Npad][2K] = (hi | lo) of w * 2^s; rows >= N are zero
-__global__ void split_weights_kernel(const float *__restrict__ W, int N, int Npad, int K, float scale, __half *__restrict__ out)
+// fp32 weights [N][K] -> fp16 [Npad][2*Kpad] = (hi | lo) of w * 2^s; rows >= N and columns >= K are zero
+__global__ void split_weights_kernel(const float *__restrict__ W, int N, int Npad, int K, int Kpad, float scale,
+                                     __half *__restrict__ out)
 {
-    const long long total = (long long)Npad * K;
+    const long long total = (long long)Npad * Kpad;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long n = i / K;
-        const int k = (int)(i - n * K);
-        const float w = n < N ? W[i] * scale : 0.f;
+        const long long n = i / Kpad;
+        const int k = (int)(i - n * Kpad);
+        const float w = (n < N && k < K) ? W[(size_t)n * K + k] * scale : 0.f;
         const __half hi = __float2half_rn(w);
         const __half lo = __float2half_rn(w - __half2float(hi));
-        out[(size_t)n * 2 * K + k] = hi;
-        out[(size_t)n * 2 * K + K + k] = lo;
+        out[(size_t)n * 2 * Kpad + k] = hi;
+        out[(size_t)n * 2 * Kpad + Kpad + k] = lo;
     }
 }
 
@@ -337,13 +359,22 @@ int encode_map(CUtensorMap *map, const void *base, long long rows, long long col
 // ---------------------------------------------------------------------------------------------
 // host interface used by qnet.cu
 // ---------------------------------------------------------------------------------------------
-int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K)
+template <int BN>
+int set_smem_attr()
 {
-    GAD_REQUIRE(K % BK == 0, "tcgen05 layer: K=%d must be a multiple of %d", K, BK);
+    GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    return GAD_OK;
+}
+
+int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, int BN)
+{
+    GAD_REQUIRE(BN == TC_BN_L1 || BN == TC_BN_L2 || BN == TC_BN_L3, "tcgen05 layer: unsupported BN=%d", BN);
     L->N = N;
     L->K = K;
-    L->BN = TC_BN;
-    L->Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
+    L->Kpad = (K + BK - 1) / BK * BK;
+    L->BN = BN;
+    L->Npad = (N + BN - 1) / BN * BN;
     float mx = 0.f;
     for (size_t i = 0; i < (size_t)N * K; ++i) mx = fmaxf(mx, fabsf(h_W[i]));
     int s = 0;
@@ -352,15 +383,15 @@ int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K)
     if (s < -60) s = -60;
     L->scale = ldexpf(1.f, s);
     L->inv_scale = ldexpf(1.f, -s);
-    GAD_CUDA(cudaMalloc((void **)&L->W2, (size_t)L->Npad * 2 * K * sizeof(__half)));
-    split_weights_kernel<<<GAD_NUM_SMS * 8, 256>>>(d_W, N, L->Npad, K, L->scale, (__half *)L->W2);
+    GAD_CUDA(cudaMalloc((void **)&L->W2, (size_t)L->Npad * 2 * L->Kpad * sizeof(__half)));
+    split_weights_kernel<<<GAD_NUM_SMS * 8, 256>>>(d_W, N, L->Npad, K, L->Kpad, L->scale, (__half *)L->W2);
     GAD_LAUNCH_CHECK();
     GAD_CUDA(cudaDeviceSynchronize());
-    int rc = encode_map((CUtensorMap *)L->map_b, L->W2, L->Npad, 2ll * K, TC_BN);
+    int rc = encode_map((CUtensorMap *)L->map_b, L->W2, L->Npad, 2ll * L->Kpad, BN);
     if (rc) return rc;
-    GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<TC_BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<TC_BN>::SMEM));
-    return GAD_OK;
+    if (BN == TC_BN_L1) return set_smem_attr<TC_BN_L1>();
+    if (BN == TC_BN_L2) return set_smem_attr<TC_BN_L2>();
+    return set_smem_attr<TC_BN_L3>();
 }
 
 void tc_layer_free(TcLayer *L)
@@ -371,19 +402,31 @@ void tc_layer_free(TcLayer *L)
 
 int tc_layer_bind_a(TcLayer *L, const void *d_A2, long long rows)
 {
-    return encode_map((CUtensorMap *)L->map_a, d_A2, rows, 2ll * L->K, BM);
+    return encode_map((CUtensorMap *)L->map_a, d_A2, rows, 2ll * L->Kpad, BM);
 }
 
-int tc_layer_run(const TcLayer *L, const float *d_bias, float *d_C, int ldc, const int32_t *d_m, long long m_max,
-                 int leaky, cudaStream_t st)
+template <int BN>
+int run_bn(const TcLayer *L, const float *d_bias, void *d_out, int ldc, int lo_offset, int split_out, const int32_t *d_m,
+           long long m_max, int leaky, cudaStream_t st)
 {
-    const long long tiles = ((m_max + BM - 1) / BM) * ((L->N + TC_BN - 1) / TC_BN);
+    const long long tiles = ((m_max + BM - 1) / BM) * ((L->N + BN - 1) / BN);
     if (tiles == 0) return GAD_OK;
     const unsigned grid = (unsigned)(tiles < GAD_NUM_SMS ? tiles : GAD_NUM_SMS);
-    gemm_split_f16_kernel<TC_BN><<<grid, 64 + 32 * EPI_WARPS, Cfg<TC_BN>::SMEM, st>>>(*(const CUtensorMap *)L->map_a,
-                                                                       *(const CUtensorMap *)L->map_b, d_bias,
-                                                                       L->inv_scale, d_C, ldc, d_m, m_max, L->N, L->K,
-                                                                       leaky);
+    const CUtensorMap &ma = *(const CUtensorMap *)L->map_a, &mb = *(const CUtensorMap *)L->map_b;
+    if (split_out)
+        gemm_split_f16_kernel<BN, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+    else
+        gemm_split_f16_kernel<BN, false><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
+}
+
+int tc_layer_run(const TcLayer *L, const float *d_bias, void *d_out, int ldc, int lo_offset, int split_out,
+                 const int32_t *d_m, long long m_max, int leaky, cudaStream_t st)
+{
+    if (L->BN == TC_BN_L1) return run_bn<TC_BN_L1>(L, d_bias, d_out, ldc, lo_offset, split_out, d_m, m_max, leaky, st);
+    if (L->BN == TC_BN_L2) return run_bn<TC_BN_L2>(L, d_bias, d_out, ldc, lo_offset, split_out, d_m, m_max, leaky, st);
+    return run_bn<TC_BN_L3>(L, d_bias, d_out, ldc, lo_offset, split_out, d_m, m_max, leaky, st);
 }

@@ -41,7 +41,10 @@ struct gad_qnet {
     uint8_t *tok = nullptr;
     float *Z = nullptr, *H1 = nullptr, *H2 = nullptr, *Q = nullptr;
     __half *Z2 = nullptr;            // (hi | lo) fp16 split of Z, [cap][2K]: A operand of the tcgen05 l1
-    TcLayer *tc1 = nullptr;          // NULL = fp32 SIMT l1 (GAD_QNET_SIMT=1)
+    TcLayer *tc1 = nullptr;          // NULL = fp32 SIMT dense layers (GAD_QNET_SIMT=1)
+    TcLayer *tc2 = nullptr, *tc3 = nullptr;
+    __half *H1s = nullptr, *H2s = nullptr;   // (hi | lo) activations between the tensor-core layers
+    float *Qpre = nullptr;           // l3 output before tanh, [cap][64]
     int32_t *act = nullptr;
     // episode state for `ecap` episodes
     long long ecap = 0;
@@ -716,6 +719,28 @@ dense_kernel(const float *__restrict__ A, const float *__restrict__ W, const flo
     }
 }
 
+// Environment.step (env.py:246-259) for episode e with the greedy action; one thread
+__device__ __forceinline__ void env_step(const gad_qnet &net, int e, int action, int32_t *next_active, int32_t *next_count)
+{
+    const int rows = net.rows, cols = net.cols;
+    uint8_t *hd = net.heads + (size_t)e * rows;
+    for (int r = 0; r < rows; ++r)
+        if (!((action >> r) & 1) && hd[r] >= cols) return;    // illegal action: nothing changes, episode ends
+    const int t = net.steps[e];
+    const int cap = rows * cols;
+    const uint8_t *sub = net.sub + (size_t)e * rows * cols;
+    uint8_t *al = net.aligned + (size_t)e * rows * cap;
+    int left = 0;
+    for (int r = 0; r < rows; ++r) {
+        uint8_t v = GAD_GAP;
+        if (!((action >> r) & 1)) v = sub[r * cols + hd[r]++];
+        al[(size_t)r * cap + t] = v;
+        left += cols - hd[r];
+    }
+    net.steps[e] = t + 1;
+    if (left > 0) next_active[atomicAdd(next_count, 1)] = e;   // done == 1: the episode continues
+}
+
 // ---------------------------------------------------------------------------------------------
 // l3 + tanh * max_value + greedy argmax (+ Environment.step when episodes are running)
 // ---------------------------------------------------------------------------------------------
@@ -748,25 +773,44 @@ head_step_kernel(const gad_qnet net, const float *__restrict__ H2, const int32_t
     if (lane != 0) return;
     if (act_out) act_out[row] = best_a;
     if (!active) return;
-    // Environment.step (env.py:246-259) for this episode
-    const int e = active[row];
-    const int rows = net.rows, cols = net.cols;
-    uint8_t *hd = net.heads + (size_t)e * rows;
-    for (int r = 0; r < rows; ++r)
-        if (!((best_a >> r) & 1) && hd[r] >= cols) return;    // illegal action: nothing changes, episode ends
-    const int t = net.steps[e];
-    const int cap = rows * cols;
-    const uint8_t *sub = net.sub + (size_t)e * rows * cols;
-    uint8_t *al = net.aligned + (size_t)e * rows * cap;
-    int left = 0;
-    for (int r = 0; r < rows; ++r) {
-        uint8_t v = GAD_GAP;
-        if (!((best_a >> r) & 1)) v = sub[r * cols + hd[r]++];
-        al[(size_t)r * cap + t] = v;
-        left += cols - hd[r];
+    env_step(net, active[row], best_a, next_active, next_count);
+}
+
+// tanh * max_value + greedy argmax (+ Environment.step) from the l3 pre-activations of the tensor-core chain
+__global__ void __launch_bounds__(256)
+head_from_logits_kernel(const gad_qnet net, const float *__restrict__ Zpre, int ldz, const int32_t *__restrict__ n_rows_ptr,
+                        long long n_rows_fixed, float max_value, float *__restrict__ Qout,
+                        int32_t *__restrict__ act_out, const int32_t *__restrict__ active,
+                        int32_t *__restrict__ next_active, int32_t *__restrict__ next_count)
+{
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int A = net.A;
+    float best = -INFINITY;
+    int best_a = 0x7fffffff;
+    for (int a = lane; a < A; a += 32) {
+        const float q = tanhf(Zpre[(size_t)row * ldz + a]) * max_value;      // dqn.py:76-77 (bias added by the GEMM)
+        if (Qout) Qout[(size_t)row * A + a] = q;
+        if (q > best) {                                       // ascending a per lane: keeps the first maximum
+            best = q;
+            best_a = a;
+        }
     }
-    net.steps[e] = t + 1;
-    if (left > 0) next_active[atomicAdd(next_count, 1)] = e;   // done == 1: the episode continues
+    for (int o = 16; o > 0; o >>= 1) {                        // torch.argmax: first maximum
+        const float ob = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int oa = __shfl_xor_sync(0xFFFFFFFFu, best_a, o);
+        if (ob > best || (ob == best && oa < best_a)) {
+            best = ob;
+            best_a = oa;
+        }
+    }
+    if (lane != 0) return;
+    if (best_a == 0x7fffffff) best_a = 0;                     // all NaN: torch returns the first index
+    if (act_out) act_out[row] = best_a;
+    if (!active) return;
+    env_step(net, active[row], best_a, next_active, next_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -894,7 +938,9 @@ int ensure_states(gad_qnet *q, long long B)
 {
     if (B <= q->cap) return GAD_OK;
     cudaFree(q->tok); cudaFree(q->Z); cudaFree(q->Z2); cudaFree(q->H1); cudaFree(q->H2); cudaFree(q->Q); cudaFree(q->act);
+    cudaFree(q->H1s); cudaFree(q->H2s); cudaFree(q->Qpre);
     q->tok = nullptr; q->Z = q->H1 = q->H2 = q->Q = nullptr; q->act = nullptr; q->Z2 = nullptr;
+    q->H1s = q->H2s = nullptr; q->Qpre = nullptr;
     q->cap = 0;
     int rc;
     if ((rc = dev_alloc(&q->tok, (size_t)B * q->L))) return rc;
@@ -903,9 +949,19 @@ int ensure_states(gad_qnet *q, long long B)
         if ((rc = dev_alloc(&q->Z2, (size_t)rows * 2 * q->K))) return rc;
         GAD_CUDA(cudaMemset(q->Z2, 0, (size_t)rows * 2 * q->K * sizeof(__half)));
         if ((rc = tc_layer_bind_a(q->tc1, q->Z2, rows))) return rc;
+        const size_t n1 = (size_t)rows * 2 * q->tc2->Kpad, n2 = (size_t)rows * 2 * q->tc3->Kpad;
+        if ((rc = dev_alloc(&q->H1s, n1))) return rc;
+        if ((rc = dev_alloc(&q->H2s, n2))) return rc;
+        if ((rc = dev_alloc(&q->Qpre, (size_t)rows * TC_BN_L3))) return rc;
+        GAD_CUDA(cudaMemset(q->H1s, 0, n1 * sizeof(__half)));          // padding columns stay zero forever
+        GAD_CUDA(cudaMemset(q->H2s, 0, n2 * sizeof(__half)));
+        if ((rc = tc_layer_bind_a(q->tc2, q->H1s, rows))) return rc;
+        if ((rc = tc_layer_bind_a(q->tc3, q->H2s, rows))) return rc;
     } else if ((rc = dev_alloc(&q->Z, (size_t)B * q->K))) return rc;
-    if ((rc = dev_alloc(&q->H1, (size_t)B * q->h1))) return rc;
-    if ((rc = dev_alloc(&q->H2, (size_t)B * q->h2))) return rc;
+    if (!q->tc1) {
+        if ((rc = dev_alloc(&q->H1, (size_t)B * q->h1))) return rc;
+        if ((rc = dev_alloc(&q->H2, (size_t)B * q->h2))) return rc;
+    }
     if ((rc = dev_alloc(&q->Q, (size_t)B * q->A))) return rc;
     if ((rc = dev_alloc(&q->act, (size_t)B))) return rc;
     q->cap = B;
@@ -982,18 +1038,23 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
         encode_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
     }
     GAD_LAUNCH_CHECK();
-    const unsigned mt = (unsigned)((n_max + GM_BM - 1) / GM_BM);
     if (q->tc1) {
-        int rc = tc_layer_run(q->tc1, q->b1, q->H1, q->h1, n_ptr, n_max, 1, st);
+        // l1 -> l2 -> l3 on tcgen05; activations travel as (hi | lo) fp16, the last layer emits fp32 pre-activations
+        int rc = tc_layer_run(q->tc1, q->b1, q->H1s, 2 * q->tc2->Kpad, q->tc2->Kpad, 1, n_ptr, n_max, 1, st);
+        if (!rc) rc = tc_layer_run(q->tc2, q->b2, q->H2s, 2 * q->tc3->Kpad, q->tc3->Kpad, 1, n_ptr, n_max, 1, st);
+        if (!rc) rc = tc_layer_run(q->tc3, q->b3, q->Qpre, TC_BN_L3, 0, 0, n_ptr, n_max, 0, st);
         if (rc) return rc;
+        head_from_logits_kernel<<<(unsigned)((n_max + 7) / 8), 256, 0, st>>>(*q, q->Qpre, TC_BN_L3, n_ptr, n_max, max_value,
+                                                                             Qout, act_out, active, next_active, next_count);
     } else {
+        const unsigned mt = (unsigned)((n_max + GM_BM - 1) / GM_BM);
         dense_kernel<<<dim3((q->h1 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->Z, q->W1, q->b1, q->H1, n_ptr, n_max,
                                                                             q->h1, q->K, 1);
+        dense_kernel<<<dim3((q->h2 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->H1, q->W2, q->b2, q->H2, n_ptr, n_max,
+                                                                            q->h2, q->h1, 1);
+        head_step_kernel<<<(unsigned)((n_max + 7) / 8), 256, 0, st>>>(*q, q->H2, n_ptr, n_max, max_value, Qout, act_out,
+                                                                      active, next_active, next_count);
     }
-    dense_kernel<<<dim3((q->h2 + GM_BN - 1) / GM_BN, mt), 256, 0, st>>>(q->H1, q->W2, q->b2, q->H2, n_ptr, n_max, q->h2,
-                                                                        q->h1, 1);
-    head_step_kernel<<<(unsigned)((n_max + 7) / 8), 256, 0, st>>>(*q, q->H2, n_ptr, n_max, max_value, Qout, act_out,
-                                                                  active, next_active, next_count);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
@@ -1113,9 +1174,14 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
     up(&q->W3, h_weights[14], (size_t)q->A * h2);
     up(&q->b3, h_weights[15], q->A);
     const char *simt = getenv("GAD_QNET_SIMT");
-    if (!rc && !(simt && simt[0] == '1')) {                 // l1 on tcgen05 (default); GAD_QNET_SIMT=1 keeps the fp32 SIMT tiles
+    // dense layers on tcgen05 (default); GAD_QNET_SIMT=1, or more than 64 actions, keeps the fp32 SIMT tiles
+    if (!rc && !(simt && simt[0] == '1') && q->A <= TC_BN_L3) {
         q->tc1 = new TcLayer();
-        rc = tc_layer_init(q->tc1, q->W1, h_weights[10], h1, q->K);
+        q->tc2 = new TcLayer();
+        q->tc3 = new TcLayer();
+        rc = tc_layer_init(q->tc1, q->W1, h_weights[10], h1, q->K, TC_BN_L1);
+        if (!rc) rc = tc_layer_init(q->tc2, q->W2, h_weights[12], h2, h1, TC_BN_L2);
+        if (!rc) rc = tc_layer_init(q->tc3, q->W3, h_weights[14], q->A, h2, TC_BN_L3);
     }
     if (!rc) rc = dev_alloc(&q->counts, 2);
     if (!rc && cudaMallocHost((void **)&q->h_count, 2 * sizeof(int32_t)) != cudaSuccess) {
@@ -1138,10 +1204,14 @@ extern "C" int gad_qnet_destroy(gad_qnet *q)
     cudaFree(q->Z2);
     cudaFree(q->VFh);
     cudaFree(q->VFl);
-    if (q->tc1) {
-        tc_layer_free(q->tc1);
-        delete q->tc1;
-    }
+    for (TcLayer *t : {q->tc1, q->tc2, q->tc3})
+        if (t) {
+            tc_layer_free(t);
+            delete t;
+        }
+    cudaFree(q->H1s);
+    cudaFree(q->H2s);
+    cudaFree(q->Qpre);
     cudaFree(q->tok); cudaFree(q->act); cudaFree(q->sub); cudaFree(q->heads); cudaFree(q->aligned);
     cudaFree(q->steps); cudaFree(q->list0); cudaFree(q->list1); cudaFree(q->counts);
     if (q->h_count) cudaFreeHost(q->h_count);
@@ -1263,10 +1333,10 @@ extern "C" int gad_qnet_time_l1(gad_qnet *q, int64_t M, int reps, float *ms_per_
     GAD_CUDA(cudaEventCreate(&e0));
     GAD_CUDA(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i)
-        if ((rc = tc_layer_run(q->tc1, q->b1, q->H1, q->h1, nullptr, M, 1, st))) return rc;
+        if ((rc = tc_layer_run(q->tc1, q->b1, q->H1s, 2 * q->tc2->Kpad, q->tc2->Kpad, 1, nullptr, M, 1, st))) return rc;
     GAD_CUDA(cudaEventRecord(e0, st));
     for (int i = 0; i < reps; ++i)
-        if ((rc = tc_layer_run(q->tc1, q->b1, q->H1, q->h1, nullptr, M, 1, st))) return rc;
+        if ((rc = tc_layer_run(q->tc1, q->b1, q->H1s, 2 * q->tc2->Kpad, q->tc2->Kpad, 1, nullptr, M, 1, st))) return rc;
     GAD_CUDA(cudaEventRecord(e1, st));
     GAD_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
