@@ -35,6 +35,9 @@ struct gad_qnet {
     float *X = nullptr, *T = nullptr, *VF = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
     __half *VFh = nullptr, *VFl = nullptr;   // VF * 2^sv split into fp16 hi + lo (encode_mma_kernel's B operand)
     float vf_inv_scale = 1.f;
+    // attention as tensor-core products (encode_fa_kernel): Q' = QM * log2(e) * 2^sq and K' = X * 2^sk, fp16 hi + lo
+    __half *Qh = nullptr, *Ql = nullptr, *Kh = nullptr, *Kl = nullptr;
+    float s_inv_scale = 1.f;                 // 2^-(sq+sk): raw MMA sum -> logit in the log2 domain
     float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *W3 = nullptr, *b3 = nullptr;
     // activation scratch for `cap` states
     long long cap = 0;
@@ -622,6 +625,287 @@ int encode_mma_smem_bytes(int L)
     return 2 * LK * EM_VP * 2 + 2 * EM_RB * EM_KP * 2 + EM_RB * 4 + 2 * L * 4 + ((L + 15) & ~15);
 }
 
+// Encoder as a flash-attention style kernel on mma.sync (the default for the reference's window sizes).
+// Nothing is gathered element by element: a state's queries, keys and values are rows of three small
+// (token, position) tables (fp16 hi + lo), i.e. whole 128-byte rows.
+//   S = Q' K'^T          (16 query rows per warp x 16 keys per trip, 3 split MMAs per tile, log2 domain)
+//   online softmax       (running max / sum per row in registers, ex2)
+//   O += P V             (P re-used from the S accumulator registers as the A operand, split hi + lo)
+//   epilogue             O / sum * 2^-sv + residual, LayerNorm across the lane quad, (hi | lo) store
+#define FA_WARPS 6
+#define FA_KP 72           // row stride of the K / V tiles in halves (144 B: conflict-free ldmatrix rows)
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b)
+{
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(FA_WARPS * 32, 2)
+encode_fa_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
+                 const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
+                 __half *__restrict__ Z2out)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int L = net.L;
+    const int LK = (L + 15) & ~15;
+    __half *Ks_h = reinterpret_cast<__half *>(smem);                 // [LK][FA_KP] each
+    __half *Ks_l = Ks_h + (size_t)LK * FA_KP;
+    __half *Vs_h = Ks_l + (size_t)LK * FA_KP;
+    __half *Vs_l = Vs_h + (size_t)LK * FA_KP;
+    int *kj = reinterpret_cast<int *>(Vs_l + (size_t)LK * FA_KP);    // [L] valid key positions
+    uint8_t *tok = reinterpret_cast<uint8_t *>(kj + L);              // [L]
+    __shared__ int s_nk;
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quad = lane & 3, qrow = lane >> 2;
+    const float sc = net.s_inv_scale;
+    const int n_mtiles = (L + 15) >> 4;
+
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();
+        if (tok_in) {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
+            __syncthreads();
+        } else {
+            const int e = active[row];
+            build_tokens(tok, net.sub + (size_t)e * net.rows * net.cols, net.heads + (size_t)e * net.rows, net.rows,
+                         net.cols, L);
+        }
+        if (warp == 0) {                                 // ordered list of unmasked keys
+            int base = 0;
+            for (int j0 = 0; j0 < L; j0 += 32) {
+                const int j = j0 + lane;
+                const bool v = j < L && tok[j] != 0;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, v);
+                if (v) kj[base + __popc(m & ((1u << lane) - 1u))] = j;
+                base += __popc(m);
+            }
+            if (lane == 0) s_nk = base;
+        }
+        __syncthreads();
+        int nk = s_nk;
+        if (nk == 0) {                                   // every key masked: the reference's softmax is uniform over all keys;
+            for (int j = threadIdx.x; j < L; j += blockDim.x) kj[j] = j;   // handled by zeroing the logits below
+            __syncthreads();
+        }
+        const bool all_masked = nk == 0;
+        if (all_masked) nk = L;
+        const int nk16 = (nk + 15) & ~15;
+        // K and V rows of the valid keys: 4 tables x 128 bytes per key, 16 bytes per thread; zero rows up to nk16
+        for (int i = threadIdx.x; i < nk16 * 8; i += blockDim.x) {
+            const int k = i >> 3, c8 = (i & 7) * 8;
+            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, c = a, d = a;
+            if (k < nk) {
+                const int j = kj[k];
+                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c8;
+                a = __ldg(reinterpret_cast<const uint4 *>(net.Kh + src));
+                b = __ldg(reinterpret_cast<const uint4 *>(net.Kl + src));
+                c = __ldg(reinterpret_cast<const uint4 *>(net.VFh + src));
+                d = __ldg(reinterpret_cast<const uint4 *>(net.VFl + src));
+            }
+            const size_t dst = (size_t)k * FA_KP + c8;
+            *reinterpret_cast<uint4 *>(Ks_h + dst) = a;
+            *reinterpret_cast<uint4 *>(Ks_l + dst) = b;
+            *reinterpret_cast<uint4 *>(Vs_h + dst) = c;
+            *reinterpret_cast<uint4 *>(Vs_l + dst) = d;
+        }
+        __syncthreads();
+
+        const uint32_t kb_off = (uint32_t)((((lane & 7) + ((lane >> 4) & 1) * 8) * FA_KP + ((lane >> 3) & 1) * 8) * 2);
+        const uint32_t vb_off = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * FA_KP + (lane >> 4) * 8) * 2);
+        const uint32_t kh0 = (uint32_t)__cvta_generic_to_shared(Ks_h) + kb_off;
+        const uint32_t kl0 = (uint32_t)__cvta_generic_to_shared(Ks_l) + kb_off;
+        const uint32_t vh0 = (uint32_t)__cvta_generic_to_shared(Vs_h) + vb_off;
+        const uint32_t vl0 = (uint32_t)__cvta_generic_to_shared(Vs_l) + vb_off;
+
+        for (int mt = warp; mt < n_mtiles; mt += FA_WARPS) {
+            const int iA = mt * 16 + qrow, iB = iA + 8;
+            const int rA = min(iA, L - 1), rB = min(iB, L - 1);       // rows beyond the state are computed and dropped
+            // Q fragments straight from the tables (A operand layout: a0 rowA k0.., a1 rowB k0.., a2 rowA k8.., a3 rowB k8..)
+            uint32_t qh[4][4], ql[4][4];
+            {
+                const size_t oA = ((size_t)tok[rA] * L + rA) * QN_D + quad * 2, oB = ((size_t)tok[rB] * L + rB) * QN_D + quad * 2;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    qh[ks][0] = __ldg(reinterpret_cast<const uint32_t *>(net.Qh + oA + ks * 16));
+                    qh[ks][1] = __ldg(reinterpret_cast<const uint32_t *>(net.Qh + oB + ks * 16));
+                    qh[ks][2] = __ldg(reinterpret_cast<const uint32_t *>(net.Qh + oA + ks * 16 + 8));
+                    qh[ks][3] = __ldg(reinterpret_cast<const uint32_t *>(net.Qh + oB + ks * 16 + 8));
+                    ql[ks][0] = __ldg(reinterpret_cast<const uint32_t *>(net.Ql + oA + ks * 16));
+                    ql[ks][1] = __ldg(reinterpret_cast<const uint32_t *>(net.Ql + oB + ks * 16));
+                    ql[ks][2] = __ldg(reinterpret_cast<const uint32_t *>(net.Ql + oA + ks * 16 + 8));
+                    ql[ks][3] = __ldg(reinterpret_cast<const uint32_t *>(net.Ql + oB + ks * 16 + 8));
+                }
+            }
+            float o[8][4];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[t][c] = 0.f;
+            float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
+
+            for (int kb = 0; kb < nk16; kb += 16) {
+                float s[2][4];
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[t][c] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t kh[4], kl[4];
+                    ldsm_x4(kh, kh0 + (kb * FA_KP + ks * 16) * 2);
+                    ldsm_x4(kl, kl0 + (kb * FA_KP + ks * 16) * 2);
+                    mma_16816(s[0], ql[ks], kh[0], kh[1]);
+                    mma_16816(s[0], qh[ks], kl[0], kl[1]);
+                    mma_16816(s[0], qh[ks], kh[0], kh[1]);
+                    mma_16816(s[1], ql[ks], kh[2], kh[3]);
+                    mma_16816(s[1], qh[ks], kl[2], kl[3]);
+                    mma_16816(s[1], qh[ks], kh[2], kh[3]);
+                }
+                // logits of this thread: key = kb + 8t + 2*quad + {0,1}; c0,c1 -> row A, c2,c3 -> row B
+                float bxA = -INFINITY, bxB = -INFINITY;
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int key = kb + 8 * t + 2 * quad + (c & 1);
+                        float v = all_masked ? 0.f : s[t][c] * sc;
+                        if (key >= nk) v = -INFINITY;
+                        s[t][c] = v;
+                        if (c < 2) bxA = fmaxf(bxA, v); else bxB = fmaxf(bxB, v);
+                    }
+                bxA = fmaxf(bxA, __shfl_xor_sync(0xFFFFFFFFu, bxA, 1));
+                bxA = fmaxf(bxA, __shfl_xor_sync(0xFFFFFFFFu, bxA, 2));
+                bxB = fmaxf(bxB, __shfl_xor_sync(0xFFFFFFFFu, bxB, 1));
+                bxB = fmaxf(bxB, __shfl_xor_sync(0xFFFFFFFFu, bxB, 2));
+                const float nA = fmaxf(mA, bxA), nB = fmaxf(mB, bxB);      // every 16-key block holds at least one valid key
+                const float fA = exp2f(mA - nA), fB = exp2f(mB - nB);      // exp2(-inf) = 0 on the first block
+                mA = nA;
+                mB = nB;
+                float p[2][4];
+                float sumA = 0.f, sumB = 0.f;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    p[t][0] = exp2f(s[t][0] - nA);
+                    p[t][1] = exp2f(s[t][1] - nA);
+                    p[t][2] = exp2f(s[t][2] - nB);
+                    p[t][3] = exp2f(s[t][3] - nB);
+                    sumA += p[t][0] + p[t][1];
+                    sumB += p[t][2] + p[t][3];
+                }
+                lA = fmaf(lA, fA, sumA);
+                lB = fmaf(lB, fB, sumB);
+                if (__any_sync(0xFFFFFFFFu, fA != 1.f || fB != 1.f)) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        o[t][0] *= fA;
+                        o[t][1] *= fA;
+                        o[t][2] *= fB;
+                        o[t][3] *= fB;
+                    }
+                }
+                // P as the A operand of the next product (16 rows x 16 keys), split hi + lo
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const __half2 hA = __floats2half2_rn(p[t][0], p[t][1]), hB = __floats2half2_rn(p[t][2], p[t][3]);
+                    const float2 fAh = __half22float2(hA), fBh = __half22float2(hB);
+                    ph[2 * t + 0] = *reinterpret_cast<const uint32_t *>(&hA);
+                    ph[2 * t + 1] = *reinterpret_cast<const uint32_t *>(&hB);
+                    pl[2 * t + 0] = pack_half2(p[t][0] - fAh.x, p[t][1] - fAh.y);
+                    pl[2 * t + 1] = pack_half2(p[t][2] - fBh.x, p[t][3] - fBh.y);
+                }
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {         // 16 channels per trip
+                    uint32_t vh[4], vl[4];
+                    ldsm_x4_trans(vh, vh0 + (kb * FA_KP + pr * 16) * 2);
+                    ldsm_x4_trans(vl, vl0 + (kb * FA_KP + pr * 16) * 2);
+                    mma_16816(o[2 * pr], pl, vh[0], vh[1]);
+                    mma_16816(o[2 * pr], ph, vl[0], vl[1]);
+                    mma_16816(o[2 * pr], ph, vh[0], vh[1]);
+                    mma_16816(o[2 * pr + 1], pl, vh[2], vh[3]);
+                    mma_16816(o[2 * pr + 1], ph, vl[2], vl[3]);
+                    mma_16816(o[2 * pr + 1], ph, vh[2], vh[3]);
+                }
+            }
+            // ---- epilogue: the lane quad holds a whole 64-channel row
+            lA += __shfl_xor_sync(0xFFFFFFFFu, lA, 1);
+            lA += __shfl_xor_sync(0xFFFFFFFFu, lA, 2);
+            lB += __shfl_xor_sync(0xFFFFFFFFu, lB, 1);
+            lB += __shfl_xor_sync(0xFFFFFFFFu, lB, 2);
+            const float invA = net.vf_inv_scale / lA, invB = net.vf_inv_scale / lB;
+            const float *xA = net.X + ((size_t)tok[rA] * L + rA) * QN_D + quad * 2;
+            const float *xB = net.X + ((size_t)tok[rB] * L + rB) * QN_D + quad * 2;
+            float smA = 0.f, smB = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float2 a = __ldg(reinterpret_cast<const float2 *>(xA + 8 * t));
+                const float2 b = __ldg(reinterpret_cast<const float2 *>(xB + 8 * t));
+                o[t][0] = fmaf(o[t][0], invA, a.x);
+                o[t][1] = fmaf(o[t][1], invA, a.y);
+                o[t][2] = fmaf(o[t][2], invB, b.x);
+                o[t][3] = fmaf(o[t][3], invB, b.y);
+                smA += o[t][0] + o[t][1];
+                smB += o[t][2] + o[t][3];
+            }
+            smA += __shfl_xor_sync(0xFFFFFFFFu, smA, 1);
+            smA += __shfl_xor_sync(0xFFFFFFFFu, smA, 2);
+            smB += __shfl_xor_sync(0xFFFFFFFFu, smB, 1);
+            smB += __shfl_xor_sync(0xFFFFFFFFu, smB, 2);
+            const float muA = smA * (1.f / QN_D), muB = smB * (1.f / QN_D);
+            float vrA = 0.f, vrB = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                o[t][0] -= muA;
+                o[t][1] -= muA;
+                o[t][2] -= muB;
+                o[t][3] -= muB;
+                vrA += o[t][0] * o[t][0] + o[t][1] * o[t][1];
+                vrB += o[t][2] * o[t][2] + o[t][3] * o[t][3];
+            }
+            vrA += __shfl_xor_sync(0xFFFFFFFFu, vrA, 1);
+            vrA += __shfl_xor_sync(0xFFFFFFFFu, vrA, 2);
+            vrB += __shfl_xor_sync(0xFFFFFFFFu, vrB, 1);
+            vrB += __shfl_xor_sync(0xFFFFFFFFu, vrB, 2);
+            const float rsA = rsqrtf(vrA * (1.f / QN_D) + 1e-6f), rsB = rsqrtf(vrB * (1.f / QN_D) + 1e-6f);   // models.py:166
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int c = 8 * t + quad * 2;
+                const float2 g = *reinterpret_cast<const float2 *>(net.ln2_g + c);
+                const float2 be = *reinterpret_cast<const float2 *>(net.ln2_b + c);
+                const float zA0 = o[t][0] * rsA * g.x + be.x, zA1 = o[t][1] * rsA * g.y + be.y;
+                const float zB0 = o[t][2] * rsB * g.x + be.x, zB1 = o[t][3] * rsB * g.y + be.y;
+                if (Z2out) {
+                    if (iA < L) {
+                        __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)iA * QN_D + c;
+                        const __half2 h = __floats2half2_rn(zA0, zA1);
+                        const float2 hf = __half22float2(h);
+                        *reinterpret_cast<__half2 *>(zh) = h;
+                        *reinterpret_cast<__half2 *>(zh + net.K) = __floats2half2_rn(zA0 - hf.x, zA1 - hf.y);
+                    }
+                    if (iB < L) {
+                        __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)iB * QN_D + c;
+                        const __half2 h = __floats2half2_rn(zB0, zB1);
+                        const float2 hf = __half22float2(h);
+                        *reinterpret_cast<__half2 *>(zh) = h;
+                        *reinterpret_cast<__half2 *>(zh + net.K) = __floats2half2_rn(zB0 - hf.x, zB1 - hf.y);
+                    }
+                } else {
+                    if (iA < L) *reinterpret_cast<float2 *>(Zout + (size_t)row * net.K + (size_t)iA * QN_D + c) = make_float2(zA0, zA1);
+                    if (iB < L) *reinterpret_cast<float2 *>(Zout + (size_t)row * net.K + (size_t)iB * QN_D + c) = make_float2(zB0, zB1);
+                }
+            }
+        }
+    }
+}
+
+int encode_fa_smem_bytes(int L)
+{
+    const int LK = (L + 15) & ~15;
+    return 4 * LK * FA_KP * 2 + L * 4 + ((L + 15) & ~15);
+}
+
 // ---------------------------------------------------------------------------------------------
 // dense layers: C[M][N] = leaky_relu(A[M][K] . W[N][K]^T + b), fp32 SIMT tiles 128x128x16
 // ---------------------------------------------------------------------------------------------
@@ -1014,8 +1298,18 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
                    float max_value, float *Qout, int32_t *act_out, int32_t *next_active, int32_t *next_count,
                    cudaStream_t st)
 {
-    const char *enc = getenv("GAD_QNET_ENCODER");      // "simt" keeps the fp32 register-tiled encoder (A/B testing)
-    if (q->L <= 192 && !(enc && enc[0] == 's')) {
+    // GAD_QNET_ENCODER (A/B testing): unset = flash-attention style kernel, "mma" = table logits + mma.sync
+    // product, "simt" = table logits + fp32 register tiles
+    const char *enc = getenv("GAD_QNET_ENCODER");
+    if (encode_fa_smem_bytes(q->L) <= 110 * 1024 && !enc) {
+        const int bytes = encode_fa_smem_bytes(q->L);
+        if (bytes > 48 * 1024)
+            GAD_CUDA(cudaFuncSetAttribute(encode_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        long long per_sm = (224 * 1024) / (bytes + 1024);
+        if (per_sm > 4) per_sm = 4;
+        const long long grid = n_max < (long long)GAD_NUM_SMS * per_sm ? n_max : (long long)GAD_NUM_SMS * per_sm;
+        encode_fa_kernel<<<(unsigned)grid, FA_WARPS * 32, bytes, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
+    } else if (q->L <= 192 && !(enc && enc[0] == 's')) {
         const int bytes = encode_mma_smem_bytes(q->L);
         if (bytes > 48 * 1024)
             GAD_CUDA(cudaFuncSetAttribute(encode_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1165,6 +1459,32 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
             rc = GAD_ECUDA;
         }
     }
+    {
+        auto split_upload = [&](const std::vector<double> &src, double mul, __half **dh, __half **dl, int *shift) {
+            double mx = 0;
+            for (double v : src) mx = fmax(mx, fabs(v * mul));
+            int sh = mx > 0 ? (int)floor(log2(16384.0 / mx)) : 0;
+            sh = sh > 40 ? 40 : (sh < -40 ? -40 : sh);
+            *shift = sh;
+            std::vector<__half> vh(src.size()), vl(src.size());
+            for (size_t i = 0; i < src.size(); ++i) {
+                const float v = (float)ldexp(src[i] * mul, sh);
+                vh[i] = __float2half_rn(v);
+                vl[i] = __float2half_rn(v - __half2float(vh[i]));
+            }
+            if (!rc) rc = dev_alloc(dh, vh.size());
+            if (!rc) rc = dev_alloc(dl, vl.size());
+            if (!rc && (cudaMemcpy(*dh, vh.data(), vh.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess ||
+                        cudaMemcpy(*dl, vl.data(), vl.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)) {
+                gad_set_error("gad_qnet_create: upload of a split table failed");
+                rc = GAD_ECUDA;
+            }
+        };
+        int sq = 0, sk = 0;
+        split_upload(QM, 1.4426950408889634, &q->Qh, &q->Ql, &sq);      // logits in the log2 domain: exp -> ex2
+        split_upload(Xd, 1.0, &q->Kh, &q->Kl, &sk);
+        q->s_inv_scale = ldexpf(1.f, -(sq + sk));
+    }
     up(&q->ln2_g, h_weights[8], QN_D);
     up(&q->ln2_b, h_weights[9], QN_D);
     up(&q->W1, h_weights[10], (size_t)h1 * q->K);
@@ -1204,6 +1524,7 @@ extern "C" int gad_qnet_destroy(gad_qnet *q)
     cudaFree(q->Z2);
     cudaFree(q->VFh);
     cudaFree(q->VFl);
+    cudaFree(q->Qh); cudaFree(q->Ql); cudaFree(q->Kh); cudaFree(q->Kl);
     for (TcLayer *t : {q->tc1, q->tc2, q->tc3})
         if (t) {
             tc_layer_free(t);

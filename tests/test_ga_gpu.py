@@ -545,3 +545,82 @@ def test_inference_driver_writes_reference_report_format(gpu, weight_files, cfg,
     random.seed(1)
     import GA as ga_mod
     assert ga_mod.GA(sets[mod.datasets[0]], "sp").run(name) == want
+
+
+# ------------------------------------------------------------------------------------------- BASELINE sizes: properties
+def _synthetic_population(R, C, P, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(1, 5, size=(R, C), dtype=np.uint8)
+    gaps = max(1, round(C * 0.05))
+    W = C + gaps
+    stride = -(-W // 16) * 16
+    boards = np.full((P, R, stride), 5, np.uint8)
+    rowlen = np.full((P, R), C, np.int32)
+    boards[:, :, :C] = base[None]
+    n_clone = P // 4
+    pos = rng.integers(0, C, size=(P - n_clone, R, gaps))
+    for g in range(gaps):                                  # insert one gap per pass (vectorised over boards and rows)
+        p = pos[:, :, g][:, :, None]
+        idx = np.arange(stride)[None, None, :]
+        sub = boards[n_clone:]
+        shifted = np.concatenate((sub[:, :, :1], sub[:, :, :-1]), axis=2)
+        boards[n_clone:] = np.where(idx < p, sub, np.where(idx == p, 5, shifted))
+        rowlen[n_clone:] += 1
+    return boards, rowlen
+
+
+@pytest.mark.parametrize("R,C,P,rw,cw,mode", [(6, 60, 65536, 6, 30, "mo"), (20, 200, 16384, 3, 30, "cs"),
+                                              (64, 1000, 1024, 3, 30, "sp")])
+def test_generation_properties_at_baseline_shapes(gpu, weight_files, cfg, R, C, P, rw, cw, mode):
+    """One whole generation at the BASELINE board shapes (c3 at full population; c4/c5 shapes at a reduced
+    population), checked through size-independent properties: every board keeps each row's residues in order
+    (mutation and crossover only move gaps / recombine whole rows of boards with the same residues), the
+    population size is restored, scores of a sample agree with the oracle, the hall of fame dominates."""
+    from population import DevicePopulation
+    from DPAMSA.dqn import load_qnet
+    name, _ = weight_files[(rw, cw)]
+    boards, rowlen = _synthetic_population(R, C, P, R * 7 + C)
+    residues = [row[row != 5].tolist() for row in boards[0]]
+    extra = (rw - 1) * cw
+    wide = np.full((P, R, -(-(boards.shape[2] + extra) // 16) * 16), 5, np.uint8)
+    wide[:, :, :boards.shape[2]] = boards
+    dev = DevicePopulation.from_numpy(wide, rowlen, capacity=P)
+    net = load_qnet(name, rw, cw)
+    w = WEIGHTS
+    dev.fitness(*w)
+    dev.hof_update(mode)
+    n_mut = round(P * 0.25)
+    idx = dev.rank_order(mode, n_mut)
+    tile = dev.worst_tiles(idx, rw, cw, mode, *w)
+    assert int(tile.min().item()) >= 0
+    dev.mutate(net, idx, tile, cw * (rw * (rw - 1) / 2 * 4))
+    dev.fitness(*w)
+    dev.hof_update(mode)
+    n_keep = dev.select(mode, P // 2)
+    assert (n_keep == P // 2) if mode != "mo" else (n_keep >= 1)
+    dev.fitness(*w)
+    dev.hof_update(mode)
+    random.seed(9)
+    plan = np.array(O.crossover_plan(n_keep, R, P - n_keep), dtype=np.int32).reshape(-1, 3)
+    dev.crossover(plan, 0)
+    sp, em, al = [t.clone() for t in dev.fitness(*w)]
+    dev.hof_update(mode)
+    assert dev.n == P
+    b, r = dev.to_numpy()
+    rng = np.random.default_rng(1)
+    for p in rng.choice(P, 64, replace=False):
+        assert len(set(r[p].tolist())) == 1                                   # rectangular after the pass
+        for k in range(R):
+            row = b[p, k, :r[p, k]]
+            assert row[row != 5].tolist() == residues[k]                      # residues preserved, in order
+        board = [b[p, k, :r[p, k]].tolist() for k in range(R)]
+        assert int(sp[p]) == O.sum_of_pairs(board, 0, R, 0, len(board[0]))
+        assert int(em[p]) == O.exact_columns(board, 0, R, 0, len(board[0]))
+        assert not any(all(row[c] == 5 for row in board) for c in range(len(board[0])))   # no all-gap column left
+    hb, (hidx, hsp, hem, hal) = dev.hof_numpy()
+    if mode == "sp":
+        assert hsp >= int(sp.max())
+    elif mode == "cs":
+        assert hem / hal >= float((em.double() / al.double()).max())
+    for k in range(R):
+        assert hb[k][hb[k] != 5].tolist() == residues[k]
