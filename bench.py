@@ -302,6 +302,7 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
         phases = {"mutation": 0.0, "fitness": 0.0, "selection": 0.0, "crossover": 0.0}
         evals = forwards = episodes = 0
         total = 0.0
+        per_gen = []
         for it in range(n_warm + n_gen):
             e0, f0 = counters()
             stamps = []
@@ -312,6 +313,8 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
                 fn()
                 sync()
                 stamps.append((name, time.perf_counter() - t0))
+            per_gen.append({"ms": round(1e3 * sum(dt for _, dt in stamps), 2), "forwards": counters()[1] - f0,
+                            "timed": it >= n_warm})
             if it >= n_warm:
                 for name, dt in stamps:
                     phases[name] += dt
@@ -342,7 +345,10 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
             "hall_of_fame_score": list(hof[1]) if hof else None,
             "reference_net_flops_per_state": QNET_FLOPS.get((rw, cw)),
             "individuals_per_s": P_total * n_gen / total,
+            "per_generation": per_gen,
             "roofline": tensor,
+            "forward_ms_full_batch": (qnet_forward_ms(model, rw, cw, min(32768, round(P_total * config.MUTATION_RATE)))
+                                      if rank == 0 else None),
         }
         if world > 1:
             out["collective_bytes_received_per_generation_rank0"] = g.comm_bytes / (n_warm + n_gen)
@@ -374,6 +380,36 @@ def l1_tensor_roofline(model, rw, cw, M):
             "flops_per_launch": fl.value, "peak_source": src,
             "note": "executed FLOPs: three fp16 passes (hi.hi + lo.hi + hi.lo) give fp32-class accuracy; the "
                     "single-pass-equivalent (algorithmic 2*M*K*N) rate is one third of `achieved`"}
+
+
+def qnet_forward_ms(model, rw, cw, B):
+    """One full-batch Net.forward + argmax (encoder, l1, l2, l3, head) over B random environment-like states,
+    CUDA events on the launching stream - the per-step cost of the lock-step episodes at full batch."""
+    import torch
+    import _native as nat
+    from DPAMSA import dqn
+    net = dqn.load_qnet(model, rw, cw)
+    rng = np.random.default_rng(5)
+    L = rw * (cw + 1)
+    states = np.zeros((B, L), np.uint8)
+    fill = rng.integers(L // 2, L + 1, size=B)
+    body = rng.integers(1, 6, size=(B, L), dtype=np.uint8)
+    states[np.arange(L)[None, :] < fill[:, None]] = body[np.arange(L)[None, :] < fill[:, None]]
+    d_states = torch.from_numpy(states).cuda()
+    d_act = torch.empty(B, dtype=torch.int32, device="cuda")
+    def run():
+        nat.call("gad_qnet_forward", net.handle, d_states.data_ptr(), B, 1800.0, None, d_act.data_ptr(),
+                 nat.current_stream_ptr())
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 10
 
 
 def cpu_generation_port(workload, cores, n_mut_per_core=1):

@@ -746,23 +746,28 @@ encode_fa_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
 
             for (int kb = 0; kb < nk16; kb += 16) {
-                float s[2][4];
+                // six independent accumulation chains (3 split terms x 2 key tiles) instead of two chains of 12 MMAs
+                float s[2][4], s1[2][4], s2[2][4];
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) s[t][c] = 0.f;
+                    for (int c = 0; c < 4; ++c) s[t][c] = s1[t][c] = s2[t][c] = 0.f;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     uint32_t kh[4], kl[4];
                     ldsm_x4(kh, kh0 + (kb * FA_KP + ks * 16) * 2);
                     ldsm_x4(kl, kl0 + (kb * FA_KP + ks * 16) * 2);
-                    mma_16816(s[0], ql[ks], kh[0], kh[1]);
-                    mma_16816(s[0], qh[ks], kl[0], kl[1]);
+                    mma_16816(s1[0], ql[ks], kh[0], kh[1]);
+                    mma_16816(s2[0], qh[ks], kl[0], kl[1]);
                     mma_16816(s[0], qh[ks], kh[0], kh[1]);
-                    mma_16816(s[1], ql[ks], kh[2], kh[3]);
-                    mma_16816(s[1], qh[ks], kl[2], kl[3]);
+                    mma_16816(s1[1], ql[ks], kh[2], kh[3]);
+                    mma_16816(s2[1], qh[ks], kl[2], kl[3]);
                     mma_16816(s[1], qh[ks], kh[2], kh[3]);
                 }
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[t][c] += s1[t][c] + s2[t][c];
                 // logits of this thread: key = kb + 8t + 2*quad + {0,1}; c0,c1 -> row A, c2,c3 -> row B
                 float bxA = -INFINITY, bxB = -INFINITY;
 #pragma unroll
