@@ -152,9 +152,10 @@ class GA:
             self._dev.hof_valid = False
 
     # ------------------------------------------------------------------ a3
-    def _generate_host(self):
+    def _generate_host(self, own_first=0, own_step=1, min_stride=0):
         """GA.py:71-94 through the CPython-compatible MT19937 replay (same draws as the reference):
-        host arrays (boards uint8 [P,R,stride], rowlen int32 [P,R])."""
+        host arrays (boards uint8 [n,R,stride], rowlen int32 [n,R]) of the boards p with
+        p % own_step == own_first (all of them by default)."""
         nat.require_device()
         seqs = [[nucleotides_map[nuc] for nuc in seq] for seq in self.sequences]      # KeyError like GA.py:79
         R = len(seqs)
@@ -168,12 +169,18 @@ class GA:
         seq_arr = np.full((R, cstride), 5, dtype=np.uint8)
         for r, s in enumerate(seqs):
             seq_arr[r, :len(s)] = s
-        stride = -(-(cstride + int(ngaps.max())) // 16) * 16
-        boards = np.empty((P, R, stride), dtype=np.uint8)
-        rowlen = np.empty((P, R), dtype=np.int32)
+        stride = max(-(-(cstride + int(ngaps.max())) // 16) * 16, -(-int(min_stride) // 16) * 16)
+        n_own = len(range(own_first, P, own_step))
+        boards = np.empty((n_own, R, stride), dtype=np.uint8)
+        rowlen = np.empty((n_own, R), dtype=np.int32)
         state, meta = _mt_state()
-        nat.call("gad_mt_population_host", state.ctypes.data, seq_arr.ctypes.data, seqlen.ctypes.data, cstride,
-                 ngaps.ctypes.data, R, P, n_clone, boards.ctypes.data, rowlen.ctypes.data, stride)
+        if own_step == 1:
+            nat.call("gad_mt_population_host", state.ctypes.data, seq_arr.ctypes.data, seqlen.ctypes.data, cstride,
+                     ngaps.ctypes.data, R, P, n_clone, boards.ctypes.data, rowlen.ctypes.data, stride)
+        else:
+            nat.call("gad_mt_population_shard_host", state.ctypes.data, seq_arr.ctypes.data, seqlen.ctypes.data, cstride,
+                     ngaps.ctypes.data, R, P, n_clone, own_first, own_step, boards.ctypes.data, rowlen.ctypes.data,
+                     stride)
         _mt_restore(state, meta)
         return boards, rowlen
 

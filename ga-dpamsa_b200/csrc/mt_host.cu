@@ -129,3 +129,68 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
     mt_state[624] = (uint32_t)g.pos;
     return GAD_OK;
 }
+
+// Sharded form of gad_mt_population_host: the whole random stream of GA.py:71-94 is consumed (so every
+// rank stays in step with the reference's generator), but only the boards p with p % own_step == own_first
+// are materialised, densely, into h_boards / h_rowlen (ceil((P - own_first) / own_step) boards).
+// Gap positions are tracked instead of shifting the row at every insert: inserting at position a moves every
+// earlier gap at or right of a one cell to the right - O(gaps^2) per row instead of O(gaps * length).
+extern "C" int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
+                                            int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
+                                            int64_t own_first, int64_t own_step, uint8_t *h_boards, int32_t *h_rowlen,
+                                            int stride)
+{
+    GAD_REQUIRE(mt_state && h_seqs && h_seqlen && h_ngaps && h_boards && h_rowlen, "gad_mt_population_shard_host: null pointer");
+    GAD_REQUIRE(R >= 1 && P >= 0 && n_clone >= 0 && n_clone <= P && stride >= 1 && own_step >= 1 && own_first >= 0 &&
+                    own_first < own_step,
+                "gad_mt_population_shard_host: bad sizes");
+    int max_gaps = 0;
+    for (int r = 0; r < R; ++r) {
+        GAD_REQUIRE(h_seqlen[r] >= 0 && h_seqlen[r] <= seq_stride, "gad_mt_population_shard_host: bad sequence length");
+        const bool grows = n_clone < P;
+        GAD_REQUIRE(h_seqlen[r] + (grows ? h_ngaps[r] : 0) <= stride, "gad_mt_population_shard_host: row %d does not fit the stride", r);
+        GAD_REQUIRE(!grows || h_seqlen[r] >= 1, "empty sequence: the reference raises ValueError in randint(0, -1)");
+        max_gaps = h_ngaps[r] > max_gaps ? h_ngaps[r] : max_gaps;
+    }
+    MT g{mt_state, (int)mt_state[624]};
+    GAD_REQUIRE(g.pos >= 0 && g.pos <= 624, "gad_mt_population_shard_host: corrupt MT19937 position %d", g.pos);
+    std::vector<int> gaps((size_t)max_gaps + 1);
+    int64_t out = 0;
+    for (int64_t p = 0; p < P; ++p) {
+        const bool mine = p % own_step == own_first;
+        for (int r = 0; r < R; ++r) {
+            const int len0 = h_seqlen[r];
+            const int ng = p >= n_clone ? h_ngaps[r] : 0;
+            if (!mine) {                                   // keep the generator in step only
+                for (int k = 0; k < ng; ++k) g.randbelow((uint32_t)(len0 + k));
+                continue;
+            }
+            uint8_t *row = h_boards + ((size_t)out * R + r) * stride;
+            const uint8_t *seq = h_seqs + (size_t)r * seq_stride;
+            for (int k = 0; k < ng; ++k) {
+                const int at = (int)g.randbelow((uint32_t)(len0 + k));      // randint(0, len - 1)
+                for (int q = 0; q < k; ++q)
+                    if (gaps[q] >= at) ++gaps[q];
+                gaps[k] = at;
+            }
+            // emit: gap positions are distinct cells of the final row
+            const int len = len0 + ng;
+            memset(row, GAD_GAP, (size_t)stride);
+            if (ng == 0) {
+                memcpy(row, seq, (size_t)len0);
+            } else {
+                // mark gaps, then stream the residues into the other cells
+                for (int k = 0; k < ng; ++k) row[gaps[k]] = 0;
+                int src = 0;
+                for (int c = 0; c < len; ++c) {
+                    if (row[c] == 0) row[c] = GAD_GAP;
+                    else row[c] = seq[src++];
+                }
+            }
+            h_rowlen[(size_t)out * R + r] = len;
+        }
+        if (mine) ++out;
+    }
+    mt_state[624] = (uint32_t)g.pos;
+    return GAD_OK;
+}

@@ -57,18 +57,25 @@ class ShardedGA:
         self.comm_bytes = 0          # bytes this rank received through collectives
 
     # ------------------------------------------------------------------ collectives
-    def _all_gather_padded(self, t: torch.Tensor, counts):
-        """All-gather of per-rank tensors whose first dimension differs: pad to the largest, gather,
-        return the concatenation of the valid parts in rank order."""
+    def _all_gather_padded(self, t: torch.Tensor, counts, compact=True):
+        """All-gather of per-rank tensors whose first dimension differs: pad to the largest and gather into
+        one buffer. compact=True returns the concatenation of the valid parts in rank order; compact=False
+        returns the padded buffer [world * max(counts), ...] (rank r's rows start at r * max(counts)) and
+        saves the second copy - used for the survivors' boards."""
         if self.world == 1:
             return t
         mx = max(counts)
-        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        out = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(out, pad, group=self.group)
-        self.comm_bytes += pad.numel() * pad.element_size() * (self.world - 1)
-        return torch.cat([o[:c] for o, c in zip(out, counts)])
+        out = torch.empty((self.world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        if t.shape[0] == mx:
+            src = t.contiguous()
+        else:
+            src = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            src[:t.shape[0]] = t
+        dist.all_gather_into_tensor(out, src, group=self.group)
+        self.comm_bytes += src.numel() * src.element_size() * (self.world - 1)
+        if not compact:
+            return out
+        return torch.cat([out[r * mx:r * mx + c] for r, c in enumerate(counts)])
 
     def _counts(self, n_local: int):
         if self.world == 1:
@@ -81,14 +88,14 @@ class ShardedGA:
     # ------------------------------------------------------------------ a3
     def generate_population(self):
         """Every rank replays the same `random` stream (GA.py:71-94) and keeps its slice."""
-        boards, rowlen = self.backend.generate_full_population(self.sequences, self.population_size)
-        P = boards.shape[0]
+        P = self.population_size
         lo = shard_bounds(P, self.world)
         # interleaved placement (individual i -> rank i % world): the clones - the first CLONE_RATE of the
-        # list and usually the best scored, hence the first to be mutated - spread evenly over the ranks
+        # list and usually the best scored, hence the first to be mutated - spread evenly over the ranks.
+        # Every rank consumes the whole random stream but materialises only its own boards.
+        boards, rowlen = self.backend.generate_shard(self.sequences, P, self.rank, self.world)
         mine = np.arange(self.rank, P, self.world)
-        self.backend.adopt(np.ascontiguousarray(boards[mine]), np.ascontiguousarray(rowlen[mine]),
-                           capacity=lo[1] - lo[0])
+        self.backend.adopt(boards, rowlen, capacity=lo[1] - lo[0])
         self.gidx = torch.from_numpy(mine).to(self.backend.device, torch.int64)
         self.n_global = P
 
@@ -173,11 +180,15 @@ class ShardedGA:
             first = sum(need[:self.rank])
             mine = plan[first:first + need[self.rank]]
             boards, rowlen = self.backend.survivors()
-            all_boards = self._all_gather_padded(boards, counts)
-            all_rowlen = self._all_gather_padded(rowlen, counts)
+            all_boards = self._all_gather_padded(boards, counts, compact=False)      # [world * max, R, stride]
+            all_rowlen = self._all_gather_padded(rowlen, counts, compact=False)
             all_gidx = self._all_gather_padded(self.gidx, counts)
-            pos = torch.zeros(S, dtype=torch.int64, device=self.backend.device)
-            pos.index_copy_(0, all_gidx, torch.arange(S, device=self.backend.device))
+            mx = max(counts)
+            dev = self.backend.device
+            where = torch.cat([torch.arange(r * mx, r * mx + c, device=dev) for r, c in enumerate(counts)]) \
+                if self.world > 1 else torch.arange(S, device=dev)
+            pos = torch.zeros(S, dtype=torch.int64, device=dev)
+            pos.index_copy_(0, all_gidx, where)
             self.backend.crossover_from(all_boards, all_rowlen, pos, mine)
             kids = torch.arange(S + first, S + first + need[self.rank], dtype=torch.int64, device=self.backend.device)
             self.gidx = torch.cat((self.gidx, kids))
@@ -225,21 +236,25 @@ class DeviceBackend:
         self._rank_tmp = None
 
     # -- population ---------------------------------------------------------------------------
-    def generate_full_population(self, sequences, P):
+    def generate_shard(self, sequences, P, rank, world):
         import GA as ga_mod
         g = ga_mod.GA.__new__(ga_mod.GA)
         g.sequences, g.mode, g.population_size, g._dev = sequences, 'sp', P, None
         g._device = self.device
-        return g._generate_host()
+        extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
+        width = max(len(s) for s in sequences) + max(1, round(max(len(s) for s in sequences) * config.GAP_RATE))
+        return g._generate_host(rank, world, min_stride=width + extra)     # final stride at once: no second host copy
 
     def adopt(self, boards, rowlen, capacity):
         from population import DevicePopulation
         extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
-        stride = -(-(boards.shape[2] + extra) // 16) * 16
-        wide = np.full((boards.shape[0], boards.shape[1], stride), 5, dtype=np.uint8)
-        wide[:, :, :boards.shape[2]] = boards
-        self.pop = DevicePopulation.from_numpy(wide, np.ascontiguousarray(rowlen), device=self.device,
-                                               capacity=max(capacity, 1))
+        need = -(-(int(rowlen.max()) + extra) // 16) * 16
+        if boards.shape[2] < need:
+            wide = np.full((boards.shape[0], boards.shape[1], need), 5, dtype=np.uint8)
+            wide[:, :, :boards.shape[2]] = boards
+            boards = wide
+        self.pop = DevicePopulation.from_numpy(np.ascontiguousarray(boards), np.ascontiguousarray(rowlen),
+                                               device=self.device, capacity=max(capacity, 1))
         self.R = self.pop.R
 
     def board(self, local, width):

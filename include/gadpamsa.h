@@ -153,6 +153,12 @@ int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int3
                            const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone, uint8_t *h_boards,
                            int32_t *h_rowlen, int stride);
 
+/* Sharded form: the whole stream is consumed, only boards p with p % own_step == own_first are
+ * written (densely) - each rank of a sharded run generates just its slice, in step with the reference. */
+int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen, int seq_stride,
+                                 const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone, int64_t own_first,
+                                 int64_t own_step, uint8_t *h_boards, int32_t *h_rowlen, int stride);
+
 /* ---- a15: worst-fitted sub-board of every mutating individual -------------
  * utils.calculate_worst_fitted_sub_board (utils.py:276-313) over the implicit (rw, cw) tile lattice
  * of utils.get_all_different_sub_range (utils.py:230-252). d_idx[m] (NULL = identity) names the

@@ -1,0 +1,85 @@
+"""CPython-compatible MT19937 replay (host entry points of libgadpamsa, no GPU needed): crossover plans and
+populations - whole and sharded - must equal what CPython's `random` produces through the oracle's
+restatement of GA.py:71-94 / GA.py:281-293, and leave the generator in the same state."""
+import random
+
+import numpy as np
+import pytest
+
+import ga_oracle as O
+
+
+def mt_state():
+    version, words, gauss = random.getstate()
+    return np.array(words, dtype=np.uint32), (version, gauss)
+
+
+def mt_restore(arr, meta):
+    random.setstate((meta[0], tuple(int(x) for x in arr), meta[1]))
+
+
+def host_population(nat, seqs, P, clone_rate, gap_rate, first=0, step=1):
+    codes = O.encode(seqs)
+    R = len(codes)
+    seqlen = np.array([len(s) for s in codes], np.int32)
+    ngaps = np.array([max(1, round(len(s) * gap_rate)) for s in codes], np.int32)
+    cstride = int(seqlen.max())
+    arr = np.full((R, cstride), 5, np.uint8)
+    for r, s in enumerate(codes):
+        arr[r, :len(s)] = s
+    stride = -(-(cstride + int(ngaps.max())) // 16) * 16
+    n_own = len(range(first, P, step))
+    boards = np.empty((n_own, R, stride), np.uint8)
+    rowlen = np.empty((n_own, R), np.int32)
+    state, meta = mt_state()
+    if step == 1:
+        nat.call("gad_mt_population_host", state.ctypes.data, arr.ctypes.data, seqlen.ctypes.data, cstride,
+                 ngaps.ctypes.data, R, P, round(P * clone_rate), boards.ctypes.data, rowlen.ctypes.data, stride)
+    else:
+        nat.call("gad_mt_population_shard_host", state.ctypes.data, arr.ctypes.data, seqlen.ctypes.data, cstride,
+                 ngaps.ctypes.data, R, P, round(P * clone_rate), first, step, boards.ctypes.data, rowlen.ctypes.data,
+                 stride)
+    mt_restore(state, meta)
+    return [[boards[p, r, :rowlen[p, r]].tolist() for r in range(R)] for p in range(n_own)], boards, rowlen
+
+
+@pytest.mark.parametrize("seed,R,C,P,gap_rate", [(0, 3, 30, 9, 0.05), (1, 6, 60, 64, 0.05), (2, 4, 101, 33, 0.08),
+                                                 (3, 20, 200, 40, 0.05), (4, 5, 1000, 6, 0.05)])
+def test_population_whole_and_sharded(native_lib, seed, R, C, P, gap_rate):
+    rng = random.Random(100 + seed)
+    seqs = ["".join(rng.choice("ACGT-") for _ in range(C - (r % 3))) for r in range(R)]
+    random.seed(seed)
+    want = O.generate_population(seqs, P, 0.25, gap_rate)
+    after = random.random()
+    random.seed(seed)
+    got, boards, rowlen = host_population(native_lib, seqs, P, 0.25, gap_rate)
+    assert got == want
+    assert random.random() == after
+    for p in range(P):                                   # layout invariant: gap code beyond every row
+        for r in range(R):
+            assert (boards[p, r, rowlen[p, r]:] == 5).all()
+    for world in (2, 3, 8):
+        for rank in range(world):
+            random.seed(seed)
+            part, _, _ = host_population(native_lib, seqs, P, 0.25, gap_rate, rank, world)
+            assert part == want[rank::world]
+            assert random.random() == after              # every rank leaves the generator where the reference does
+
+
+def test_crossover_plan_host(native_lib):
+    for seed, (n_par, rows, n_child) in enumerate([(2, 2, 40), (3, 6, 100), (77, 20, 1000), (4096, 64, 5000)]):
+        random.seed(seed)
+        want = O.crossover_plan(n_par, rows, n_child)
+        after = random.random()
+        random.seed(seed)
+        plan = np.empty((n_child, 3), np.int32)
+        state, meta = mt_state()
+        native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, n_par, rows, n_child, None, plan.ctypes.data)
+        mt_restore(state, meta)
+        assert plan.tolist() == [list(t) for t in want]
+        assert random.random() == after
+    state, _ = mt_state()
+    with pytest.raises(ValueError):                      # the reference would loop forever (GA.py:285-290)
+        native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, 1, 6, 4, None, plan.ctypes.data)
+    with pytest.raises(ValueError):
+        native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, 5, 1, 4, None, plan.ctypes.data)

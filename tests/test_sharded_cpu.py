@@ -27,9 +27,9 @@ class OracleBackend:
         self.boards = []          # local list of boards (python lists)
         self.R = 0
 
-    def generate_full_population(self, sequences, P):
+    def generate_shard(self, sequences, P, rank, world):
         pop = O.generate_population(sequences, P, self.kb.CLONE_RATE, self.kb.GAP_RATE, random)
-        b, r = O.to_arrays(pop)
+        b, r = O.to_arrays(pop[rank::world], stride=64)
         b[b == 0] = 5
         return b, r
 
@@ -95,7 +95,7 @@ class OracleBackend:
         return np.array(O.crossover_plan(n_parents, self.R, n_children, random), dtype=np.int32).reshape(-1, 3)
 
     def crossover_from(self, all_boards, all_rowlen, pos, plan):
-        parents = O.to_lists(all_boards.numpy(), all_rowlen.numpy())
+        parents = O.to_lists(all_boards.numpy(), all_rowlen.numpy())      # padded buffer: unused slots have rowlen 0
         for a, b, c in plan.tolist():
             self.boards.append(O.horizontal_child(parents[int(pos[a])], parents[int(pos[b])], c))
 
