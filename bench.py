@@ -332,6 +332,27 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
             dist.all_reduce(c)
             evals = float(c[0])
         hof = g.hall_of_fame
+        e2e_run = None
+        if world == 1:
+            # the call a user makes: GA(seqs, mode).run(model) - population generated on the host from `random`,
+            # uploaded, GA_ITERATIONS generations on the device, the winning alignment read back as strings
+            import GA as ga_mod
+            config.GA_ITERATIONS = 3
+            random.seed(7)
+            g2 = ga_mod.GA(seqs, mode)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            best = g2.run(model)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            dev2 = g2._dev
+            e2e_run = {"value": config.GA_ITERATIONS / dt, "unit": "generations/s", "seconds": dt,
+                       "generations": config.GA_ITERATIONS, "api": "GA(sequences, mode).run(model_path)",
+                       "h2d_bytes_per_run": int(P_total * rows * dev2.stride + 4 * P_total * rows),
+                       "d2h_bytes_per_run": int(rows * dev2.stride + 32), "alignment_rows": len(best),
+                       "note": "includes host population generation (MT19937 replay), the upload, the initial fitness "
+                               "pass and the read-back of the hall of fame"}
+            del g2
         tensor = None
         if rank == 0:
             tensor = l1_tensor_roofline(model, rw, cw, min(32768, round(P_total * config.MUTATION_RATE)))
@@ -346,7 +367,7 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
             "reference_net_flops_per_state": QNET_FLOPS.get((rw, cw)),
             "individuals_per_s": P_total * n_gen / total,
             "per_generation": per_gen,
-            "roofline": tensor,
+            "roofline": tensor, "e2e": e2e_run,
             "forward_ms_full_batch": (qnet_forward_ms(model, rw, cw, min(32768, round(P_total * config.MUTATION_RATE)))
                                       if rank == 0 else None),
         }
@@ -412,7 +433,7 @@ def qnet_forward_ms(model, rw, cw, B):
     return e0.elapsed_time(e1) / 10
 
 
-def cpu_generation_port(workload, cores, n_mut_per_core=1):
+def cpu_generation_port(workload, cores, n_mut_per_core=3):
     """The reference's per-generation CPU cost from bounded samples of the oracle port: fitness passes at
     the measured python-port rate plus round(P*MUTATION_RATE) episodes at the measured per-individual
     mutation time (the reference's own torch CPU ops in eval mode, one thread per process, agent

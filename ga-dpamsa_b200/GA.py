@@ -81,8 +81,7 @@ class GA:
 
     @population.setter
     def population(self, boards):
-        if not boards:
-            self._dev = None if self._dev is None or not self._dev.hof_valid else self._dev
+        if not boards:                       # GA.py:71 `self.population = []`: the hall of fame is kept
             if self._dev is not None:
                 self._dev.n = 0
             return

@@ -51,9 +51,9 @@ def unpack_boards(boards: np.ndarray, rowlen: np.ndarray):
 
 
 class _Buffer:
-    def __init__(self, cap, R, stride, dev):
-        self.boards = torch.full((cap, R, stride), GAP, dtype=torch.uint8, device=dev)
-        self.rowlen = torch.zeros((cap, R), dtype=torch.int32, device=dev)
+    def __init__(self, cap, R, stride, dev, boards=None, rowlen=None):
+        self.boards = torch.full((cap, R, stride), GAP, dtype=torch.uint8, device=dev) if boards is None else boards
+        self.rowlen = torch.zeros((cap, R), dtype=torch.int32, device=dev) if rowlen is None else rowlen
         self.sp = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.em = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.al = torch.zeros(cap, dtype=torch.int32, device=dev)
@@ -73,11 +73,8 @@ class DevicePopulation:
         self.capacity = max(capacity or 0, self.n, 1)
         self.R = boards.shape[1]
         self.stride = boards.shape[2]
-        if self.capacity == self.n:
-            self.cur = _Buffer.__new__(_Buffer)
-            self.cur.boards, self.cur.rowlen = boards, rowlen
-            for name in ("sp", "em", "al"):
-                setattr(self.cur, name, torch.zeros(self.capacity, dtype=torch.int32, device=self.device))
+        if self.capacity == self.n:          # adopt the caller's tensors as the first buffer
+            self.cur = _Buffer(self.capacity, self.R, self.stride, self.device, boards, rowlen)
         else:
             self.cur = _Buffer(self.capacity, self.R, self.stride, self.device)
             self.cur.boards[:self.n].copy_(boards)

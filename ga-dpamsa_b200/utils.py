@@ -4,8 +4,9 @@ python lists; they are copied to the device, scored there and the result is retu
 same python type the reference returns (int SP, float CS, list of indices, ...).
 
 There is no CPU fallback: without the CUDA library or a GPU these functions raise.
-The benchmarking half of the reference's utils.py (utils.py:472-975) lives in ``bench_utils``
-and is re-exported at the bottom so ``run_benchmarks.py`` finds the same names.
+The callers' half of the reference's utils.py (utils.py:472-975) follows at the bottom: metrics, FASTA
+parsing and the CSV plumbing are host formatting around device-computed scores; the external-tool and
+plotting entry points are out of scope and raise NotImplementedError with the reference lines they stand for.
 """
 from __future__ import annotations
 
