@@ -635,6 +635,13 @@ int encode_mma_smem_bytes(int L)
 #define FA_WARPS 6
 #define FA_KP 72           // row stride of the K / V tiles in halves (144 B: conflict-free ldmatrix rows)
 
+__device__ __forceinline__ float fast_exp2(float x)       // ex2.approx.ftz: 2 ulp, exp2(-inf) = 0
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b)
 {
     const __half2 h = __floats2half2_rn(a, b);
@@ -745,9 +752,9 @@ encode_fa_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 for (int c = 0; c < 4; ++c) o[t][c] = 0.f;
             float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
 
-            for (int kb = 0; kb < nk16; kb += 16) {
-                // six independent accumulation chains (3 split terms x 2 key tiles) instead of two chains of 12 MMAs
-                float s[2][4], s1[2][4], s2[2][4];
+            // S = Q'K'^T of one 16-key block: six independent accumulation chains (3 split terms x 2 key tiles)
+            auto compute_s = [&](int kb, float (&s)[2][4]) {
+                float s1[2][4], s2[2][4];
 #pragma unroll
                 for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -768,6 +775,18 @@ encode_fa_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 for (int t = 0; t < 2; ++t)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) s[t][c] += s1[t][c] + s2[t][c];
+            };
+            // software pipeline: the MMAs of block kb+16 are issued before the softmax of block kb, so the
+            // tensor pipe keeps working while this warp does the scalar part
+            float s_next[2][4];
+            compute_s(0, s_next);
+            for (int kb = 0; kb < nk16; kb += 16) {
+                float s[2][4];
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) s[t][c] = s_next[t][c];
+                if (kb + 16 < nk16) compute_s(kb + 16, s_next);
                 // logits of this thread: key = kb + 8t + 2*quad + {0,1}; c0,c1 -> row A, c2,c3 -> row B
                 float bxA = -INFINITY, bxB = -INFINITY;
 #pragma unroll
@@ -784,18 +803,22 @@ encode_fa_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 bxA = fmaxf(bxA, __shfl_xor_sync(0xFFFFFFFFu, bxA, 2));
                 bxB = fmaxf(bxB, __shfl_xor_sync(0xFFFFFFFFu, bxB, 1));
                 bxB = fmaxf(bxB, __shfl_xor_sync(0xFFFFFFFFu, bxB, 2));
-                const float nA = fmaxf(mA, bxA), nB = fmaxf(mB, bxB);      // every 16-key block holds at least one valid key
-                const float fA = exp2f(mA - nA), fB = exp2f(mB - nB);      // exp2(-inf) = 0 on the first block
+                // Lazy rescaling: the running reference max only moves when a block exceeds it by more than 2^8
+                // (numerators then stay <= 256, exact enough in the hi + lo fp16 split), so the accumulator
+                // rescale below runs for the first block or two of a row tile and almost never again.
+                // Every 16-key block holds at least one valid key, so the maxima are finite.
+                const float nA = bxA > mA + 8.f ? bxA : mA, nB = bxB > mB + 8.f ? bxB : mB;
+                const float fA = fast_exp2(mA - nA), fB = fast_exp2(mB - nB);      // exp2(-inf) = 0 on the first block
                 mA = nA;
                 mB = nB;
                 float p[2][4];
                 float sumA = 0.f, sumB = 0.f;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    p[t][0] = exp2f(s[t][0] - nA);
-                    p[t][1] = exp2f(s[t][1] - nA);
-                    p[t][2] = exp2f(s[t][2] - nB);
-                    p[t][3] = exp2f(s[t][3] - nB);
+                    p[t][0] = fast_exp2(s[t][0] - nA);
+                    p[t][1] = fast_exp2(s[t][1] - nA);
+                    p[t][2] = fast_exp2(s[t][2] - nB);
+                    p[t][3] = fast_exp2(s[t][3] - nB);
                     sumA += p[t][0] + p[t][1];
                     sumB += p[t][2] + p[t][3];
                 }
