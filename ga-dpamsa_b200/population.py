@@ -51,9 +51,20 @@ def unpack_boards(boards: np.ndarray, rowlen: np.ndarray):
 
 
 class _Buffer:
-    def __init__(self, cap, R, stride, dev, boards=None, rowlen=None):
-        self.boards = torch.full((cap, R, stride), GAP, dtype=torch.uint8, device=dev) if boards is None else boards
-        self.rowlen = torch.zeros((cap, R), dtype=torch.int32, device=dev) if rowlen is None else rowlen
+    def __init__(self, cap, R, stride, dev, boards=None, rowlen=None, alloc=None):
+        if boards is None:
+            if alloc is None:
+                boards = torch.full((cap, R, stride), GAP, dtype=torch.uint8, device=dev)
+                rowlen = torch.zeros((cap, R), dtype=torch.int32, device=dev)
+            else:                                  # e.g. symmetric memory, so that peers can read the boards
+                boards = alloc((cap, R, stride), torch.uint8)
+                boards.fill_(GAP)
+                rowlen = alloc((cap, R), torch.int32)
+                rowlen.zero_()
+        self.boards = boards
+        self.rowlen = rowlen
+        self.peer_boards = None                    # device int64[world]: this buffer's address on every rank
+        self.peer_rowlen = None
         self.sp = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.em = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.al = torch.zeros(cap, dtype=torch.int32, device=dev)
@@ -63,7 +74,7 @@ class DevicePopulation:
     """Up to ``capacity`` boards of R rows resident on one GPU, plus the GA state that goes with them
     (scores, hall of fame, ranking workspace)."""
 
-    def __init__(self, boards: torch.Tensor, rowlen: torch.Tensor, capacity=None):
+    def __init__(self, boards: torch.Tensor, rowlen: torch.Tensor, capacity=None, allocator=None):
         assert boards.is_cuda and boards.dtype == torch.uint8 and boards.dim() == 3
         assert rowlen.dtype == torch.int32 and rowlen.shape == boards.shape[:2]
         assert boards.is_contiguous() and rowlen.is_contiguous()
@@ -73,10 +84,12 @@ class DevicePopulation:
         self.capacity = max(capacity or 0, self.n, 1)
         self.R = boards.shape[1]
         self.stride = boards.shape[2]
-        if self.capacity == self.n:          # adopt the caller's tensors as the first buffer
+        self._alloc = allocator
+        self.on_realloc = None                   # called after the buffers were re-allocated (sharded: re-rendezvous)
+        if self.capacity == self.n and allocator is None:      # adopt the caller's tensors as the first buffer
             self.cur = _Buffer(self.capacity, self.R, self.stride, self.device, boards, rowlen)
         else:
-            self.cur = _Buffer(self.capacity, self.R, self.stride, self.device)
+            self.cur = self._new_buffer(self.capacity)
             self.cur.boards[:self.n].copy_(boards)
             self.cur.rowlen[:self.n].copy_(rowlen)
         self.alt = None                          # second buffer, allocated by the first selection
@@ -97,6 +110,13 @@ class DevicePopulation:
         self.forwards = 0                        # lock-step Q-net forwards so far
 
     # ------------------------------------------------------------------ construction / readback
+    def _new_buffer(self, cap):
+        return _Buffer(cap, self.R, self.stride, self.device, alloc=self._alloc)
+
+    def ensure_alt(self):
+        if self.alt is None or self.alt.boards.shape != self.cur.boards.shape:
+            self.alt = self._new_buffer(self.capacity)
+
     @classmethod
     def from_lists(cls, population, device="cuda", stride=None, extra_capacity=0, capacity=None):
         nat.require_device()
@@ -104,9 +124,9 @@ class DevicePopulation:
         return cls.from_numpy(boards, rowlen, device, capacity)
 
     @classmethod
-    def from_numpy(cls, boards: np.ndarray, rowlen: np.ndarray, device="cuda", capacity=None):
+    def from_numpy(cls, boards: np.ndarray, rowlen: np.ndarray, device="cuda", capacity=None, allocator=None):
         nat.require_device()
-        pop = cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity)
+        pop = cls(torch.from_numpy(boards).to(device), torch.from_numpy(rowlen).to(device), capacity, allocator)
         pop.width_hint = int(rowlen.max()) if rowlen.size else 0
         return pop
 
@@ -166,17 +186,22 @@ class DevicePopulation:
         need = round_up(need, 16)
         if need <= self.stride:
             return
+        old = self.stride
+        self.stride = need
         for name in ("cur", "alt"):
             buf = getattr(self, name)
             if buf is None:
                 continue
-            wide = torch.full((buf.boards.shape[0], self.R, need), GAP, dtype=torch.uint8, device=self.device)
-            wide[:, :, :self.stride].copy_(buf.boards)
-            buf.boards = wide
+            wide = self._new_buffer(buf.boards.shape[0])
+            wide.boards[:, :, :old].copy_(buf.boards)
+            for f in ("rowlen", "sp", "em", "al"):
+                getattr(wide, f).copy_(getattr(buf, f))
+            setattr(self, name, wide)
         hof = torch.full((self.R, need), GAP, dtype=torch.uint8, device=self.device)
-        hof[:, :self.stride].copy_(self.hof_board)
+        hof[:, :old].copy_(self.hof_board)
         self.hof_board = hof
-        self.stride = need
+        if self.on_realloc:
+            self.on_realloc()
 
     def ensure_capacity(self, cap: int):
         if cap <= self.capacity:
@@ -185,12 +210,14 @@ class DevicePopulation:
             buf = getattr(self, name)
             if buf is None:
                 continue
-            big = _Buffer(cap, self.R, self.stride, self.device)
+            big = self._new_buffer(cap)
             for f in ("boards", "rowlen", "sp", "em", "al"):
                 getattr(big, f)[:self.capacity].copy_(getattr(buf, f))
             setattr(self, name, big)
         self.capacity = cap
         self._ws = None
+        if self.on_realloc:
+            self.on_realloc()
 
     # ------------------------------------------------------------------ a4-a7 + a8
     def fitness(self, match: int, mismatch: int, gap: int):
@@ -243,8 +270,7 @@ class DevicePopulation:
         """GA.py:232-259: keep the survivors, in original order. Returns their number (one 4-byte
         device->host read: the crossover plan needs it on the host)."""
         self.select_flags(mode, top_n)
-        if self.alt is None or self.alt.boards.shape != self.cur.boards.shape:
-            self.alt = _Buffer(self.capacity, self.R, self.stride, self.device)
+        self.ensure_alt()
         s, d = self.cur, self.alt
         nat.call("gad_compact", nat.ptr(s.boards), nat.ptr(s.rowlen), nat.ptr(s.sp), nat.ptr(s.em), nat.ptr(s.al),
                  nat.ptr(self._keep), nat.ptr(self._dst), self.n, self.R, self.stride, nat.ptr(d.boards),
@@ -285,8 +311,7 @@ class DevicePopulation:
         n = self.n
         k8 = keep.to(torch.uint8).contiguous()
         dst = (torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - keep.to(torch.int32)).contiguous()
-        if self.alt is None or self.alt.boards.shape != self.cur.boards.shape:
-            self.alt = _Buffer(self.capacity, self.R, self.stride, self.device)
+        self.ensure_alt()
         s, d = self.cur, self.alt
         nat.call("gad_compact", nat.ptr(s.boards), nat.ptr(s.rowlen), nat.ptr(s.sp), nat.ptr(s.em), nat.ptr(s.al),
                  nat.ptr(k8), nat.ptr(dst), n, self.R, self.stride, nat.ptr(d.boards), nat.ptr(d.rowlen),
@@ -311,6 +336,22 @@ class DevicePopulation:
         nat.call("gad_crossover_from", nat.ptr(src_boards), nat.ptr(src_rowlen), nat.ptr(b.boards), nat.ptr(b.rowlen),
                  self.n, nat.ptr(d_plan), n_children, self.R, self.stride, int(kind), self._stream())
         torch.cuda.current_stream().synchronize()          # src buffers are temporaries of the caller
+        self.n += n_children
+
+    def crossover_peer(self, peer_slots: int, pos, plan: np.ndarray, kind: int = 0):
+        """Append children whose parents are read from the owning ranks' buffers over NVLink (fused exchange +
+        crossover, gad_crossover_peer). `plan` holds logical parent indices; pos[logical] = rank * peer_slots + slot."""
+        n_children = int(plan.shape[0])
+        if n_children == 0:
+            return
+        assert self.n + n_children <= self.capacity, "symmetric buffers cannot grow inside a collective phase"
+        d_plan = torch.from_numpy(np.ascontiguousarray(plan)).to(self.device)
+        d_plan[:, 0] = pos[d_plan[:, 0].long()].to(torch.int32)
+        d_plan[:, 1] = pos[d_plan[:, 1].long()].to(torch.int32)
+        d_plan = d_plan.contiguous()
+        b = self.cur
+        nat.call("gad_crossover_peer", nat.ptr(b.peer_boards), nat.ptr(b.peer_rowlen), int(peer_slots), nat.ptr(b.boards),
+                 nat.ptr(b.rowlen), self.n, nat.ptr(d_plan), n_children, self.R, self.stride, int(kind), self._stream())
         self.n += n_children
 
     def mutate(self, qnet, idx, tile, max_value: float, width=None):

@@ -179,6 +179,22 @@ class ShardedGA:
             assert sum(need) == n_children, (need, n_children)
             first = sum(need[:self.rank])
             mine = plan[first:first + need[self.rank]]
+            if getattr(self.backend, "peer_ready", False):
+                # fused exchange + crossover: only the (rank, slot) address of every survivor is exchanged
+                # (8 bytes each); the kernel reads the parents' rows from the owners' buffers over NVLink
+                mx = max(counts)
+                all_gidx = self._all_gather_padded(self.gidx, counts)
+                dev = self.backend.device
+                where = torch.cat([torch.arange(r * mx, r * mx + c, device=dev) for r, c in enumerate(counts)])
+                pos = torch.zeros(S, dtype=torch.int64, device=dev)
+                pos.index_copy_(0, all_gidx, where)
+                self.backend.crossover_peer(mx, pos, mine)
+                self.comm_bytes += int(mine.shape[0]) * self.backend.R * self.backend.pop.stride * (self.world - 1) // self.world
+                kids = torch.arange(S + first, S + first + need[self.rank], dtype=torch.int64, device=dev)
+                self.gidx = torch.cat((self.gidx, kids))
+                self.n_global = P
+                self.calculate_fitness_score()
+                return
             boards, rowlen = self.backend.survivors()
             all_boards = self._all_gather_padded(boards, counts, compact=False)      # [world * max, R, stride]
             all_rowlen = self._all_gather_padded(rowlen, counts, compact=False)
@@ -225,7 +241,10 @@ class ShardedGA:
 class DeviceBackend:
     """The product backend: libgadpamsa kernels on this rank's GPU."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, peer=None):
+        """peer=None: read parents from peer memory when torch's symmetric memory is usable on this group
+        (GAD_SHARDED_EXCHANGE=allgather forces the NCCL all-gather of the survivors' boards)."""
+        import os
         import _native as nat
         nat.require_device()
         self.nat = nat
@@ -234,6 +253,31 @@ class DeviceBackend:
         self.pop = None
         self.R = 0
         self._rank_tmp = None
+        self.peer_ready = False
+        self._handles = []
+        want = peer if peer is not None else os.environ.get("GAD_SHARDED_EXCHANGE", "peer") != "allgather"
+        self._symm = None
+        if want and dist.is_initialized() and dist.get_world_size() > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._symm = symm_mem
+            except Exception:                        # pragma: no cover - depends on the torch build
+                self._symm = None
+
+    def _symm_alloc(self, shape, dtype):
+        return self._symm.empty(*shape, dtype=dtype, device=self.device)
+
+    def _rendezvous(self):
+        """Map both population buffers of every rank into this process (collective)."""
+        self._handles = []
+        world = dist.get_world_size()
+        for buf in (self.pop.cur, self.pop.alt):
+            hb = self._symm.rendezvous(buf.boards, dist.group.WORLD)
+            hr = self._symm.rendezvous(buf.rowlen, dist.group.WORLD)
+            self._handles += [hb, hr]
+            buf.peer_boards = torch.tensor([int(p) for p in hb.buffer_ptrs[:world]], dtype=torch.int64, device=self.device)
+            buf.peer_rowlen = torch.tensor([int(p) for p in hr.buffer_ptrs[:world]], dtype=torch.int64, device=self.device)
+        self.peer_ready = True
 
     # -- population ---------------------------------------------------------------------------
     def generate_shard(self, sequences, P, rank, world):
@@ -254,8 +298,20 @@ class DeviceBackend:
             wide[:, :, :boards.shape[2]] = boards
             boards = wide
         self.pop = DevicePopulation.from_numpy(np.ascontiguousarray(boards), np.ascontiguousarray(rowlen),
-                                               device=self.device, capacity=max(capacity, 1))
+                                               device=self.device, capacity=max(capacity, 1),
+                                               allocator=self._symm_alloc if self._symm else None)
         self.R = self.pop.R
+        if self._symm:
+            self.pop.ensure_alt()
+            self.pop.on_realloc = self._on_realloc
+            self._rendezvous()
+
+    def _on_realloc(self):
+        self.pop.ensure_alt()
+        self._rendezvous()
+
+    def crossover_peer(self, peer_slots, pos, plan):
+        self.pop.crossover_peer(peer_slots, pos, plan)
 
     def board(self, local, width):
         return self.pop.cur.boards[local, :, :width].contiguous()

@@ -141,6 +141,15 @@ int gad_crossover_from(const uint8_t *d_src_boards, const int32_t *d_src_rowlen,
                        int32_t *d_dst_rowlen, int64_t dst_first, const int32_t *d_plan, int64_t n_children, int R,
                        int stride, int kind, void *stream);
 
+/* Fused exchange + crossover for a sharded population: d_peer_boards[rank] / d_peer_rowlen[rank] are the
+ * ranks' population buffers mapped into this process (peer pointers of a symmetric allocation, read over
+ * NVLink); a parent is named by pos = owner_rank * peer_slots + slot in d_plan[c] = {pos1, pos2, cut}.
+ * Children go to slots [dst_first, dst_first + n_children) of the local buffer. The caller orders the launch
+ * after every rank has finished writing its survivors (the preceding score all-gather does). */
+int gad_crossover_peer(const uint8_t *const *d_peer_boards, const int32_t *const *d_peer_rowlen, int64_t peer_slots,
+                       uint8_t *d_dst_boards, int32_t *d_dst_rowlen, int64_t dst_first, const int32_t *d_plan,
+                       int64_t n_children, int R, int stride, int kind, void *stream);
+
 /* CPython-compatible MT19937 replay (random.getstate()[1] = 624 words + position, in/out):
  * the (parent1, parent2, cut) triples of GA.py:281-293 for n_children children. h_widths (one
  * per parent) selects the vertical cut rule randint(1, min(w1,w2)-1); NULL = horizontal. */
