@@ -299,6 +299,12 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
         sync()
         t_pop = time.perf_counter() - t0
         g.calculate_fitness_score()
+        # a fresh box idles at 120 MHz and needs about a second of dense work to settle its clocks and power
+        # state: burn ~1.5 s of Q-net forwards before any timed generation (on top of the warm-up generations)
+        t_burn = time.perf_counter()
+        while time.perf_counter() - t_burn < 1.5:
+            qnet_forward_ms(model, rw, cw, 8192)
+        sync()
         phases = {"mutation": 0.0, "fitness": 0.0, "selection": 0.0, "crossover": 0.0}
         evals = forwards = episodes = 0
         total = 0.0
