@@ -66,13 +66,7 @@ def inference(mode, dataset=None, start=0, end=-1, model_path='model_3x30', debu
         Environment.set_alignment(env, best_alignment)
         m = utils.calculate_metrics(env)
         with open(report_file_name, 'a') as fh:
-            fh.write(f"File: {name}\n"
-                     f"Number of Sequences (QTY): {m['QTY']}\n"
-                     f"Alignment Length (AL): {m['AL']}\n"
-                     f"Sum of Pairs (SP): {m['SP']}\n"
-                     f"Exact Matches (EM): {m['EM']}\n"
-                     f"Column Score (CS): {m['CS']:.3f}\n"
-                     f"Alignment:\n{env.get_alignment()}\n\n")
+            fh.write(utils.report_block(name, m, env.get_alignment()))
         with open(csv_file_name, 'a', newline='') as fh:
             csv.writer(fh).writerow([name, m['QTY'], m['AL'], m['SP'], m['EM'], m['CS']])
     print(f"\nInference completed successfully.\nReport saved at: {report_file_name}\nCSV saved at: {csv_file_name}\n")

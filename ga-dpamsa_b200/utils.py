@@ -253,15 +253,114 @@ def run_ga_dpamsa_inference(mode, dataset, dataset_name, model_path):
     return os.path.join(config.GA_DPAMSA_INF_CSV_PATH, f"{dataset_name}_{mode_tag}_GA_DPAMSA_results.csv")
 
 
-def _out_of_scope(name, where):
-    def stub(*_args, **_kwargs):
-        raise NotImplementedError("%s (reference %s) is outside the generation-loop scope of this build "
-                                  "(SURVEY.md section 2)" % (name, where))
-    stub.__name__ = name
-    return stub
+CSV_COLUMNS_QTY_FIRST = ["File Name", "Number of Sequences (QTY)", "Alignment Length (AL)", "Sum of Pairs (SP)",
+                         "Exact Matches (EM)", "Column Score (CS)"]
 
 
-run_dpamsa_inference = _out_of_scope("run_dpamsa_inference", "utils.py:783-807")
-run_tool_and_generate_report = _out_of_scope("run_tool_and_generate_report", "utils.py:610-697")
-display_menu = _out_of_scope("display_menu", "utils.py:563-607")
-plot_metrics = _out_of_scope("plot_metrics", "utils.py:813-975")
+def report_block(name, metrics, alignment):
+    """One record of the reference's report files (mainGA.py:137-145, DPAMSA/main.py:291-299, utils.py:677-683) -
+    the format of the 1 340 published records."""
+    return (f"File: {name}\n"
+            f"Number of Sequences (QTY): {metrics['QTY']}\n"
+            f"Alignment Length (AL): {metrics['AL']}\n"
+            f"Sum of Pairs (SP): {metrics['SP']}\n"
+            f"Exact Matches (EM): {metrics['EM']}\n"
+            f"Column Score (CS): {metrics['CS']:.3f}\n"
+            f"Alignment:\n{alignment}\n\n")
+
+
+def run_dpamsa_inference(dataset, dataset_name, model_path):
+    """reference utils.py:801-807: plain DPAMSA (no GA) over a dataset module; returns the CSV path."""
+    import os
+    from DPAMSA.main import inference as dpamsa_inference
+    dpamsa_inference(dataset=dataset, model_path=model_path, truncate_file=True)
+    return os.path.join(config.DPAMSA_INF_CSV_PATH, f"{dataset_name}_DPAMSA_results.csv")
+
+
+def display_menu():
+    """reference utils.py:593-607: the three benchmarking options, asked on stdin until the answer is valid."""
+    options = {1: "GA-DPAMSA vs DPAMSA", 2: "GA-DPAMSA vs Other MSA Tools", 3: "GA-DPAMSA vs DPAMSA vs Other MSA Tools"}
+    print("Select the benchmarking option:")
+    for key, text in options.items():
+        print(f"{key}. {text}")
+    while True:
+        answer = input("Enter your choice (1, 2, or 3): ")
+        try:
+            choice = int(answer)
+        except ValueError:
+            print("Invalid input. Please enter a number.")
+            continue
+        if choice in options:
+            return choice
+        print("Please select a valid option (1, 2, or 3).")
+
+
+def run_tool_and_generate_report(tool_name, file_paths, dataset_name):
+    """reference utils.py:629-697: run an external MSA tool (config.TOOLS[tool_name]) on FASTA files, score its
+    alignments on the GPU and write the report; returns [file, QTY, AL, SP, EM, CS] rows. Host plumbing around
+    subprocess - the tools themselves are not part of this build (a missing binary raises FileNotFoundError)."""
+    import glob
+    import os
+    import subprocess
+    from DPAMSA.env import Environment
+    tool = config.TOOLS[tool_name]
+    out_dir = os.path.join(tool['output_dir'], dataset_name)
+    os.makedirs(out_dir, exist_ok=True)
+    os.makedirs(tool['report_dir'], exist_ok=True)
+    rows = []
+    with open(os.path.join(tool['report_dir'], f"{dataset_name}.txt"), 'w') as report:
+        for path in file_paths:
+            fname = os.path.basename(path)
+            stem = os.path.splitext(fname)[0]
+            command = tool['command'](path, os.path.join(out_dir, fname))
+            if isinstance(command, str):                       # shell pipeline (MAFFT in the reference)
+                done = subprocess.run(command, shell=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            else:
+                done = subprocess.run(command, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            produced = {"UPP": os.path.join(out_dir, fname, "output_alignment.fasta"),
+                        "PASTA": os.path.join(out_dir, fname, f"pastajob.marker001.{stem}.aln")}.get(
+                            tool_name, os.path.join(out_dir, fname))
+            if os.path.exists(produced):
+                with open(produced) as fh:
+                    fasta = fh.read()
+            else:
+                fasta = done.stdout or ""
+            aligned = parse_fasta_to_sequences(fasta)
+            env = Environment(aligned, convert_data=False)
+            Environment.set_alignment(env, aligned)
+            m = calculate_metrics(env)
+            report.write(report_block(fname, m, env.get_alignment()))
+            rows.append([fname, m['QTY'], m['AL'], m['SP'], m['EM'], m['CS']])
+            if tool_name == 'ClustalW':
+                for dnd in glob.glob(os.path.join(os.path.dirname(path), '*.dnd')):
+                    os.remove(dnd)
+    return rows
+
+
+def plot_metrics(tool_csv_paths, dataset_name):
+    """reference utils.py:813-975 draws box/bar charts with matplotlib. Plotting is outside the scope of this
+    build: with matplotlib installed a compact SP / CS bar chart per tool is written under config.CHARTS_PATH,
+    without it the per-tool means are printed. Returns {tool: {"SP": mean, "CS": mean}}."""
+    import os
+    import pandas as pd
+    summary = {}
+    for tool, path in tool_csv_paths.items():
+        df = pd.read_csv(path)
+        summary[tool] = {"SP": float(df["Sum of Pairs (SP)"].mean()), "CS": float(df["Column Score (CS)"].mean())}
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        for tool, m in summary.items():
+            print(f"{dataset_name} {tool}: mean SP {m['SP']:.2f}, mean CS {m['CS']:.4f}")
+        return summary
+    os.makedirs(config.CHARTS_PATH, exist_ok=True)
+    for metric in ("SP", "CS"):
+        fig, ax = plt.subplots(figsize=(max(4, len(summary)), 3))
+        ax.bar(list(summary), [m[metric] for m in summary.values()])
+        ax.set_title(f"{dataset_name}: mean {metric}")
+        fig.tight_layout()
+        fig.savefig(os.path.join(config.CHARTS_PATH, f"{dataset_name}_{metric}.png"))
+        plt.close(fig)
+    return summary

@@ -624,3 +624,40 @@ def test_generation_properties_at_baseline_shapes(gpu, weight_files, cfg, R, C, 
         assert hem / hal >= float((em.double() / al.double()).max())
     for k in range(R):
         assert hb[k][hb[k] != 5].tolist() == residues[k]
+
+
+def test_benchmark_callers_thin_host_versions(gpu, weight_files, cfg, datasets_json, tmp_path, monkeypatch):
+    """run_benchmarks.py's other entry points: plain DPAMSA inference (greedy episode per whole set, against the
+    oracle's episode), an external tool run (a fake tool that echoes the FASTA), the menu and the summary."""
+    import types
+    import utils
+    name, sd = weight_files[(3, 30)]
+    sets = datasets_json["synthetic_dataset_3x30bp"]
+    keys = list(sets)[:2]
+    mod = types.SimpleNamespace(file_name="unit_3x30bp.py", datasets=keys, **{k: sets[k] for k in keys})
+    csv_path = utils.run_dpamsa_inference(mod, "unit_3x30bp", name)
+    lines = open(csv_path).read().strip().split("\n")
+    assert len(lines) == 3
+    for key, line in zip(keys, lines[1:]):
+        board = O.encode(sets[key])
+        O.mutate_board(board, (0, 3, 0, 30), sd, qdtype=np.float64)        # one greedy episode over the whole board
+        R, W = len(board), len(board[0])
+        got = line.split(",")
+        assert got[0] == key and int(got[1]) == R and int(got[2]) == W
+        assert int(got[3]) == O.sum_of_pairs(board, 0, R, 0, W) and int(got[4]) == O.exact_columns(board, 0, R, 0, W)
+    # external tool plumbing with a stand-in command
+    fasta = tmp_path / "set0.fasta"
+    fasta.write_text(">a\nACGT-A\n>b\nACGTTA\n>c\nAC-TTA\n")
+    monkeypatch.setitem(cfg.TOOLS, "Echo", {"command": lambda src, dst: ["cat", src],
+                                            "output_dir": str(tmp_path / "out"), "report_dir": str(tmp_path / "rep")})
+    rows = utils.run_tool_and_generate_report("Echo", [str(fasta)], "unit")
+    board = O.encode(["ACGT-A", "ACGTTA", "AC-TTA"])
+    assert rows == [["set0.fasta", 3, 6, O.sum_of_pairs(board, 0, 3, 0, 6), O.exact_columns(board, 0, 3, 0, 6),
+                     O.column_score(board, 0, 3, 0, 6)]]
+    assert "File: set0.fasta" in open(tmp_path / "rep" / "unit.txt").read()
+    tool_csv = utils.save_inference_csv(rows, "Echo", "unit")
+    summary = utils.plot_metrics({"Echo": tool_csv, "DPAMSA": csv_path}, "unit")
+    assert set(summary) == {"Echo", "DPAMSA"} and summary["Echo"]["SP"] == rows[0][3]
+    answers = iter(["x", "7", "2"])
+    monkeypatch.setattr("builtins.input", lambda _prompt: next(answers))
+    assert utils.display_menu() == 2
