@@ -175,7 +175,7 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
             uint32_t valid[4];
             count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) boardsums_fold(bs, cc[k], valid[k], false);
+            for (int k = 0; k < 4; ++k) boardsums_fold_word(bs, cc[k], valid[k] != 0u);
         }
         bs.q2 = group_sum<GS>(bs.q2, gmask);
         bs.s1 = group_sum<GS>(bs.s1, gmask);
@@ -392,6 +392,7 @@ extern "C" int gad_window_score_host(const uint8_t *h_board, int R, int stride, 
                 R, stride);
     GAD_REQUIRE(0 <= from_row && from_row <= to_row && to_row <= R, "gad_window_score_host: row window [%d,%d) outside [0,%d)",
                 from_row, to_row, R);
+    GAD_REQUIRE((long long)R * R * stride < (1ll << 31), "gad_window_score_host: R*R*stride overflows the 32-bit column sums");
     GAD_REQUIRE(0 <= from_col && from_col <= to_col && to_col <= stride,
                 "gad_window_score_host: column window [%d,%d) outside [0,%d)", from_col, to_col, stride);
     HostStage &s = g_stage;

@@ -145,6 +145,24 @@ __device__ __forceinline__ uint32_t boardsums_fold(BoardSums &b, const ColCounts
     return keep;
 }
 
+// Fast path of boardsums_fold for the fitness pass: the word is either wholly inside the board or wholly
+// outside it (`inside`), all-gap columns have zero counts already, so no per-lane masking is needed.
+__device__ __forceinline__ uint32_t boardsums_fold_word(BoardSums &b, const ColCounts &c, bool inside)
+{
+    if (!inside) return 0u;
+    const uint32_t s = c.c1 + c.c2 + c.c3 + c.c4;          // non-gap cells per column
+    const uint32_t keep = nonzero_lanes(s);
+    b.q2 = __dp4a(c.c1, c.c1, b.q2);
+    b.q2 = __dp4a(c.c2, c.c2, b.q2);
+    b.q2 = __dp4a(c.c3, c.c3, b.q2);
+    b.q2 = __dp4a(c.c4, c.c4, b.q2);
+    b.s1 = __dp4a(s, GAD_LSB4, b.s1);
+    b.s2 = __dp4a(s, s, b.s2);
+    b.kept += __popc(keep);
+    b.exact += __popc(~nonzero_lanes(c.diff) & keep);
+    return keep;
+}
+
 // Closed form of utils.py:62-76 from the board sums over `kept` columns of `rows` cells:
 //   match pairs    M  = sum c(c-1)/2                      = (q2 - s1)/2
 //   gap pairs      Gp = sum g(g-1)/2 + g(rows-g), g=rows-s = ((2 rows-1) G1 - G2)/2
@@ -152,11 +170,13 @@ __device__ __forceinline__ uint32_t boardsums_fold(BoardSums &b, const ColCounts
 __device__ __forceinline__ long long sum_of_pairs_closed_form(const BoardSums &b, int rows, int match, int mismatch,
                                                               int gap)
 {
-    const long long R = rows, nk = b.kept, s1 = b.s1, s2 = b.s2, q2 = b.q2;
-    const long long M = (q2 - s1) / 2;
-    const long long G1 = R * nk - s1;
-    const long long G2 = R * R * nk - 2 * R * s1 + s2;
-    const long long Gp = ((2 * R - 1) * G1 - G2) / 2;
-    const long long T = nk * R * (R - 1) / 2;
-    return (long long)match * M + (long long)gap * Gp + (long long)mismatch * (T - M - Gp);
+    // every term is below 2 * rows^2 * columns, which the entry points keep under 2^32: 32-bit unsigned
+    // arithmetic, 64 bits only for the weighted sum
+    const uint32_t R = (uint32_t)rows, nk = b.kept, s1 = b.s1, s2 = b.s2, q2 = b.q2;
+    const uint32_t M = (q2 - s1) >> 1;
+    const uint32_t G1 = R * nk - s1;
+    const uint32_t G2 = R * R * nk - 2u * R * s1 + s2;
+    const uint32_t Gp = ((2u * R - 1u) * G1 - G2) >> 1;
+    const uint32_t T = (nk * R * (R - 1u)) >> 1;
+    return (long long)match * M + (long long)gap * Gp + (long long)mismatch * (long long)(T - M - Gp);
 }
