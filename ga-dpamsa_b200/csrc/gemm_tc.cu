@@ -39,13 +39,19 @@ constexpr int TMEM_COLS = 512;
 constexpr int CHUNK_KB = 8;                 // k-blocks (of 64) per TMEM accumulation chunk = 32 MMAs
 constexpr int EPI_WARPS = 8;                // 2 per TMEM lane quarter, each owning half of the tile's columns
 
-template <int BN> struct Cfg {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// FUSED: one stage holds the hi AND lo tiles of both operands for a 32-wide k-block (64-byte swizzle rows), so
+// the three split products (lo.hi, hi.lo, hi.hi) are issued from one load of four tiles instead of three loads
+// of two - a third less L2 -> shared-memory traffic for the same MMAs.
+constexpr int BKF = 32;
+constexpr int CHUNK_KB_F = 6;               // fused k-blocks per TMEM accumulation chunk = 36 MMAs
+
+template <int BN, bool FUSED = false> struct Cfg {
+    static constexpr int A_BYTES = FUSED ? BM * BKF * 2 : BM * BK * 2;          // one tile (hi or lo)
+    static constexpr int B_BYTES = FUSED ? BN * BKF * 2 : BN * BK * 2;
+    static constexpr int STAGE_BYTES = FUSED ? 2 * (A_BYTES + B_BYTES) : A_BYTES + B_BYTES;
     static constexpr int STAGES = (220 * 1024) / STAGE_BYTES > 6 ? 6 : (220 * 1024) / STAGE_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-    static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment (BN multiple of 8)");
+    static_assert(B_BYTES % (FUSED ? 512 : 1024) == 0, "tiles must keep the swizzle-atom alignment");
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
 };
 
@@ -107,14 +113,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major operand tile in smem written by TMA with 128-byte swizzle: rows of 128 bytes, 8-row atoms of
 // 1024 bytes (stride byte offset), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+// sw64 = false: 128-byte rows / 1024-byte atoms (layout type 2); sw64 = true: 64-byte rows / 512-byte atoms (type 4)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool sw64 = false)
 {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address        bits [0,14)
     d |= (uint64_t)0 << 16;                             // leading byte offset  bits [16,30) (unused: swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset   bits [32,46)
+    d |= (uint64_t)((sw64 ? 512 : 1024) >> 4) << 32;    // stride byte offset   bits [32,46): one 8-row swizzle atom
     d |= (uint64_t)1 << 46;                             // descriptor version   bits [46,48)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B         bits [61,64)
+    d |= (uint64_t)(sw64 ? 4 : 2) << 61;                // SWIZZLE_64B / SWIZZLE_128B  bits [61,64)
     return d;
 }
 
@@ -124,13 +131,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN, bool SPLIT_OUT>
+template <int BN, bool SPLIT_OUT, bool FUSED = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const float *__restrict__ bias, float out_scale, void *__restrict__ Cout, int ldc, int lo_offset,
                       const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky)
 {
-    using C_ = Cfg<BN>;
+    using C_ = Cfg<BN, FUSED>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C_::STAGES * C_::STAGE_BYTES);
@@ -143,7 +150,10 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const long long M = m_ptr ? (long long)*m_ptr : m_fixed;
     const int tiles_n = (N + BN - 1) / BN;
     const long long tiles = ((M + BM - 1) / BM) * tiles_n;
-    const int kblocks = K / BK;                          // per segment
+    const int kblocks = K / BK;                          // per segment (unfused)
+    // k-blocks and chunk length of one tile in this kernel's own units
+    const int total_kb = FUSED ? K / BKF : 3 * kblocks;
+    constexpr int CHUNK = FUSED ? CHUNK_KB_F : CHUNK_KB;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C_::STAGES; ++s) {
@@ -173,17 +183,34 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m_blk = (int)(t / tiles_n), n_blk = (int)(t % tiles_n);
-                for (int seg = 0; seg < 3; ++seg) {
-                    const int a_off = seg == 1 ? K : 0, b_off = seg == 2 ? K : 0;
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                if constexpr (FUSED) {
+                    for (int kb = 0; kb < total_kb; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
+                        const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES);
+                        const uint32_t sal = sa + C_::A_BYTES, sb = sal + C_::A_BYTES, sbl = sb + C_::B_BYTES;
                         mbar_expect_tx(full0 + 8 * stage, C_::STAGE_BYTES);
-                        tma_load_2d(sa, &map_a, full0 + 8 * stage, a_off + kb * BK, m_blk * BM);
-                        tma_load_2d(sb, &map_b, full0 + 8 * stage, b_off + kb * BK, n_blk * BN);
+                        tma_load_2d(sa, &map_a, full0 + 8 * stage, kb * BKF, m_blk * BM);          // Zh
+                        tma_load_2d(sal, &map_a, full0 + 8 * stage, K + kb * BKF, m_blk * BM);     // Zl
+                        tma_load_2d(sb, &map_b, full0 + 8 * stage, kb * BKF, n_blk * BN);          // Wh
+                        tma_load_2d(sbl, &map_b, full0 + 8 * stage, K + kb * BKF, n_blk * BN);     // Wl
                         if (++stage == C_::STAGES) {
                             stage = 0;
                             phase ^= 1;
+                        }
+                    }
+                } else {
+                    for (int seg = 0; seg < 3; ++seg) {
+                        const int a_off = seg == 1 ? K : 0, b_off = seg == 2 ? K : 0;
+                        for (int kb = 0; kb < kblocks; ++kb) {
+                            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                            const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
+                            mbar_expect_tx(full0 + 8 * stage, C_::STAGE_BYTES);
+                            tma_load_2d(sa, &map_a, full0 + 8 * stage, a_off + kb * BK, m_blk * BM);
+                            tma_load_2d(sb, &map_b, full0 + 8 * stage, b_off + kb * BK, n_blk * BN);
+                            if (++stage == C_::STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
                 }
@@ -196,23 +223,35 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             long long chunk = 0;                                                  // running chunk counter (buffer = chunk & 1)
-            const int total_kb = 3 * kblocks;
             for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK_KB, ++chunk) {
+                for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK, ++chunk) {
                     const int as = (int)(chunk & 1);
                     mbar_wait(tempty0 + 8 * as, (uint32_t)((chunk >> 1) & 1) ^ 1);    // epilogue has drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tmem_d = tmem_base + as * ACC_COLS;
-                    const int kb1 = kb0 + CHUNK_KB < total_kb ? kb0 + CHUNK_KB : total_kb;
+                    const int kb1 = kb0 + CHUNK < total_kb ? kb0 + CHUNK : total_kb;
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(full0 + 8 * stage, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES), sb = sa + C_::A_BYTES;
-                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+                        const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES);
+                        if constexpr (FUSED) {
+                            const uint32_t sal = sa + C_::A_BYTES, sb = sal + C_::A_BYTES, sbl = sb + C_::B_BYTES;
+                            const uint64_t dah = make_smem_desc(sa, true), dal = make_smem_desc(sal, true);
+                            const uint64_t dbh = make_smem_desc(sb, true), dbl = make_smem_desc(sbl, true);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
-                            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || k != 0);
+                            for (int k = 0; k < BKF / UMMA_K; ++k) {     // small terms first, hi.hi last
+                                umma_f16(tmem_d, dal + 2 * k, dbh + 2 * k, idesc, (kb > kb0) || k != 0);
+                                umma_f16(tmem_d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+                                umma_f16(tmem_d, dah + 2 * k, dbh + 2 * k, idesc, 1u);
+                            }
+                        } else {
+                            const uint32_t sb = sa + C_::A_BYTES;
+                            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
+                                umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || k != 0);
+                            }
                         }
                         umma_commit(empty0 + 8 * stage);                          // frees the smem stage when the MMAs retire
                         if (++stage == C_::STAGES) {
@@ -230,14 +269,13 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         constexpr int NLD = HALF / 8;                      // x8 loads per chunk
         static_assert(HALF % 8 == 0, "BN/2 must be a multiple of 8");
         const int quarter = warp & 3, half = (warp - 2) >> 2;
-        const int total_kb = 3 * kblocks;
         long long chunk = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int m_blk = (int)(t / tiles_n), n_blk = (int)(t % tiles_n);
             float acc[HALF];
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
-            for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK_KB, ++chunk) {
+            for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK, ++chunk) {
                 const int as = (int)(chunk & 1);
                 mbar_wait(tfull0 + 8 * as, (uint32_t)((chunk >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -329,7 +367,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_map(CUtensorMap *map, const void *base, long long rows, long long cols, int box_rows)
+int encode_map(CUtensorMap *map, const void *base, long long rows, long long cols, int box_rows, bool fused = false)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -341,11 +379,11 @@ int encode_map(CUtensorMap *map, const void *base, long long rows, long long col
     }
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)(fused ? BKF : BK), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, fused ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         gad_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box=%dx%d)", (int)rc, rows, cols,
                       BK, box_rows);
@@ -364,11 +402,16 @@ int set_smem_attr()
 {
     GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN, true>::SMEM));
+    GAD_CUDA(cudaFuncSetAttribute(gemm_split_f16_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN, true>::SMEM));
     return GAD_OK;
 }
 
-int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, int BN)
+int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, int BN, int fused)
 {
+    L->fused = fused;
     GAD_REQUIRE(BN == TC_BN_L1 || BN == TC_BN_L2 || BN == TC_BN_L3, "tcgen05 layer: unsupported BN=%d", BN);
     L->N = N;
     L->K = K;
@@ -387,7 +430,7 @@ int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, 
     split_weights_kernel<<<GAD_NUM_SMS * 8, 256>>>(d_W, N, L->Npad, K, L->Kpad, L->scale, (__half *)L->W2);
     GAD_LAUNCH_CHECK();
     GAD_CUDA(cudaDeviceSynchronize());
-    int rc = encode_map((CUtensorMap *)L->map_b, L->W2, L->Npad, 2ll * L->Kpad, BN);
+    int rc = encode_map((CUtensorMap *)L->map_b, L->W2, L->Npad, 2ll * L->Kpad, BN, L->fused != 0);
     if (rc) return rc;
     if (BN == TC_BN_L1) return set_smem_attr<TC_BN_L1>();
     if (BN == TC_BN_L2) return set_smem_attr<TC_BN_L2>();
@@ -402,7 +445,7 @@ void tc_layer_free(TcLayer *L)
 
 int tc_layer_bind_a(TcLayer *L, const void *d_A2, long long rows)
 {
-    return encode_map((CUtensorMap *)L->map_a, d_A2, rows, 2ll * L->Kpad, BM);
+    return encode_map((CUtensorMap *)L->map_a, d_A2, rows, 2ll * L->Kpad, BM, L->fused != 0);
 }
 
 template <int BN>
@@ -413,7 +456,13 @@ int run_bn(const TcLayer *L, const float *d_bias, void *d_out, int ldc, int lo_o
     if (tiles == 0) return GAD_OK;
     const unsigned grid = (unsigned)(tiles < GAD_NUM_SMS ? tiles : GAD_NUM_SMS);
     const CUtensorMap &ma = *(const CUtensorMap *)L->map_a, &mb = *(const CUtensorMap *)L->map_b;
-    if (split_out)
+    if (L->fused && split_out)
+        gemm_split_f16_kernel<BN, true, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+    else if (L->fused)
+        gemm_split_f16_kernel<BN, false, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+    else if (split_out)
         gemm_split_f16_kernel<BN, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
             ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
     else

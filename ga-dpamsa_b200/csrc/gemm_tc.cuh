@@ -9,6 +9,7 @@
 
 struct TcLayer {
     int N = 0, K = 0, Kpad = 0, BN = 0, Npad = 0;
+    int fused = 0;                           // 1: hi and lo tiles of a 32-wide k-block share a stage (64B swizzle)
     float scale = 1.f, inv_scale = 1.f;      // weights are stored as w * 2^s; the epilogue multiplies by 2^-s
     void *W2 = nullptr;                      // fp16 [Npad][2*Kpad] = (hi | lo), zero beyond N and K
     alignas(64) unsigned char map_a[128];    // CUtensorMap of the activations (hi | lo), rebound when they move
@@ -17,7 +18,7 @@ struct TcLayer {
 
 // BN must be one of the TC_BN_* values. K is padded to a multiple of 64 (Kpad); the activation buffer
 // bound with tc_layer_bind_a is fp16 [rows][2*Kpad] = (hi | lo) with zeros in the padding columns.
-int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, int BN);
+int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, int BN, int fused);
 void tc_layer_free(TcLayer *L);
 int tc_layer_bind_a(TcLayer *L, const void *d_A2, long long rows);
 // out[m][n] = act((A . W^T)[m][n] * 2^-s + bias[n]) for m < *d_m (or m_max when d_m is NULL), n < N.

@@ -1527,9 +1527,10 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
         q->tc1 = new TcLayer();
         q->tc2 = new TcLayer();
         q->tc3 = new TcLayer();
-        rc = tc_layer_init(q->tc1, q->W1, h_weights[10], h1, q->K, TC_BN_L1);
-        if (!rc) rc = tc_layer_init(q->tc2, q->W2, h_weights[12], h2, h1, TC_BN_L2);
-        if (!rc) rc = tc_layer_init(q->tc3, q->W3, h_weights[14], q->A, h2, TC_BN_L3);
+        const char *unf = getenv("GAD_L1_UNFUSED");        // A/B switch: 1 = three separate (hi.hi, lo.hi, hi.lo) k-loops
+        rc = tc_layer_init(q->tc1, q->W1, h_weights[10], h1, q->K, TC_BN_L1, (unf && unf[0] == '1') ? 0 : 1);
+        if (!rc) rc = tc_layer_init(q->tc2, q->W2, h_weights[12], h2, h1, TC_BN_L2, 0);
+        if (!rc) rc = tc_layer_init(q->tc3, q->W3, h_weights[14], q->A, h2, TC_BN_L3, 0);
     }
     if (!rc) rc = dev_alloc(&q->counts, 2);
     if (!rc && cudaMallocHost((void **)&q->h_count, 2 * sizeof(int32_t)) != cudaSuccess) {
