@@ -191,3 +191,30 @@ def test_full_size_population_properties(gpu):
     assert np.array_equal(sp.cpu().numpy()[idx], osp)
     assert np.array_equal(em.cpu().numpy()[idx], oem)
     assert np.array_equal(al.cpu().numpy()[idx], oal)
+
+
+def test_randomized_shape_sweep(gpu):
+    """Many (rows, width, stride, weights) combinations, including rows > 30 (several nibble-counter epochs),
+    rows up to 255, widths past 1000 and boards made mostly of gaps - device == oracle, bit for bit."""
+    rng = np.random.default_rng(2025)
+    shapes = [(1, 5), (2, 1), (7, 16), (8, 17), (9, 64), (29, 40), (30, 33), (31, 47), (32, 100), (61, 130),
+              (64, 1050), (100, 90), (255, 20), (13, 1200), (5, 257)]
+    for R, W in shapes:
+        P = 40 if R * W < 20000 else 6
+        stride = -(-(W + int(rng.integers(0, 40))) // 16) * 16
+        boards = np.zeros((P, R, stride), np.uint8)
+        rowlen = np.zeros((P, R), np.int32)
+        for p in range(P):
+            gap_p = rng.choice([0.05, 0.3, 0.9])
+            w = int(rng.integers(max(1, W - 20), W + 1))
+            for r in range(R):
+                n = int(rng.integers(max(0, w - 9), w + 1))
+                row = rng.integers(1, 5, size=n).astype(np.uint8)
+                row[rng.random(n) < gap_p] = 5
+                boards[p, r, :n] = row
+                rowlen[p, r] = n
+            for c in rng.integers(0, w, size=3):                  # a few all-gap columns
+                boards[p, :, c] = np.where(np.arange(R) < R, 5, 5)
+        pop = O.to_lists(boards, rowlen)
+        for weights in ((4, -4, -4), (7, -2, -11)):
+            assert_parity(copy.deepcopy(pop), weights=weights, stride=stride)
