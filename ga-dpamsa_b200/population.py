@@ -186,7 +186,8 @@ class DevicePopulation:
         need = round_up(need, 16)
         if need <= self.stride:
             return
-        old = self.stride
+        need = max(need, round_up(self.stride + self.stride // 4, 16))      # grow geometrically: re-laying out a
+        old = self.stride                                                    # sharded population costs a rendezvous
         self.stride = need
         for name in ("cur", "alt"):
             buf = getattr(self, name)
