@@ -285,7 +285,8 @@ class DeviceBackend:
         g = ga_mod.GA.__new__(ga_mod.GA)
         g.sequences, g.mode, g.population_size, g._dev = sequences, 'sp', P, None
         g._device = self.device
-        extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
+        # room for two worst-case mutations: re-laying out symmetric buffers later costs a rendezvous (~0.1 s)
+        extra = max(32, 2 * (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
         width = max(len(s) for s in sequences) + max(1, round(max(len(s) for s in sequences) * config.GAP_RATE))
         return g._generate_host(rank, world, min_stride=width + extra)     # final stride at once: no second host copy
 
