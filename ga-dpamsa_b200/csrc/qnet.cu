@@ -54,6 +54,11 @@ struct gad_qnet {
     uint8_t *sub = nullptr, *heads = nullptr, *aligned = nullptr;
     int32_t *steps = nullptr, *list0 = nullptr, *list1 = nullptr, *counts = nullptr;   // counts[2]
     int32_t *h_count = nullptr;   // pinned
+    // staging of gad_qnet_forward_host (DQN.predict from python)
+    long long hcap = 0;
+    uint8_t *hs_states = nullptr;
+    float *hs_q = nullptr;
+    int32_t *hs_act = nullptr;
 };
 
 namespace {
@@ -1331,8 +1336,11 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
     const char *enc = getenv("GAD_QNET_ENCODER");
     if (encode_fa_smem_bytes(q->L) <= 110 * 1024 && !enc) {
         const int bytes = encode_fa_smem_bytes(q->L);
-        if (bytes > 48 * 1024)
+        static int fa_attr_bytes = 0;                      // opt in to > 48 KB of dynamic shared memory once per size
+        if (bytes > 48 * 1024 && bytes != fa_attr_bytes) {
             GAD_CUDA(cudaFuncSetAttribute(encode_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            fa_attr_bytes = bytes;
+        }
         long long per_sm = (224 * 1024) / (bytes + 1024);
         if (per_sm > 4) per_sm = 4;
         const long long grid = n_max < (long long)GAD_NUM_SMS * per_sm ? n_max : (long long)GAD_NUM_SMS * per_sm;
@@ -1554,6 +1562,7 @@ extern "C" int gad_qnet_destroy(gad_qnet *q)
     cudaFree(q->VFh);
     cudaFree(q->VFl);
     cudaFree(q->Qh); cudaFree(q->Ql); cudaFree(q->Kh); cudaFree(q->Kl);
+    cudaFree(q->hs_states); cudaFree(q->hs_q); cudaFree(q->hs_act);
     for (TcLayer *t : {q->tc1, q->tc2, q->tc3})
         if (t) {
             tc_layer_free(t);
@@ -1602,22 +1611,23 @@ extern "C" int gad_qnet_forward_host(gad_qnet *q, const uint8_t *h_states, int64
 {
     GAD_REQUIRE(q && h_states && B >= 0, "gad_qnet_forward_host: bad argument");
     if (B == 0) return GAD_OK;
-    uint8_t *d_states = nullptr;
-    float *d_q = nullptr;
-    int32_t *d_a = nullptr;
-    int rc = dev_alloc(&d_states, (size_t)B * q->L);
-    if (!rc) rc = dev_alloc(&d_q, (size_t)B * q->A);
-    if (!rc) rc = dev_alloc(&d_a, (size_t)B);
-    if (!rc && cudaMemcpy(d_states, h_states, (size_t)B * q->L, cudaMemcpyHostToDevice) != cudaSuccess) rc = GAD_ECUDA;
-    if (!rc) rc = gad_qnet_forward(q, d_states, B, max_value, d_q, d_a, nullptr);
-    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = GAD_ECUDA;
-    if (!rc && h_q && cudaMemcpy(h_q, d_q, (size_t)B * q->A * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GAD_ECUDA;
-    if (!rc && h_action && cudaMemcpy(h_action, d_a, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = GAD_ECUDA;
-    if (rc == GAD_ECUDA) gad_set_error("gad_qnet_forward_host: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(d_states);
-    cudaFree(d_q);
-    cudaFree(d_a);
-    return rc;
+    int rc = GAD_OK;
+    if (B > q->hcap) {
+        cudaFree(q->hs_states); cudaFree(q->hs_q); cudaFree(q->hs_act);
+        q->hs_states = nullptr; q->hs_q = nullptr; q->hs_act = nullptr;
+        q->hcap = 0;
+        rc = dev_alloc(&q->hs_states, (size_t)B * q->L);
+        if (!rc) rc = dev_alloc(&q->hs_q, (size_t)B * q->A);
+        if (!rc) rc = dev_alloc(&q->hs_act, (size_t)B);
+        if (rc) return rc;
+        q->hcap = B;
+    }
+    GAD_CUDA(cudaMemcpy(q->hs_states, h_states, (size_t)B * q->L, cudaMemcpyHostToDevice));
+    if ((rc = gad_qnet_forward(q, q->hs_states, B, max_value, q->hs_q, q->hs_act, nullptr))) return rc;
+    GAD_CUDA(cudaDeviceSynchronize());
+    if (h_q) GAD_CUDA(cudaMemcpy(h_q, q->hs_q, (size_t)B * q->A * sizeof(float), cudaMemcpyDeviceToHost));
+    if (h_action) GAD_CUDA(cudaMemcpy(h_action, q->hs_act, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return GAD_OK;
 }
 
 // GA.mutation for M individuals (GA.py:335-373): d_idx[m] is the individual, d_tile[m] = {from_row,

@@ -45,3 +45,25 @@ def test_argument_errors_without_gpu(native_lib):
     assert b"R" in lib.gad_last_error()
     rc = lib.gad_fitness(None, None, 4, 3, 10, 0, 4, -4, -4, None, None, None, None, None)
     assert rc == native_lib.GAD_EINVAL and b"stride" in lib.gad_last_error()
+
+
+def test_product_path_fails_loudly_without_a_gpu(native_lib):
+    """No CPU fallback: on a machine without a CUDA device every compute entry of the facade raises
+    (nothing under ga-dpamsa_b200/ may import the oracle or compute on the host)."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import config      # noqa: F401
+    import utils
+    import GA
+    board = [[1, 2, 3], [1, 2, 4]]
+    with pytest.raises(native_lib.GadError):
+        utils.get_sum_of_pairs(board, 0, 2, 0, 3)
+    with pytest.raises(native_lib.GadError):
+        utils.clean_unnecessary_gaps([[1, 5], [2, 5]])
+    with pytest.raises(native_lib.GadError):
+        GA.GA(["ACGT", "ACGA"], "sp").generate_population()
+    src = "".join(open(os.path.join(ROOT, "ga-dpamsa_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "ga-dpamsa_b200")) if f.endswith(".py"))
+    assert "ga_oracle" not in src and "import oracle" not in src
