@@ -76,23 +76,18 @@ def synth_population(rows, cols, P, seed):
     boards[:n_clone, :, :cols] = seqs[None]
     rowlen[:n_clone] = cols
     m = P - n_clone
-    # gap positions: choose n_gap of the `width` output slots per row (same support as repeated insert)
-    keys = rng.random((m, rows, width))
+    # gap positions: n_gap distinct output slots per row; a gap is never the last cell because every insert
+    # goes in front of an existing element (randint(0, len - 1)), so slots come from [0, width - 1)
+    keys = rng.random((m, rows, width - 1))
     gap_slots = np.argsort(keys, axis=2)[:, :, :n_gap]
     is_gap = np.zeros((m, rows, width), dtype=bool)
     np.put_along_axis(is_gap, gap_slots, True, axis=2)
-    is_gap[:, :, width - 1] = False            # randint(0, len-1) never appends at the very end
-    src = np.cumsum(~is_gap, axis=2) - 1
-    src = np.clip(src, 0, cols - 1)
+    src = np.clip(np.cumsum(~is_gap, axis=2) - 1, 0, cols - 1)
     vals = np.take_along_axis(np.broadcast_to(seqs[None], (m, rows, cols)), src, axis=2)
     vals[is_gap] = 5
-    n_real = (~is_gap).sum(axis=2)
-    lens = np.minimum(width, cols + is_gap.sum(axis=2)).astype(np.int32)
-    col_idx = np.arange(width)[None, None, :]
-    vals[col_idx >= lens[:, :, None]] = 5
+    lens = np.full((m, rows), width, dtype=np.int32)
     boards[n_clone:, :, :width] = vals
     rowlen[n_clone:] = lens
-    del n_real
     return boards, rowlen
 
 
