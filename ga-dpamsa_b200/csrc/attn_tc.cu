@@ -1,0 +1,377 @@
+// The encoder's attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// Same mathematics as encode_fa_kernel (qnet.cu) - S = Q'K'^T from split fp16 row tables, softmax in the
+// log2 domain, O = P V with the output projection folded into V, residual, LayerNorm - but both products run
+// as tcgen05.mma with the accumulators in tensor memory:
+//
+//   one CTA per state (persistent), 1 CTA per SM, 288 threads:
+//     warps 0-3   own the 128 query rows of tile 0 (thread = row = TMEM lane), warps 4-7 those of tile 1
+//     warp 8      lane 0 issues every tcgen05.mma; the warp also allocates / frees the 512 TMEM columns
+//   shared memory (K-major, 128-byte swizzled operand tiles, written by the threads themselves):
+//     Q'  hi|lo  2 tiles x [128 rows][64]      64 KB      A operand of S
+//     K'  hi|lo  [<=192 keys][64]              48 KB      B operand of S (N = keys)
+//     V^T hi|lo  3 atoms x [64 ch][64 keys]    48 KB      B operand of O (N = 64 channels, K = keys)
+//     P   hi|lo  per tile [128 rows][64 keys]  64 KB      A operand of O, one 64-key slice at a time
+//   tensor memory: S of tile 0 / 1 at columns 0 / 192 (fp32, up to 192 keys), O of tile 0 / 1 at 384 / 448.
+//
+//   MMA warp : S(t0), S(t1)  ->  per 64-key slice: wait P(t) -> 12 MMAs O(t) += P V -> commit (frees P(t))
+//   row thread: wait S -> row max (tcgen05.ld) -> per slice: p = ex2(s - max), hi/lo fp16 into the swizzled
+//               P tile, fence.proxy.async, arrive -> ... -> wait O -> /sum, residual, LayerNorm, (hi|lo) store
+// Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi), so the result is fp32-class like the other
+// encoders; a row's softmax and LayerNorm need no cross-thread reduction at all.
+#include "qnet.cuh"
+#include "tc_ptx.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+using namespace tcptx;
+
+namespace {
+
+constexpr int AT_ROWS = 128;                 // query rows per tile = UMMA M
+constexpr int AT_MAXK = 192;                 // keys (and query rows / 128 * 128 <= 256)
+constexpr int AT_THREADS = 288;
+constexpr int AT_TILE_Q = AT_ROWS * 128;     // bytes of one [128][64] fp16 tile
+constexpr int AT_TILE_K = AT_MAXK * 128;
+constexpr int AT_ATOM_V = 64 * 128;          // [64 ch][64 keys]
+constexpr int OFF_QH = 0;                                    // 2 tiles
+constexpr int OFF_QL = OFF_QH + 2 * AT_TILE_Q;
+constexpr int OFF_KH = OFF_QL + 2 * AT_TILE_Q;
+constexpr int OFF_KL = OFF_KH + AT_TILE_K;
+constexpr int OFF_VH = OFF_KL + AT_TILE_K;                   // 3 atoms
+constexpr int OFF_VL = OFF_VH + 3 * AT_ATOM_V;
+constexpr int OFF_PH = OFF_VL + 3 * AT_ATOM_V;               // 2 tiles
+constexpr int OFF_PL = OFF_PH + 2 * AT_TILE_Q;
+constexpr int OFF_BAR = OFF_PL + 2 * AT_TILE_Q;              // 229 376
+constexpr int AT_SMEM = OFF_BAR + 128 + 1024;                // + barriers + alignment slack
+constexpr int COL_S = 0, COL_O = 384;
+constexpr int TMEM_COLS = 512;
+
+// byte offset of the 16-byte chunk c of row r inside a K-major tile with 128-byte rows and 128B swizzle
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ float fast_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
+                 const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
+                 __half *__restrict__ Z2out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
+    // bars: s_full[2], p_ready[2], p_free[2], o_full[2], then the TMEM base address
+    const uint32_t b_sfull = smem_u32(bars), b_pready = b_sfull + 16, b_pfree = b_pready + 16, b_ofull = b_pfree + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    __shared__ int kj[AT_MAXK];
+    __shared__ uint8_t tok[AT_MAXK + 64];
+    __shared__ int s_nk;
+
+    const int L = net.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (L + AT_ROWS - 1) / AT_ROWS;
+    const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(b_sfull + 8 * t, 1);
+            mbar_init(b_pready + 8 * t, AT_ROWS);
+            mbar_init(b_pfree + 8 * t, 1);
+            mbar_init(b_ofull + 8 * t, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // phase bits of the per-state barriers (every barrier completes the same number of times per state for
+    // all of its waiters, so each thread tracks the parity itself)
+    uint32_t ph_s = 0, ph_o = 0, ph_pready[2] = {0, 0}, ph_pfree = 0;
+
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        __syncthreads();                                  // previous state fully consumed (its epilogue is done)
+        if (tok_in) {
+            for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
+            __syncthreads();
+        } else {
+            const int e = active[row];
+            build_tokens(tok, net.sub + (size_t)e * net.rows * net.cols, net.heads + (size_t)e * net.rows, net.rows,
+                         net.cols, L);
+        }
+        if (warp == 0) {                                  // ordered list of unmasked keys
+            int base = 0;
+            for (int j0 = 0; j0 < L; j0 += 32) {
+                const int j = j0 + lane;
+                const bool v = j < L && tok[j] != 0;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, v);
+                if (v) kj[base + __popc(m & ((1u << lane) - 1u))] = j;
+                base += __popc(m);
+            }
+            if (lane == 0) s_nk = base;
+        }
+        __syncthreads();
+        int nk = s_nk;
+        const bool all_masked = nk == 0;                  // reference: softmax over all -1e9 is uniform over every key
+        if (all_masked) {
+            for (int j = threadIdx.x; j < L; j += blockDim.x) kj[j] = j;
+            nk = L;
+            __syncthreads();
+        }
+        const int nk16 = (nk + 15) & ~15;
+        const int n_slices = (nk16 + 63) >> 6;
+
+        // ---- staging: every thread copies 16-byte chunks into the swizzled operand tiles
+        for (int idx = threadIdx.x; idx < n_tiles * AT_ROWS * 8; idx += blockDim.x) {      // Q' rows (all query positions)
+            const int i = idx >> 3, c = idx & 7;
+            uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+            if (i < L) {
+                const size_t src = ((size_t)tok[i] * L + i) * QN_D + c * 8;
+                h = __ldg(reinterpret_cast<const uint4 *>(net.Qh + src));
+                l = __ldg(reinterpret_cast<const uint4 *>(net.Ql + src));
+            }
+            const uint32_t off = (uint32_t)(i >> 7) * AT_TILE_Q + sw128(i & 127, c);
+            *reinterpret_cast<uint4 *>(sm + OFF_QH + off) = h;
+            *reinterpret_cast<uint4 *>(sm + OFF_QL + off) = l;
+        }
+        for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {                    // K' rows of the valid keys
+            const int k = idx >> 3, c = idx & 7;
+            uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+            if (k < nk) {
+                const int j = kj[k];
+                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
+                h = __ldg(reinterpret_cast<const uint4 *>(net.Kh + src));
+                l = __ldg(reinterpret_cast<const uint4 *>(net.Kl + src));
+            }
+            *reinterpret_cast<uint4 *>(sm + OFF_KH + sw128(k, c)) = h;
+            *reinterpret_cast<uint4 *>(sm + OFF_KL + sw128(k, c)) = l;
+        }
+        for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {                    // V^T: [channel][key]
+            const int k = idx % nk16, c8 = idx / nk16;                                      // consecutive threads: consecutive keys
+            uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+            if (k < nk) {
+                const int j = kj[k];
+                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c8 * 8;
+                h = __ldg(reinterpret_cast<const uint4 *>(net.VFh + src));
+                l = __ldg(reinterpret_cast<const uint4 *>(net.VFl + src));
+            }
+            const __half *hh = reinterpret_cast<const __half *>(&h), *ll = reinterpret_cast<const __half *>(&l);
+            const int atom = k >> 6, kk = k & 63;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ch = c8 * 8 + e;
+                const uint32_t off = (uint32_t)atom * AT_ATOM_V + sw128(ch, kk >> 3) + (kk & 7) * 2;
+                *reinterpret_cast<__half *>(sm + OFF_VH + off) = hh[e];
+                *reinterpret_cast<__half *>(sm + OFF_VL + off) = ll[e];
+            }
+        }
+        fence_async_smem();                               // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+
+        if (warp == 8) {
+            // ======================= MMA issuer =======================
+            if (lane == 0) {
+                tc_fence_after();
+                const uint32_t idesc_s = make_idesc_f16(AT_ROWS, nk16);
+                const uint32_t idesc_o = make_idesc_f16(AT_ROWS, QN_D);
+                const uint64_t dkh = make_smem_desc(smem_u32(sm + OFF_KH)), dkl = make_smem_desc(smem_u32(sm + OFF_KL));
+                for (int t = 0; t < n_tiles; ++t) {       // S(t) = Q'(t) K'^T : 4 k-steps x (lo.hi, hi.lo, hi.hi)
+                    const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH + t * AT_TILE_Q));
+                    const uint64_t dql = make_smem_desc(smem_u32(sm + OFF_QL + t * AT_TILE_Q));
+                    const uint32_t d = tmem_base + COL_S + t * AT_MAXK;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_f16(d, dql + 2 * ks, dkh + 2 * ks, idesc_s, ks != 0);
+                        umma_f16(d, dqh + 2 * ks, dkl + 2 * ks, idesc_s, 1u);
+                        umma_f16(d, dqh + 2 * ks, dkh + 2 * ks, idesc_s, 1u);
+                    }
+                    umma_commit(b_sfull + 8 * t);
+                }
+                uint32_t php[2] = {ph_pready[0], ph_pready[1]};
+                for (int sl = 0; sl < n_slices; ++sl) {
+                    const int ksteps = min(4, (nk16 - 64 * sl) >> 4);
+                    for (int t = 0; t < n_tiles; ++t) {   // O(t) += P(t, slice) V(slice)
+                        mbar_wait(b_pready + 8 * t, php[t]);
+                        php[t] ^= 1;
+                        tc_fence_after();
+                        const uint64_t dph = make_smem_desc(smem_u32(sm + OFF_PH + t * AT_TILE_Q));
+                        const uint64_t dpl = make_smem_desc(smem_u32(sm + OFF_PL + t * AT_TILE_Q));
+                        const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_VH + sl * AT_ATOM_V));
+                        const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_VL + sl * AT_ATOM_V));
+                        const uint32_t d = tmem_base + COL_O + t * QN_D;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            umma_f16(d, dpl + 2 * ks, dvh + 2 * ks, idesc_o, (sl | ks) != 0);
+                            umma_f16(d, dph + 2 * ks, dvl + 2 * ks, idesc_o, 1u);
+                            umma_f16(d, dph + 2 * ks, dvh + 2 * ks, idesc_o, 1u);
+                        }
+                        if (sl + 1 < n_slices) umma_commit(b_pfree + 8 * t);      // the P tile may be overwritten
+                        else umma_commit(b_ofull + 8 * t);                         // O(t) complete
+                    }
+                }
+            }
+            // keep the warp's phase bookkeeping in step with the row threads
+            for (int t = 0; t < n_tiles; ++t)
+                if (n_slices & 1) ph_pready[t] ^= 1;
+        } else if (warp < 4 * n_tiles) {
+            // ======================= row threads: thread = query row =======================
+            const int t = warp >> 2;
+            const int r = (warp & 3) * 32 + lane;         // row inside the tile = TMEM lane
+            const int i = t * AT_ROWS + r;                // query position
+            const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            const float sc = net.s_inv_scale;
+            mbar_wait(b_sfull + 8 * t, ph_s);
+            tc_fence_after();
+            // pass 1: row maximum over the valid keys
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < nk16; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + COL_S + t * AT_MAXK + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (c0 + u < nk) mx = fmaxf(mx, __uint_as_float(v[u]));
+            }
+            if (all_masked) mx = 0.f;
+            const float mxs = mx * sc;
+            float lsum = 0.f;
+            uint32_t my_pfree = ph_pfree;
+            for (int sl = 0; sl < n_slices; ++sl) {
+                if (sl > 0) {                             // the previous slice's MMAs must have read the P tile
+                    mbar_wait(b_pfree + 8 * t, my_pfree);
+                    my_pfree ^= 1;
+                }
+                const int kend = min(64, nk16 - 64 * sl);
+                for (int c0 = 0; c0 < kend; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(lane_addr + COL_S + t * AT_MAXK + 64 * sl + c0, v);
+                    tmem_ld_wait();
+                    float p[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int key = 64 * sl + c0 + u;
+                        float x = all_masked ? 1.f : fast_ex2(fmaf(__uint_as_float(v[u]), sc, -mxs));
+                        if (key >= nk) x = 0.f;
+                        p[u] = x;
+                        lsum += x;
+                    }
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const __half2 h = __floats2half2_rn(p[2 * u], p[2 * u + 1]);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(p[2 * u] - hf.x, p[2 * u + 1] - hf.y);
+                        hi[u] = *reinterpret_cast<const uint32_t *>(&h);
+                        lo[u] = *reinterpret_cast<const uint32_t *>(&l);
+                    }
+                    const int c = c0 >> 3;                // two 16-byte chunks (8 keys each) per 16 columns
+                    uint8_t *ph = sm + OFF_PH + t * AT_TILE_Q, *pl = sm + OFF_PL + t * AT_TILE_Q;
+                    *reinterpret_cast<uint4 *>(ph + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(ph + sw128(r, c + 1)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4 *>(pl + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(pl + sw128(r, c + 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(b_pready + 8 * t);
+            }
+            // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the 64 channels of this thread's row
+            mbar_wait(b_ofull + 8 * t, ph_o);
+            tc_fence_after();
+            float y[QN_D];
+#pragma unroll
+            for (int c0 = 0; c0 < QN_D; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + COL_O + t * QN_D + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 16; ++u) y[c0 + u] = __uint_as_float(v[u]);
+            }
+            tc_fence_before();
+            if (i < L) {
+                const float inv = net.vf_inv_scale / lsum;
+                const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[i] * L + i) * QN_D);
+                float s1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < QN_D / 4; ++c) {
+                    const float4 x = __ldg(x4 + c);
+                    y[4 * c + 0] = fmaf(y[4 * c + 0], inv, x.x);
+                    y[4 * c + 1] = fmaf(y[4 * c + 1], inv, x.y);
+                    y[4 * c + 2] = fmaf(y[4 * c + 2], inv, x.z);
+                    y[4 * c + 3] = fmaf(y[4 * c + 3], inv, x.w);
+                    s1 += (y[4 * c + 0] + y[4 * c + 1]) + (y[4 * c + 2] + y[4 * c + 3]);
+                }
+                const float mu = s1 * (1.f / QN_D);
+                float s2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < QN_D; ++c) {
+                    y[c] -= mu;
+                    s2 = fmaf(y[c], y[c], s2);
+                }
+                const float rstd = rsqrtf(s2 * (1.f / QN_D) + 1e-6f);          // LayerNorm(eps=1e-6), models.py:166
+                if (Z2out) {
+                    __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D, *zl = zh + net.K;
+#pragma unroll
+                    for (int c = 0; c < QN_D; c += 8) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float z0 = y[c + 2 * u] * rstd * net.ln2_g[c + 2 * u] + net.ln2_b[c + 2 * u];
+                            const float z1 = y[c + 2 * u + 1] * rstd * net.ln2_g[c + 2 * u + 1] + net.ln2_b[c + 2 * u + 1];
+                            const __half2 h = __floats2half2_rn(z0, z1);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
+                            hi[u] = *reinterpret_cast<const uint32_t *>(&h);
+                            lo[u] = *reinterpret_cast<const uint32_t *>(&l);
+                        }
+                        *reinterpret_cast<uint4 *>(zh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(zl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                } else {
+                    float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D;
+#pragma unroll
+                    for (int c = 0; c < QN_D; ++c) z[c] = y[c] * rstd * net.ln2_g[c] + net.ln2_b[c];
+                }
+            }
+            ph_pfree = my_pfree;
+        }
+        // per-state phase flips (identical for every thread that used the barrier)
+        ph_s ^= 1;
+        ph_o ^= 1;
+        if (warp != 8 && (n_slices & 1))
+            for (int t = 0; t < 2; ++t) ph_pready[t] ^= 1;
+        if (warp >= 4 * n_tiles && warp != 8 && ((n_slices - 1) & 1)) ph_pfree ^= 1;      // idle row warps keep the parity
+    }
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+}  // namespace
+
+int attn_tc_supported(const gad_qnet *q) { return q->L <= AT_MAXK && q->L >= 16; }
+
+int launch_encode_tc(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const int32_t *n_ptr, long long n_max,
+                     cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        attr_set = true;
+    }
+    const long long grid = n_max < GAD_NUM_SMS ? n_max : GAD_NUM_SMS;
+    encode_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}

@@ -17,49 +17,13 @@
 //     GEMM over all active episodes; l3 + tanh + argmax + Environment.step are fused in one kernel.
 //   * episodes run in lock-step on device with an active list that shrinks as episodes finish; the
 //     host only polls the active count.
-#include "gad_common.cuh"
-#include "gemm_tc.cuh"
+#include "qnet.cuh"
 
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-
-#define QN_D 64            // d_model of the reference encoder (dqn.py:54)
-#define QN_VOCAB 6         // 0 = padding, 1..5 = A T C G gap
-
-struct gad_qnet {
-    int rows, cols, L, A, K, h1, h2;
-    // parameters / folded tables (device, fp32)
-    float *X = nullptr, *T = nullptr, *VF = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
-    __half *VFh = nullptr, *VFl = nullptr;   // VF * 2^sv split into fp16 hi + lo (encode_mma_kernel's B operand)
-    float vf_inv_scale = 1.f;
-    // attention as tensor-core products (encode_fa_kernel): Q' = QM * log2(e) * 2^sq and K' = X * 2^sk, fp16 hi + lo
-    __half *Qh = nullptr, *Ql = nullptr, *Kh = nullptr, *Kl = nullptr;
-    float s_inv_scale = 1.f;                 // 2^-(sq+sk): raw MMA sum -> logit in the log2 domain
-    float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr, *W3 = nullptr, *b3 = nullptr;
-    // activation scratch for `cap` states
-    long long cap = 0;
-    uint8_t *tok = nullptr;
-    float *Z = nullptr, *H1 = nullptr, *H2 = nullptr, *Q = nullptr;
-    __half *Z2 = nullptr;            // (hi | lo) fp16 split of Z, [cap][2K]: A operand of the tcgen05 l1
-    TcLayer *tc1 = nullptr;          // NULL = fp32 SIMT dense layers (GAD_QNET_SIMT=1)
-    TcLayer *tc2 = nullptr, *tc3 = nullptr;
-    __half *H1s = nullptr, *H2s = nullptr;   // (hi | lo) activations between the tensor-core layers
-    float *Qpre = nullptr;           // l3 output before tanh, [cap][64]
-    int32_t *act = nullptr;
-    // episode state for `ecap` episodes
-    long long ecap = 0;
-    uint8_t *sub = nullptr, *heads = nullptr, *aligned = nullptr;
-    int32_t *steps = nullptr, *list0 = nullptr, *list1 = nullptr, *counts = nullptr;   // counts[2]
-    int32_t *h_count = nullptr;   // pinned
-    // staging of gad_qnet_forward_host (DQN.predict from python)
-    long long hcap = 0;
-    uint8_t *hs_states = nullptr;
-    float *hs_q = nullptr;
-    int32_t *hs_act = nullptr;
-};
 
 namespace {
 
@@ -69,37 +33,6 @@ const long long kMaxBatch = 32768;     // states per lock-step chunk (Z is kMaxB
 // encoder: tokens -> Z[row][L*64]  (attention over table logits, + residual, second LayerNorm)
 // ---------------------------------------------------------------------------------------------
 #define ENC_QT 4           // query rows per warp trip
-
-// tokens of episode e from its sub-board and head pointers (env.py:147-153): every row's remaining
-// tokens followed by one gap code, rows concatenated, zero padding up to L
-__device__ __forceinline__ int build_tokens(uint8_t *tok, const uint8_t *sub, const uint8_t *heads, int rows, int cols,
-                                            int L)
-{
-    __shared__ int s_off[33];
-    if (threadIdx.x == 0) {
-        int o = 0;
-        for (int r = 0; r < rows; ++r) {
-            s_off[r] = o;
-            o += cols - heads[r] + 1;
-        }
-        s_off[rows] = o;
-    }
-    __syncthreads();
-    const int nvalid = s_off[rows];
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        uint8_t t = 0;
-        if (i < nvalid) {
-            int r = 0;
-            while (i >= s_off[r + 1]) ++r;
-            const int k = i - s_off[r];
-            const int rem = cols - heads[r];
-            t = k < rem ? sub[r * cols + heads[r] + k] : (uint8_t)GAD_GAP;
-        }
-        tok[i] = t;
-    }
-    __syncthreads();
-    return nvalid;
-}
 
 __global__ void __launch_bounds__(256)
 encode_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
@@ -1334,7 +1267,10 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
     // GAD_QNET_ENCODER (A/B testing): unset = flash-attention style kernel, "mma" = table logits + mma.sync
     // product, "simt" = table logits + fp32 register tiles
     const char *enc = getenv("GAD_QNET_ENCODER");
-    if (encode_fa_smem_bytes(q->L) <= 110 * 1024 && !enc) {
+    if (enc && enc[0] == 't' && attn_tc_supported(q)) {   // "tc": attention on tcgen05 (attn_tc.cu)
+        int rc = launch_encode_tc(q, tok_in, active, n_ptr, n_max, st);
+        if (rc) return rc;
+    } else if (encode_fa_smem_bytes(q->L) <= 110 * 1024 && !(enc && (enc[0] == 'm' || enc[0] == 's'))) {
         const int bytes = encode_fa_smem_bytes(q->L);
         static int fa_attr_bytes = 0;                      // opt in to > 48 KB of dynamic shared memory once per size
         if (bytes > 48 * 1024 && bytes != fa_attr_bytes) {
