@@ -18,6 +18,12 @@
 //               P tile, fence.proxy.async, arrive -> ... -> wait O -> /sum, residual, LayerNorm, (hi|lo) store
 // Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi), so the result is fp32-class like the other
 // encoders; a row's softmax and LayerNorm need no cross-thread reduction at all.
+//
+// Status (round 1): correct (parity tests pass with GAD_QNET_ENCODER=tc) but ~15 % slower than encode_fa_kernel at
+// 6x30 (2.0 ms vs 1.7 ms for 16 384 states): with 224 KB of operand tiles only one CTA fits an SM and the phases
+// of a state (staging -> S -> softmax -> P V -> epilogue) run back to back, so the tensor pipe is 10 % busy.
+// It is therefore opt-in; overlapping consecutive states (double-buffered K/V tiles need the Q tiles out of
+// shared memory, e.g. as a TMEM A operand) is the next step.
 #include "qnet.cuh"
 #include "tc_ptx.cuh"
 
@@ -132,50 +138,62 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         const int nk16 = (nk + 15) & ~15;
         const int n_slices = (nk16 + 63) >> 6;
 
-        // ---- staging: every thread copies 16-byte chunks into the swizzled operand tiles
+        // ---- staging. Q' and K' rows are straight 16-byte chunk copies into swizzled positions: cp.async
+        // (no registers, all copies of a thread in flight at once); rows outside the state are zero-filled
+        // through the src-size operand. The V^T transposes below run while these copies are in flight.
         for (int idx = threadIdx.x; idx < n_tiles * AT_ROWS * 8; idx += blockDim.x) {      // Q' rows (all query positions)
             const int i = idx >> 3, c = idx & 7;
-            uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
-            if (i < L) {
-                const size_t src = ((size_t)tok[i] * L + i) * QN_D + c * 8;
-                h = __ldg(reinterpret_cast<const uint4 *>(net.Qh + src));
-                l = __ldg(reinterpret_cast<const uint4 *>(net.Ql + src));
-            }
+            const int ii = i < L ? i : 0;
+            const size_t src = ((size_t)tok[ii] * L + ii) * QN_D + c * 8;
             const uint32_t off = (uint32_t)(i >> 7) * AT_TILE_Q + sw128(i & 127, c);
-            *reinterpret_cast<uint4 *>(sm + OFF_QH + off) = h;
-            *reinterpret_cast<uint4 *>(sm + OFF_QL + off) = l;
+            const uint32_t nbytes = i < L ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QH + off)),
+                         "l"(net.Qh + src), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + off)),
+                         "l"(net.Ql + src), "r"(nbytes) : "memory");
         }
         for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {                    // K' rows of the valid keys
             const int k = idx >> 3, c = idx & 7;
-            uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
-            if (k < nk) {
-                const int j = kj[k];
-                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
-                h = __ldg(reinterpret_cast<const uint4 *>(net.Kh + src));
-                l = __ldg(reinterpret_cast<const uint4 *>(net.Kl + src));
-            }
-            *reinterpret_cast<uint4 *>(sm + OFF_KH + sw128(k, c)) = h;
-            *reinterpret_cast<uint4 *>(sm + OFF_KL + sw128(k, c)) = l;
+            const int j = kj[k < nk ? k : 0];
+            const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
+            const uint32_t nbytes = k < nk ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KH + sw128(k, c))),
+                         "l"(net.Kh + src), "r"(nbytes) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KL + sw128(k, c))),
+                         "l"(net.Kl + src), "r"(nbytes) : "memory");
         }
-        for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {                    // V^T: [channel][key]
-            const int k = idx % nk16, c8 = idx / nk16;                                      // consecutive threads: consecutive keys
-            uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
-            if (k < nk) {
-                const int j = kj[k];
-                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c8 * 8;
-                h = __ldg(reinterpret_cast<const uint4 *>(net.VFh + src));
-                l = __ldg(reinterpret_cast<const uint4 *>(net.VFl + src));
-            }
-            const __half *hh = reinterpret_cast<const __half *>(&h), *ll = reinterpret_cast<const __half *>(&l);
-            const int atom = k >> 6, kk = k & 63;
+        // V^T: [channel][key]. One task = 8 keys x 8 channels of one table: eight 16-byte loads (one per key),
+        // an 8x8 transpose in registers, eight 16-byte stores (one per channel row).
+        for (int task = threadIdx.x; task < (nk16 >> 3) * 8 * 2; task += blockDim.x) {
+            const int lo_tab = task & 1, kg = (task >> 1) % (nk16 >> 3), c8 = (task >> 1) / (nk16 >> 3);
+            const __half *tab = lo_tab ? net.VFl : net.VFh;
+            uint32_t in[8][4];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int ch = c8 * 8 + e;
-                const uint32_t off = (uint32_t)atom * AT_ATOM_V + sw128(ch, kk >> 3) + (kk & 7) * 2;
-                *reinterpret_cast<__half *>(sm + OFF_VH + off) = hh[e];
-                *reinterpret_cast<__half *>(sm + OFF_VL + off) = ll[e];
+                const int k = kg * 8 + e;
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (k < nk) {
+                    const int j = kj[k];
+                    x = __ldg(reinterpret_cast<const uint4 *>(tab + ((size_t)tok[j] * L + j) * QN_D + c8 * 8));
+                }
+                in[e][0] = x.x; in[e][1] = x.y; in[e][2] = x.z; in[e][3] = x.w;
+            }
+            const int atom = kg >> 3, chunk = kg & 7;     // 8 keys = one 16-byte chunk of the [ch][64 keys] atom
+            uint8_t *base = sm + (lo_tab ? OFF_VL : OFF_VH) + atom * AT_ATOM_V;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {                 // channel pair (2w, 2w+1) of this 8-channel group
+                uint32_t even[4], odd[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {             // keys 2e, 2e+1
+                    even[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x5410);      // low halves  -> channel 2w
+                    odd[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x7632);       // high halves -> channel 2w+1
+                }
+                const int ch = c8 * 8 + 2 * w;
+                *reinterpret_cast<uint4 *>(base + sw128(ch, chunk)) = make_uint4(even[0], even[1], even[2], even[3]);
+                *reinterpret_cast<uint4 *>(base + sw128(ch + 1, chunk)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
@@ -232,14 +250,14 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             const float sc = net.s_inv_scale;
             mbar_wait(b_sfull + 8 * t, ph_s);
             tc_fence_after();
-            // pass 1: row maximum over the valid keys
+            // pass 1: row maximum over the valid keys (64 columns per tensor-memory load)
             float mx = -INFINITY;
-            for (int c0 = 0; c0 < nk16; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(lane_addr + COL_S + t * AT_MAXK + c0, v);
+            for (int c0 = 0; c0 < nk16; c0 += 64) {
+                uint32_t v[64];
+                tmem_ld64(lane_addr + COL_S + t * AT_MAXK + c0, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int u = 0; u < 16; ++u)
+                for (int u = 0; u < 64; ++u)
                     if (c0 + u < nk) mx = fmaxf(mx, __uint_as_float(v[u]));
             }
             if (all_masked) mx = 0.f;
@@ -252,34 +270,30 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     my_pfree ^= 1;
                 }
                 const int kend = min(64, nk16 - 64 * sl);
-                for (int c0 = 0; c0 < kend; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(lane_addr + COL_S + t * AT_MAXK + 64 * sl + c0, v);
-                    tmem_ld_wait();
-                    float p[16];
+                uint32_t v[64];                           // columns beyond nk16 hold stale accumulator data: masked below
+                tmem_ld64(lane_addr + COL_S + t * AT_MAXK + 64 * sl, v);
+                tmem_ld_wait();
+                uint8_t *ph = sm + OFF_PH + t * AT_TILE_Q, *pl = sm + OFF_PL + t * AT_TILE_Q;
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        const int key = 64 * sl + c0 + u;
-                        float x = all_masked ? 1.f : fast_ex2(fmaf(__uint_as_float(v[u]), sc, -mxs));
-                        if (key >= nk) x = 0.f;
-                        p[u] = x;
-                        lsum += x;
-                    }
-                    uint32_t hi[8], lo[8];
+                for (int c = 0; c < 8; ++c) {             // one 16-byte chunk = 8 keys
+                    if (8 * c >= kend) break;
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const __half2 h = __floats2half2_rn(p[2 * u], p[2 * u + 1]);
+                    for (int u = 0; u < 4; ++u) {
+                        const int key = 64 * sl + 8 * c + 2 * u;
+                        float x0 = all_masked ? 1.f : fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u]), sc, -mxs));
+                        float x1 = all_masked ? 1.f : fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u + 1]), sc, -mxs));
+                        if (key >= nk) x0 = 0.f;
+                        if (key + 1 >= nk) x1 = 0.f;
+                        lsum += x0 + x1;
+                        const __half2 h = __floats2half2_rn(x0, x1);
                         const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn(p[2 * u] - hf.x, p[2 * u + 1] - hf.y);
+                        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
                         hi[u] = *reinterpret_cast<const uint32_t *>(&h);
                         lo[u] = *reinterpret_cast<const uint32_t *>(&l);
                     }
-                    const int c = c0 >> 3;                // two 16-byte chunks (8 keys each) per 16 columns
-                    uint8_t *ph = sm + OFF_PH + t * AT_TILE_Q, *pl = sm + OFF_PL + t * AT_TILE_Q;
                     *reinterpret_cast<uint4 *>(ph + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(ph + sw128(r, c + 1)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                     *reinterpret_cast<uint4 *>(pl + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4 *>(pl + sw128(r, c + 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
                 fence_async_smem();
                 tc_fence_before();
@@ -289,13 +303,12 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             mbar_wait(b_ofull + 8 * t, ph_o);
             tc_fence_after();
             float y[QN_D];
-#pragma unroll
-            for (int c0 = 0; c0 < QN_D; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(lane_addr + COL_O + t * QN_D + c0, v);
+            {
+                uint32_t v[64];
+                tmem_ld64(lane_addr + COL_O + t * QN_D, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int u = 0; u < 16; ++u) y[c0 + u] = __uint_as_float(v[u]);
+                for (int u = 0; u < QN_D; ++u) y[u] = __uint_as_float(v[u]);
             }
             tc_fence_before();
             if (i < L) {

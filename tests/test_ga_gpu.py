@@ -337,6 +337,24 @@ def test_qnet_tensor_core_l1_against_fp32_tiles(gpu, weight_files, monkeypatch):
         assert np.array_equal(q_big[:len(states)], net.forward(states, max_value)[0])
 
 
+@pytest.mark.parametrize("variant", ["tc", "mma", "simt"])
+def test_qnet_encoder_variants_agree(gpu, weight_files, monkeypatch, variant):
+    """The alternative encoders (attention on tcgen05; table logits + mma.sync; table logits + fp32 tiles) give
+    the default flash-attention style kernel's Q-values to fp32 rounding and the same greedy actions."""
+    from DPAMSA.dqn import QNet
+    z = np.load(os.path.join(GOLDEN, "qnet_vectors.npz"))
+    for (rows, cols), (name, sd) in weight_files.items():
+        states = z["states_%dx%d" % (rows, cols)].astype(np.uint8)
+        max_value = cols * rows * (rows - 1) / 2 * 4
+        net = QNet(sd, rows, cols)
+        monkeypatch.delenv("GAD_QNET_ENCODER", raising=False)
+        q0, a0 = net.forward(states, max_value)
+        monkeypatch.setenv("GAD_QNET_ENCODER", variant)
+        q1, a1 = net.forward(states, max_value)
+        assert np.all(np.abs(q1 - q0) <= 3e-5 * np.abs(q0) + 2e-6 * max_value), np.abs(q1 - q0).max()
+        assert np.array_equal(a1, a0)
+
+
 def test_dqn_and_environment_facade(gpu, weight_files, primitives):
     from DPAMSA.dqn import DQN
     from DPAMSA.env import Environment
