@@ -1,29 +1,24 @@
 // The encoder's attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
 // Same mathematics as encode_fa_kernel (qnet.cu) - S = Q'K'^T from split fp16 row tables, softmax in the
 // log2 domain, O = P V with the output projection folded into V, residual, LayerNorm - but both products run
-// as tcgen05.mma with the accumulators in tensor memory:
+// as tcgen05.mma with the accumulators in tensor memory.
 //
-//   one CTA per state (persistent), 1 CTA per SM, 288 threads:
-//     warps 0-3   own the 128 query rows of tile 0 (thread = row = TMEM lane), warps 4-7 those of tile 1
-//     warp 8      lane 0 issues every tcgen05.mma; the warp also allocates / frees the 512 TMEM columns
-//   shared memory (K-major, 128-byte swizzled operand tiles, written by the threads themselves):
-//     Q'  hi|lo  2 tiles x [128 rows][64]      64 KB      A operand of S
-//     K'  hi|lo  [<=192 keys][64]              48 KB      B operand of S (N = keys)
-//     V^T hi|lo  3 atoms x [64 ch][64 keys]    48 KB      B operand of O (N = 64 channels, K = keys)
-//     P   hi|lo  per tile [128 rows][64 keys]  64 KB      A operand of O, one 64-key slice at a time
-//   tensor memory: S of tile 0 / 1 at columns 0 / 192 (fp32, up to 192 keys), O of tile 0 / 1 at 384 / 448.
+//   work item = (state, tile of 128 query rows); persistent CTAs of 160 threads, two CTAs per SM so that one
+//   CTA's staging and softmax overlap the other's MMAs:
+//     warps 0-3   thread = query row = TMEM lane: softmax, LayerNorm, all staging
+//     warp 4      lane 0 issues every tcgen05.mma; the warp allocates / frees 256 TMEM columns
+//   shared memory: two buffers of K-major, 128-byte swizzled operand tiles, each used twice per item
+//     QP  hi|lo  [128 rows][64]      32 KB   Q' (A operand of S), then - once S is complete - the P slices
+//     KV  hi|lo  [<=192][64]         48 KB   K' (B operand of S), then V^T as 3 atoms [64 ch][64 keys] (B of O)
+//   tensor memory: S at columns 0..191 (fp32, one column per key), O at 192..255.
 //
-//   MMA warp : S(t0), S(t1)  ->  per 64-key slice: wait P(t) -> 12 MMAs O(t) += P V -> commit (frees P(t))
-//   row thread: wait S -> row max (tcgen05.ld) -> per slice: p = ex2(s - max), hi/lo fp16 into the swizzled
-//               P tile, fence.proxy.async, arrive -> ... -> wait O -> /sum, residual, LayerNorm, (hi|lo) store
-// Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi), so the result is fp32-class like the other
-// encoders; a row's softmax and LayerNorm need no cross-thread reduction at all.
-//
-// Status (round 1): correct (parity tests pass with GAD_QNET_ENCODER=tc) but ~15 % slower than encode_fa_kernel at
-// 6x30 (2.0 ms vs 1.7 ms for 16 384 states): with 224 KB of operand tiles only one CTA fits an SM and the phases
-// of a state (staging -> S -> softmax -> P V -> epilogue) run back to back, so the tensor pipe is 10 % busy.
-// It is therefore opt-in; overlapping consecutive states (double-buffered K/V tiles need the Q tiles out of
-// shared memory, e.g. as a TMEM A operand) is the next step.
+//   item: cp.async Q', K' -> S = 12 MMAs (N = keys) -> commit
+//         row threads: wait S; transpose V rows into KV; row max from TMEM; per 64-key slice:
+//                      p = ex2(s - max) as hi|lo fp16 into QP, fence.proxy.async, arrive
+//         MMA thread : per slice: wait P -> 12 MMAs O += P V (N = 64) -> commit (frees QP / completes O)
+//         row threads: wait O; /sum, residual, LayerNorm over the row's 64 channels, (hi|lo) store
+// Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi): fp32-class like the other encoders; a row's
+// softmax and LayerNorm need no cross-thread reduction at all.
 #include "qnet.cuh"
 #include "tc_ptx.cuh"
 
@@ -35,23 +30,19 @@ using namespace tcptx;
 namespace {
 
 constexpr int AT_ROWS = 128;                 // query rows per tile = UMMA M
-constexpr int AT_MAXK = 192;                 // keys (and query rows / 128 * 128 <= 256)
-constexpr int AT_THREADS = 288;
+constexpr int AT_MAXK = 192;                 // keys
+constexpr int AT_THREADS = 160;
 constexpr int AT_TILE_Q = AT_ROWS * 128;     // bytes of one [128][64] fp16 tile
 constexpr int AT_TILE_K = AT_MAXK * 128;
 constexpr int AT_ATOM_V = 64 * 128;          // [64 ch][64 keys]
-constexpr int OFF_QH = 0;                                    // 2 tiles
-constexpr int OFF_QL = OFF_QH + 2 * AT_TILE_Q;
-constexpr int OFF_KH = OFF_QL + 2 * AT_TILE_Q;
+constexpr int OFF_QH = 0;                    // Q' hi, later P hi
+constexpr int OFF_QL = OFF_QH + AT_TILE_Q;
+constexpr int OFF_KH = OFF_QL + AT_TILE_Q;   // K' hi, later V^T hi (3 atoms)
 constexpr int OFF_KL = OFF_KH + AT_TILE_K;
-constexpr int OFF_VH = OFF_KL + AT_TILE_K;                   // 3 atoms
-constexpr int OFF_VL = OFF_VH + 3 * AT_ATOM_V;
-constexpr int OFF_PH = OFF_VL + 3 * AT_ATOM_V;               // 2 tiles
-constexpr int OFF_PL = OFF_PH + 2 * AT_TILE_Q;
-constexpr int OFF_BAR = OFF_PL + 2 * AT_TILE_Q;              // 229 376
-constexpr int AT_SMEM = OFF_BAR + 128 + 1024;                // + barriers + alignment slack
-constexpr int COL_S = 0, COL_O = 384;
-constexpr int TMEM_COLS = 512;
+constexpr int OFF_BAR = OFF_KL + AT_TILE_K;  // 81 920
+constexpr int AT_SMEM = OFF_BAR + 128 + 1024;
+constexpr int COL_S = 0, COL_O = 192;
+constexpr int TMEM_COLS = 256;
 
 // byte offset of the 16-byte chunk c of row r inside a K-major tile with 128-byte rows and 128B swizzle
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
@@ -63,7 +54,7 @@ __device__ __forceinline__ float fast_ex2(float x)
     return y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
                  const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
                  __half *__restrict__ Z2out)
@@ -71,28 +62,32 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
-    // bars: s_full[2], p_ready[2], p_free[2], o_full[2], then the TMEM base address
-    const uint32_t b_sfull = smem_u32(bars), b_pready = b_sfull + 16, b_pfree = b_pready + 16, b_ofull = b_pfree + 16;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    // bars: s_full, p_ready, p_free, o_full, then the TMEM base address
+    const uint32_t b_sfull = smem_u32(bars), b_pready = b_sfull + 8, b_pfree = b_pready + 8, b_ofull = b_pfree + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
     __shared__ int kj[AT_MAXK];
     __shared__ uint8_t tok[AT_MAXK + 64];
     __shared__ int s_nk;
+    __shared__ float ln_g[QN_D], ln_b[QN_D];
 
     const int L = net.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (L + AT_ROWS - 1) / AT_ROWS;
     const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
+    const long long n_items = n_rows * n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(b_sfull + 8 * t, 1);
-            mbar_init(b_pready + 8 * t, AT_ROWS);
-            mbar_init(b_pfree + 8 * t, 1);
-            mbar_init(b_ofull + 8 * t, 1);
-        }
+        mbar_init(b_sfull, 1);
+        mbar_init(b_pready, AT_ROWS);
+        mbar_init(b_pfree, 1);
+        mbar_init(b_ofull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (threadIdx.x < QN_D) {
+        ln_g[threadIdx.x] = net.ln2_g[threadIdx.x];
+        ln_b[threadIdx.x] = net.ln2_b[threadIdx.x];
+    }
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -102,12 +97,13 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // phase bits of the per-state barriers (every barrier completes the same number of times per state for
-    // all of its waiters, so each thread tracks the parity itself)
-    uint32_t ph_s = 0, ph_o = 0, ph_pready[2] = {0, 0}, ph_pfree = 0;
+    // phase bits: s_full and o_full complete once per item, p_ready n_slices times, p_free n_slices - 1 times
+    uint32_t ph_s = 0, ph_o = 0, ph_pready = 0, ph_pfree = 0;
 
-    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        __syncthreads();                                  // previous state fully consumed (its epilogue is done)
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const long long row = item / n_tiles;
+        const int t = (int)(item - row * n_tiles);
+        __syncthreads();                                  // previous item fully consumed (its epilogue is done)
         if (tok_in) {
             for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
             __syncthreads();
@@ -138,21 +134,20 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         const int nk16 = (nk + 15) & ~15;
         const int n_slices = (nk16 + 63) >> 6;
 
-        // ---- staging. Q' and K' rows are straight 16-byte chunk copies into swizzled positions: cp.async
-        // (no registers, all copies of a thread in flight at once); rows outside the state are zero-filled
-        // through the src-size operand. The V^T transposes below run while these copies are in flight.
-        for (int idx = threadIdx.x; idx < n_tiles * AT_ROWS * 8; idx += blockDim.x) {      // Q' rows (all query positions)
-            const int i = idx >> 3, c = idx & 7;
+        // ---- stage Q' (this tile's rows) and K' (the valid keys): cp.async 16-byte chunks into swizzled positions,
+        // rows outside the state zero-filled through the src-size operand
+        for (int idx = threadIdx.x; idx < AT_ROWS * 8; idx += blockDim.x) {
+            const int r = idx >> 3, c = idx & 7;
+            const int i = t * AT_ROWS + r;
             const int ii = i < L ? i : 0;
             const size_t src = ((size_t)tok[ii] * L + ii) * QN_D + c * 8;
-            const uint32_t off = (uint32_t)(i >> 7) * AT_TILE_Q + sw128(i & 127, c);
             const uint32_t nbytes = i < L ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QH + off)),
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QH + sw128(r, c))),
                          "l"(net.Qh + src), "r"(nbytes) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + off)),
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + sw128(r, c))),
                          "l"(net.Ql + src), "r"(nbytes) : "memory");
         }
-        for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {                    // K' rows of the valid keys
+        for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {
             const int k = idx >> 3, c = idx & 7;
             const int j = kj[k < nk ? k : 0];
             const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
@@ -162,99 +157,87 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KL + sw128(k, c))),
                          "l"(net.Kl + src), "r"(nbytes) : "memory");
         }
-        // V^T: [channel][key]. One task = 8 keys x 8 channels of one table: eight 16-byte loads (one per key),
-        // an 8x8 transpose in registers, eight 16-byte stores (one per channel row).
-        for (int task = threadIdx.x; task < (nk16 >> 3) * 8 * 2; task += blockDim.x) {
-            const int lo_tab = task & 1, kg = (task >> 1) % (nk16 >> 3), c8 = (task >> 1) / (nk16 >> 3);
-            const __half *tab = lo_tab ? net.VFl : net.VFh;
-            uint32_t in[8][4];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = kg * 8 + e;
-                uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                if (k < nk) {
-                    const int j = kj[k];
-                    x = __ldg(reinterpret_cast<const uint4 *>(tab + ((size_t)tok[j] * L + j) * QN_D + c8 * 8));
-                }
-                in[e][0] = x.x; in[e][1] = x.y; in[e][2] = x.z; in[e][3] = x.w;
-            }
-            const int atom = kg >> 3, chunk = kg & 7;     // 8 keys = one 16-byte chunk of the [ch][64 keys] atom
-            uint8_t *base = sm + (lo_tab ? OFF_VL : OFF_VH) + atom * AT_ATOM_V;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {                 // channel pair (2w, 2w+1) of this 8-channel group
-                uint32_t even[4], odd[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {             // keys 2e, 2e+1
-                    even[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x5410);      // low halves  -> channel 2w
-                    odd[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x7632);       // high halves -> channel 2w+1
-                }
-                const int ch = c8 * 8 + 2 * w;
-                *reinterpret_cast<uint4 *>(base + sw128(ch, chunk)) = make_uint4(even[0], even[1], even[2], even[3]);
-                *reinterpret_cast<uint4 *>(base + sw128(ch + 1, chunk)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
-            }
-        }
         asm volatile("cp.async.wait_all;" ::: "memory");
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        if (warp == 8) {
+        if (warp == 4) {
             // ======================= MMA issuer =======================
             if (lane == 0) {
                 tc_fence_after();
                 const uint32_t idesc_s = make_idesc_f16(AT_ROWS, nk16);
                 const uint32_t idesc_o = make_idesc_f16(AT_ROWS, QN_D);
                 const uint64_t dkh = make_smem_desc(smem_u32(sm + OFF_KH)), dkl = make_smem_desc(smem_u32(sm + OFF_KL));
-                for (int t = 0; t < n_tiles; ++t) {       // S(t) = Q'(t) K'^T : 4 k-steps x (lo.hi, hi.lo, hi.hi)
-                    const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH + t * AT_TILE_Q));
-                    const uint64_t dql = make_smem_desc(smem_u32(sm + OFF_QL + t * AT_TILE_Q));
-                    const uint32_t d = tmem_base + COL_S + t * AT_MAXK;
+                const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH)), dql = make_smem_desc(smem_u32(sm + OFF_QL));
+                const uint32_t ds = tmem_base + COL_S, dout = tmem_base + COL_O;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        umma_f16(d, dql + 2 * ks, dkh + 2 * ks, idesc_s, ks != 0);
-                        umma_f16(d, dqh + 2 * ks, dkl + 2 * ks, idesc_s, 1u);
-                        umma_f16(d, dqh + 2 * ks, dkh + 2 * ks, idesc_s, 1u);
-                    }
-                    umma_commit(b_sfull + 8 * t);
+                for (int ks = 0; ks < 4; ++ks) {          // S = Q' K'^T : 4 k-steps x (lo.hi, hi.lo, hi.hi)
+                    umma_f16(ds, dql + 2 * ks, dkh + 2 * ks, idesc_s, ks != 0);
+                    umma_f16(ds, dqh + 2 * ks, dkl + 2 * ks, idesc_s, 1u);
+                    umma_f16(ds, dqh + 2 * ks, dkh + 2 * ks, idesc_s, 1u);
                 }
-                uint32_t php[2] = {ph_pready[0], ph_pready[1]};
-                for (int sl = 0; sl < n_slices; ++sl) {
+                umma_commit(b_sfull);
+                uint32_t php = ph_pready;
+                for (int sl = 0; sl < n_slices; ++sl) {   // O += P(slice) V(slice); P lives where Q' was, V^T where K' was
                     const int ksteps = min(4, (nk16 - 64 * sl) >> 4);
-                    for (int t = 0; t < n_tiles; ++t) {   // O(t) += P(t, slice) V(slice)
-                        mbar_wait(b_pready + 8 * t, php[t]);
-                        php[t] ^= 1;
-                        tc_fence_after();
-                        const uint64_t dph = make_smem_desc(smem_u32(sm + OFF_PH + t * AT_TILE_Q));
-                        const uint64_t dpl = make_smem_desc(smem_u32(sm + OFF_PL + t * AT_TILE_Q));
-                        const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_VH + sl * AT_ATOM_V));
-                        const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_VL + sl * AT_ATOM_V));
-                        const uint32_t d = tmem_base + COL_O + t * QN_D;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            umma_f16(d, dpl + 2 * ks, dvh + 2 * ks, idesc_o, (sl | ks) != 0);
-                            umma_f16(d, dph + 2 * ks, dvl + 2 * ks, idesc_o, 1u);
-                            umma_f16(d, dph + 2 * ks, dvh + 2 * ks, idesc_o, 1u);
-                        }
-                        if (sl + 1 < n_slices) umma_commit(b_pfree + 8 * t);      // the P tile may be overwritten
-                        else umma_commit(b_ofull + 8 * t);                         // O(t) complete
+                    mbar_wait(b_pready, php);
+                    php ^= 1;
+                    tc_fence_after();
+                    const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_KH + sl * AT_ATOM_V));
+                    const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_KL + sl * AT_ATOM_V));
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        umma_f16(dout, dql + 2 * ks, dvh + 2 * ks, idesc_o, (sl | ks) != 0);
+                        umma_f16(dout, dqh + 2 * ks, dvl + 2 * ks, idesc_o, 1u);
+                        umma_f16(dout, dqh + 2 * ks, dvh + 2 * ks, idesc_o, 1u);
                     }
+                    if (sl + 1 < n_slices) umma_commit(b_pfree);       // the P tile may be overwritten
+                    else umma_commit(b_ofull);                          // O complete
                 }
             }
-            // keep the warp's phase bookkeeping in step with the row threads
-            for (int t = 0; t < n_tiles; ++t)
-                if (n_slices & 1) ph_pready[t] ^= 1;
-        } else if (warp < 4 * n_tiles) {
+        } else {
             // ======================= row threads: thread = query row =======================
-            const int t = warp >> 2;
-            const int r = (warp & 3) * 32 + lane;         // row inside the tile = TMEM lane
+            const int r = warp * 32 + lane;               // row inside the tile = TMEM lane
             const int i = t * AT_ROWS + r;                // query position
-            const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
             const float sc = net.s_inv_scale;
-            mbar_wait(b_sfull + 8 * t, ph_s);
+            mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
             tc_fence_after();
+            // V^T into the K buffer: one task = 8 keys x 8 channels of one table - eight 16-byte loads (one per key),
+            // an 8x8 transpose in registers, eight 16-byte stores (one per channel row)
+            for (int task = threadIdx.x; task < (nk16 >> 3) * 8 * 2; task += AT_ROWS) {
+                const int lo_tab = task & 1, kg = (task >> 1) % (nk16 >> 3), c8 = (task >> 1) / (nk16 >> 3);
+                const __half *tab = lo_tab ? net.VFl : net.VFh;
+                uint32_t in[8][4];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k = kg * 8 + e;
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (k < nk) {
+                        const int j = kj[k];
+                        x = __ldg(reinterpret_cast<const uint4 *>(tab + ((size_t)tok[j] * L + j) * QN_D + c8 * 8));
+                    }
+                    in[e][0] = x.x; in[e][1] = x.y; in[e][2] = x.z; in[e][3] = x.w;
+                }
+                const int atom = kg >> 3, chunk = kg & 7; // 8 keys = one 16-byte chunk of the [ch][64 keys] atom
+                uint8_t *base = sm + (lo_tab ? OFF_KL : OFF_KH) + atom * AT_ATOM_V;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {             // channel pair (2w, 2w+1) of this 8-channel group
+                    uint32_t even[4], odd[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {         // keys 2e, 2e+1
+                        even[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x5410);      // low halves  -> channel 2w
+                        odd[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x7632);       // high halves -> channel 2w+1
+                    }
+                    const int ch = c8 * 8 + 2 * w;
+                    *reinterpret_cast<uint4 *>(base + sw128(ch, chunk)) = make_uint4(even[0], even[1], even[2], even[3]);
+                    *reinterpret_cast<uint4 *>(base + sw128(ch + 1, chunk)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
+                }
+            }
             // pass 1: row maximum over the valid keys (64 columns per tensor-memory load)
             float mx = -INFINITY;
             for (int c0 = 0; c0 < nk16; c0 += 64) {
                 uint32_t v[64];
-                tmem_ld64(lane_addr + COL_S + t * AT_MAXK + c0, v);
+                tmem_ld64(lane_addr + COL_S + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int u = 0; u < 64; ++u)
@@ -263,17 +246,15 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             if (all_masked) mx = 0.f;
             const float mxs = mx * sc;
             float lsum = 0.f;
-            uint32_t my_pfree = ph_pfree;
             for (int sl = 0; sl < n_slices; ++sl) {
                 if (sl > 0) {                             // the previous slice's MMAs must have read the P tile
-                    mbar_wait(b_pfree + 8 * t, my_pfree);
-                    my_pfree ^= 1;
+                    mbar_wait(b_pfree, ph_pfree);
+                    ph_pfree ^= 1;
                 }
                 const int kend = min(64, nk16 - 64 * sl);
                 uint32_t v[64];                           // columns beyond nk16 hold stale accumulator data: masked below
-                tmem_ld64(lane_addr + COL_S + t * AT_MAXK + 64 * sl, v);
+                tmem_ld64(lane_addr + COL_S + 64 * sl, v);
                 tmem_ld_wait();
-                uint8_t *ph = sm + OFF_PH + t * AT_TILE_Q, *pl = sm + OFF_PL + t * AT_TILE_Q;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {             // one 16-byte chunk = 8 keys
                     if (8 * c >= kend) break;
@@ -292,20 +273,20 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                         hi[u] = *reinterpret_cast<const uint32_t *>(&h);
                         lo[u] = *reinterpret_cast<const uint32_t *>(&l);
                     }
-                    *reinterpret_cast<uint4 *>(ph + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(pl + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
-                fence_async_smem();
+                fence_async_smem();                       // also publishes this thread's share of V^T before the first arrive
                 tc_fence_before();
-                mbar_arrive(b_pready + 8 * t);
+                mbar_arrive(b_pready);
             }
             // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the 64 channels of this thread's row
-            mbar_wait(b_ofull + 8 * t, ph_o);
+            mbar_wait(b_ofull, ph_o);
             tc_fence_after();
             float y[QN_D];
             {
                 uint32_t v[64];
-                tmem_ld64(lane_addr + COL_O + t * QN_D, v);
+                tmem_ld64(lane_addr + COL_O, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int u = 0; u < QN_D; ++u) y[u] = __uint_as_float(v[u]);
@@ -339,8 +320,8 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float z0 = y[c + 2 * u] * rstd * net.ln2_g[c + 2 * u] + net.ln2_b[c + 2 * u];
-                            const float z1 = y[c + 2 * u + 1] * rstd * net.ln2_g[c + 2 * u + 1] + net.ln2_b[c + 2 * u + 1];
+                            const float z0 = y[c + 2 * u] * rstd * ln_g[c + 2 * u] + ln_b[c + 2 * u];
+                            const float z1 = y[c + 2 * u + 1] * rstd * ln_g[c + 2 * u + 1] + ln_b[c + 2 * u + 1];
                             const __half2 h = __floats2half2_rn(z0, z1);
                             const float2 hf = __half22float2(h);
                             const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
@@ -353,20 +334,18 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 } else {
                     float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D;
 #pragma unroll
-                    for (int c = 0; c < QN_D; ++c) z[c] = y[c] * rstd * net.ln2_g[c] + net.ln2_b[c];
+                    for (int c = 0; c < QN_D; ++c) z[c] = y[c] * rstd * ln_g[c] + ln_b[c];
                 }
             }
-            ph_pfree = my_pfree;
         }
-        // per-state phase flips (identical for every thread that used the barrier)
+        // per-item phase flips for the barriers a thread did not wait on itself
         ph_s ^= 1;
         ph_o ^= 1;
-        if (warp != 8 && (n_slices & 1))
-            for (int t = 0; t < 2; ++t) ph_pready[t] ^= 1;
-        if (warp >= 4 * n_tiles && warp != 8 && ((n_slices - 1) & 1)) ph_pfree ^= 1;      // idle row warps keep the parity
+        if (n_slices & 1) ph_pready ^= 1;
+        if (warp == 4 && ((n_slices - 1) & 1)) ph_pfree ^= 1;
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 4) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
@@ -383,7 +362,8 @@ int launch_encode_tc(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, 
         GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         attr_set = true;
     }
-    const long long grid = n_max < GAD_NUM_SMS ? n_max : GAD_NUM_SMS;
+    const long long items = n_max * ((q->L + AT_ROWS - 1) / AT_ROWS);
+    const long long grid = items < 2ll * GAD_NUM_SMS ? items : 2ll * GAD_NUM_SMS;
     encode_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
