@@ -3,22 +3,29 @@
 // log2 domain, O = P V with the output projection folded into V, residual, LayerNorm - but both products run
 // as tcgen05.mma with the accumulators in tensor memory.
 //
-//   work item = (state, tile of 128 query rows); persistent CTAs of 160 threads, two CTAs per SM so that one
-//   CTA's staging and softmax overlap the other's MMAs:
-//     warps 0-3   thread = query row = TMEM lane: softmax, LayerNorm, all staging
-//     warp 4      lane 0 issues every tcgen05.mma; the warp allocates / frees 256 TMEM columns
+//   work item = (state, tile of TR query rows), TR = 96 or 128 chosen so that the tiles of a state are even
+//   (L = 180 -> two tiles of 96); persistent CTAs of TR + 32 threads, two CTAs per SM so that one CTA's
+//   staging and softmax overlap the other's MMAs:
+//     warps 0..TR/32-1   thread = query row = TMEM lane: softmax, LayerNorm, operand staging
+//     last warp          lane 0 issues every tcgen05.mma; while the row warps work on item n the whole warp
+//                        builds the tokens and the key list of item n+1 (double-buffered); it also owns the
+//                        256 TMEM columns
 //   shared memory: two buffers of K-major, 128-byte swizzled operand tiles, each used twice per item
 //     QP  hi|lo  [128 rows][64]      32 KB   Q' (A operand of S), then - once S is complete - the P slices
 //     KV  hi|lo  [<=192][64]         48 KB   K' (B operand of S), then V^T as 3 atoms [64 ch][64 keys] (B of O)
 //   tensor memory: S at columns 0..191 (fp32, one column per key), O at 192..255.
 //
 //   item: cp.async Q', K' -> S = 12 MMAs (N = keys) -> commit
-//         row threads: wait S; transpose V rows into KV; row max from TMEM; per 64-key slice:
-//                      p = ex2(s - max) as hi|lo fp16 into QP, fence.proxy.async, arrive
+//         row threads: (V rows of the first transpose task already in flight) wait S; transpose V rows into
+//                      KV; row max from TMEM; per 64-key slice: p = ex2(s - max) as hi|lo fp16 into QP,
+//                      fence.proxy.async, arrive
 //         MMA thread : per slice: wait P -> 12 MMAs O += P V (N = 64) -> commit (frees QP / completes O)
-//         row threads: wait O; /sum, residual, LayerNorm over the row's 64 channels, (hi|lo) store
+//         row threads: residual row loaded, wait O; /sum, residual, LayerNorm over the row's 64 channels,
+//                      (hi|lo) store
 // Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi): fp32-class like the other encoders; a row's
 // softmax and LayerNorm need no cross-thread reduction at all.
+//
+// Status: opt-in (GAD_QNET_ENCODER=tc), parity-tested against the other encoders; see DESIGN.md for timings.
 #include "qnet.cuh"
 #include "tc_ptx.cuh"
 
@@ -29,10 +36,10 @@ using namespace tcptx;
 
 namespace {
 
-constexpr int AT_ROWS = 128;                 // query rows per tile = UMMA M
+constexpr int AT_M = 128;                    // UMMA M (rows of the accumulators; a tile uses the first TR of them)
 constexpr int AT_MAXK = 192;                 // keys
-constexpr int AT_THREADS = 160;
-constexpr int AT_TILE_Q = AT_ROWS * 128;     // bytes of one [128][64] fp16 tile
+constexpr int AT_MAX_THREADS = 160;
+constexpr int AT_TILE_Q = AT_M * 128;        // bytes of one [128][64] fp16 tile
 constexpr int AT_TILE_K = AT_MAXK * 128;
 constexpr int AT_ATOM_V = 64 * 128;          // [64 ch][64 keys]
 constexpr int OFF_QH = 0;                    // Q' hi, later P hi
@@ -54,10 +61,61 @@ __device__ __forceinline__ float fast_ex2(float x)
     return y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// One warp builds the tokens of a work item's state (env.py:147-153, same rule as build_tokens in qnet.cuh) and
+// the ordered list of its unmasked keys. *nk_out = 0 marks a fully masked state (kj is then the identity).
+__device__ __forceinline__ void warp_item_tokens(const gad_qnet &net, const uint8_t *__restrict__ tok_in,
+                                                 const int32_t *__restrict__ active, long long row, int L, int lane,
+                                                 uint8_t *tok, int *kj, int *nk_out)
+{
+    if (tok_in) {
+        for (int i = lane; i < L; i += 32) tok[i] = tok_in[row * L + i];
+    } else {
+        const int e = active[row];
+        const int rows = net.rows, cols = net.cols;
+        const uint8_t *sub = net.sub + (size_t)e * rows * cols;
+        const int h = lane < rows ? (int)net.heads[(size_t)e * rows + lane] : cols + 1;
+        const int len = cols - h + 1;                     // a row's remaining tokens + its gap code; 0 beyond the rows
+        int end = len;                                    // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, end, d);
+            if (lane >= d) end += v;
+        }
+        const int nvalid = __shfl_sync(0xFFFFFFFFu, end, 31);
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            int r = 0;
+            for (int q = 0; q < rows; ++q) r += i >= __shfl_sync(0xFFFFFFFFu, end, q);
+            r = min(r, rows - 1);
+            const int hr = __shfl_sync(0xFFFFFFFFu, h, r);
+            const int off = __shfl_sync(0xFFFFFFFFu, end - len, r);
+            uint8_t t = 0;
+            if (i < nvalid) {
+                const int k = i - off;
+                t = k < cols - hr ? sub[r * cols + hr + k] : (uint8_t)GAD_GAP;
+            }
+            if (i < L) tok[i] = t;
+        }
+    }
+    __syncwarp();
+    int base = 0;
+    for (int j0 = 0; j0 < L; j0 += 32) {
+        const int j = j0 + lane;
+        const bool v = j < L && tok[j] != 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, v);
+        if (v) kj[base + __popc(m & ((1u << lane) - 1u))] = j;
+        base += __popc(m);
+    }
+    if (base == 0)                                        // reference: softmax over all -1e9 is uniform over every key
+        for (int j = lane; j < L; j += 32) kj[j] = j;
+    if (lane == 0) *nk_out = base;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(AT_MAX_THREADS, 2)
 encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
-                 const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, float *__restrict__ Zout,
-                 __half *__restrict__ Z2out)
+                 const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, const int TR, const int n_tiles,
+                 float *__restrict__ Zout, __half *__restrict__ Z2out)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -65,20 +123,20 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     // bars: s_full, p_ready, p_free, o_full, then the TMEM base address
     const uint32_t b_sfull = smem_u32(bars), b_pready = b_sfull + 8, b_pfree = b_pready + 8, b_ofull = b_pfree + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
-    __shared__ int kj[AT_MAXK];
-    __shared__ uint8_t tok[AT_MAXK + 64];
-    __shared__ int s_nk;
+    __shared__ int kj_s[2][AT_MAXK];
+    __shared__ uint8_t tok_s[2][AT_MAXK + 64];
+    __shared__ int nk_s[2];
     __shared__ float ln_g[QN_D], ln_b[QN_D];
 
     const int L = net.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = (L + AT_ROWS - 1) / AT_ROWS;
+    const int mma_warp = TR >> 5;
     const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
     const long long n_items = n_rows * n_tiles;
 
     if (threadIdx.x == 0) {
         mbar_init(b_sfull, 1);
-        mbar_init(b_pready, AT_ROWS);
+        mbar_init(b_pready, TR);
         mbar_init(b_pfree, 1);
         mbar_init(b_ofull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -87,11 +145,19 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         ln_g[threadIdx.x] = net.ln2_g[threadIdx.x];
         ln_b[threadIdx.x] = net.ln2_b[threadIdx.x];
     }
-    if (warp == 4) {
+    // rows TR..127 of the A tiles are never staged: zero them once (their accumulator rows are never read)
+    for (int idx = threadIdx.x; idx < (AT_M - TR) * 8; idx += blockDim.x) {
+        *reinterpret_cast<uint4 *>(sm + OFF_QH + TR * 128 + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sm + OFF_QL + TR * 128 + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (warp == mma_warp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if ((long long)blockIdx.x < n_items)
+            warp_item_tokens(net, tok_in, active, blockIdx.x / n_tiles, L, lane, tok_s[0], kj_s[0], &nk_s[0]);
     }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -99,46 +165,24 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
 
     // phase bits: s_full and o_full complete once per item, p_ready n_slices times, p_free n_slices - 1 times
     uint32_t ph_s = 0, ph_o = 0, ph_pready = 0, ph_pfree = 0;
+    int buf = 0;
 
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
         const long long row = item / n_tiles;
         const int t = (int)(item - row * n_tiles);
-        __syncthreads();                                  // previous item fully consumed (its epilogue is done)
-        if (tok_in) {
-            for (int i = threadIdx.x; i < L; i += blockDim.x) tok[i] = tok_in[row * L + i];
-            __syncthreads();
-        } else {
-            const int e = active[row];
-            build_tokens(tok, net.sub + (size_t)e * net.rows * net.cols, net.heads + (size_t)e * net.rows, net.rows,
-                         net.cols, L);
-        }
-        if (warp == 0) {                                  // ordered list of unmasked keys
-            int base = 0;
-            for (int j0 = 0; j0 < L; j0 += 32) {
-                const int j = j0 + lane;
-                const bool v = j < L && tok[j] != 0;
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, v);
-                if (v) kj[base + __popc(m & ((1u << lane) - 1u))] = j;
-                base += __popc(m);
-            }
-            if (lane == 0) s_nk = base;
-        }
-        __syncthreads();
-        int nk = s_nk;
-        const bool all_masked = nk == 0;                  // reference: softmax over all -1e9 is uniform over every key
-        if (all_masked) {
-            for (int j = threadIdx.x; j < L; j += blockDim.x) kj[j] = j;
-            nk = L;
-            __syncthreads();
-        }
+        __syncthreads();                                  // previous item fully consumed; this item's tokens published
+        const uint8_t *tok = tok_s[buf];
+        const int *kj = kj_s[buf];
+        const bool all_masked = nk_s[buf] == 0;
+        const int nk = all_masked ? L : nk_s[buf];
         const int nk16 = (nk + 15) & ~15;
         const int n_slices = (nk16 + 63) >> 6;
 
         // ---- stage Q' (this tile's rows) and K' (the valid keys): cp.async 16-byte chunks into swizzled positions,
         // rows outside the state zero-filled through the src-size operand
-        for (int idx = threadIdx.x; idx < AT_ROWS * 8; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < TR * 8; idx += blockDim.x) {
             const int r = idx >> 3, c = idx & 7;
-            const int i = t * AT_ROWS + r;
+            const int i = t * TR + r;
             const int ii = i < L ? i : 0;
             const size_t src = ((size_t)tok[ii] * L + ii) * QN_D + c * 8;
             const uint32_t nbytes = i < L ? 16u : 0u;
@@ -161,15 +205,15 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        if (warp == 4) {
-            // ======================= MMA issuer =======================
+        if (warp == mma_warp) {
+            // ======================= MMA issuer + next item's tokens =======================
+            const uint32_t idesc_s = make_idesc_f16(AT_M, nk16);
+            const uint32_t idesc_o = make_idesc_f16(AT_M, QN_D);
+            const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH)), dql = make_smem_desc(smem_u32(sm + OFF_QL));
+            const uint32_t ds = tmem_base + COL_S, dout = tmem_base + COL_O;
             if (lane == 0) {
                 tc_fence_after();
-                const uint32_t idesc_s = make_idesc_f16(AT_ROWS, nk16);
-                const uint32_t idesc_o = make_idesc_f16(AT_ROWS, QN_D);
                 const uint64_t dkh = make_smem_desc(smem_u32(sm + OFF_KH)), dkl = make_smem_desc(smem_u32(sm + OFF_KL));
-                const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH)), dql = make_smem_desc(smem_u32(sm + OFF_QL));
-                const uint32_t ds = tmem_base + COL_S, dout = tmem_base + COL_O;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {          // S = Q' K'^T : 4 k-steps x (lo.hi, hi.lo, hi.hi)
                     umma_f16(ds, dql + 2 * ks, dkh + 2 * ks, idesc_s, ks != 0);
@@ -177,6 +221,13 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     umma_f16(ds, dqh + 2 * ks, dkh + 2 * ks, idesc_s, 1u);
                 }
                 umma_commit(b_sfull);
+            }
+            __syncwarp();
+            const long long next = item + gridDim.x;      // the row warps are busy for a while: prepare the next item
+            if (next < n_items)
+                warp_item_tokens(net, tok_in, active, next / n_tiles, L, lane, tok_s[buf ^ 1], kj_s[buf ^ 1],
+                                 &nk_s[buf ^ 1]);
+            if (lane == 0) {
                 uint32_t php = ph_pready;
                 for (int sl = 0; sl < n_slices; ++sl) {   // O += P(slice) V(slice); P lives where Q' was, V^T where K' was
                     const int ksteps = min(4, (nk16 - 64 * sl) >> 4);
@@ -197,17 +248,20 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         } else {
             // ======================= row threads: thread = query row =======================
             const int r = warp * 32 + lane;               // row inside the tile = TMEM lane
-            const int i = t * AT_ROWS + r;                // query position
+            const int i = t * TR + r;                     // query position
+            const bool warp_live = t * TR + warp * 32 < L;                 // warps past the state's last row only stage
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-            const float sc = net.s_inv_scale;
-            mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
-            tc_fence_after();
+            const float sc = all_masked ? 0.f : net.s_inv_scale;           // fully masked: every p = ex2(0) = 1
+
             // V^T into the K buffer: one task = 8 keys x 8 channels of one table - eight 16-byte loads (one per key),
-            // an 8x8 transpose in registers, eight 16-byte stores (one per channel row)
-            for (int task = threadIdx.x; task < (nk16 >> 3) * 8 * 2; task += AT_ROWS) {
-                const int lo_tab = task & 1, kg = (task >> 1) % (nk16 >> 3), c8 = (task >> 1) / (nk16 >> 3);
+            // an 8x8 transpose in registers, eight 16-byte stores (one per channel row). A task's loads are issued one
+            // task ahead; the first ones before S is waited for.
+            const int ng = nk16 >> 3;                     // groups of 8 keys
+            const int n_tasks = ng * 16;                  // x 8 channel groups x {hi, lo}
+            auto load_task = [&](int task, uint32_t (&in)[8][4]) {
+                const int lo_tab = task & 1, u = task >> 1;
+                const int c8 = u / ng, kg = u - c8 * ng;
                 const __half *tab = lo_tab ? net.VFl : net.VFh;
-                uint32_t in[8][4];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int k = kg * 8 + e;
@@ -218,6 +272,10 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     }
                     in[e][0] = x.x; in[e][1] = x.y; in[e][2] = x.z; in[e][3] = x.w;
                 }
+            };
+            auto store_task = [&](int task, const uint32_t (&in)[8][4]) {
+                const int lo_tab = task & 1, u = task >> 1;
+                const int c8 = u / ng, kg = u - c8 * ng;
                 const int atom = kg >> 3, chunk = kg & 7; // 8 keys = one 16-byte chunk of the [ch][64 keys] atom
                 uint8_t *base = sm + (lo_tab ? OFF_KL : OFF_KH) + atom * AT_ATOM_V;
 #pragma unroll
@@ -232,79 +290,108 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     *reinterpret_cast<uint4 *>(base + sw128(ch, chunk)) = make_uint4(even[0], even[1], even[2], even[3]);
                     *reinterpret_cast<uint4 *>(base + sw128(ch + 1, chunk)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
                 }
+            };
+            uint32_t va[8][4], vb[8][4];
+            int task = threadIdx.x;
+            if (task < n_tasks) load_task(task, va);
+            mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
+            tc_fence_after();
+            while (task < n_tasks) {                      // two tasks per trip, ping-pong register sets
+                if (task + TR < n_tasks) load_task(task + TR, vb);
+                store_task(task, va);
+                task += TR;
+                if (task >= n_tasks) break;
+                if (task + TR < n_tasks) load_task(task + TR, va);
+                store_task(task, vb);
+                task += TR;
             }
-            // pass 1: row maximum over the valid keys (64 columns per tensor-memory load)
-            float mx = -INFINITY;
-            for (int c0 = 0; c0 < nk16; c0 += 64) {
-                uint32_t v[64];
-                tmem_ld64(lane_addr + COL_S + c0, v);
-                tmem_ld_wait();
+
+            float mxs = 0.f, lsum = 0.f;
+            if (warp_live) {
+                // pass 1: row maximum over the valid keys (64 columns per tensor-memory load)
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < nk16; c0 += 64) {
+                    uint32_t v[64];
+                    tmem_ld64(lane_addr + COL_S + c0, v);
+                    tmem_ld_wait();
+                    if (c0 + 64 <= nk) {
 #pragma unroll
-                for (int u = 0; u < 64; ++u)
-                    if (c0 + u < nk) mx = fmaxf(mx, __uint_as_float(v[u]));
+                        for (int u = 0; u < 64; ++u) mx = fmaxf(mx, __uint_as_float(v[u]));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 64; ++u)
+                            if (c0 + u < nk) mx = fmaxf(mx, __uint_as_float(v[u]));
+                    }
+                }
+                mxs = mx * sc;
             }
-            if (all_masked) mx = 0.f;
-            const float mxs = mx * sc;
-            float lsum = 0.f;
             for (int sl = 0; sl < n_slices; ++sl) {
                 if (sl > 0) {                             // the previous slice's MMAs must have read the P tile
                     mbar_wait(b_pfree, ph_pfree);
                     ph_pfree ^= 1;
                 }
-                const int kend = min(64, nk16 - 64 * sl);
-                uint32_t v[64];                           // columns beyond nk16 hold stale accumulator data: masked below
-                tmem_ld64(lane_addr + COL_S + 64 * sl, v);
-                tmem_ld_wait();
+                if (warp_live) {
+                    const int kend = min(64, nk16 - 64 * sl);
+                    uint32_t v[64];                       // columns beyond nk16 hold stale accumulator data: never used
+                    tmem_ld64(lane_addr + COL_S + 64 * sl, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {             // one 16-byte chunk = 8 keys
-                    if (8 * c >= kend) break;
-                    uint32_t hi[4], lo[4];
+                    for (int c = 0; c < 8; ++c) {         // one 16-byte chunk = 8 keys
+                        if (8 * c >= kend) break;
+                        const bool full = 64 * sl + 8 * c + 8 <= nk;
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int key = 64 * sl + 8 * c + 2 * u;
-                        float x0 = all_masked ? 1.f : fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u]), sc, -mxs));
-                        float x1 = all_masked ? 1.f : fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u + 1]), sc, -mxs));
-                        if (key >= nk) x0 = 0.f;
-                        if (key + 1 >= nk) x1 = 0.f;
-                        lsum += x0 + x1;
-                        const __half2 h = __floats2half2_rn(x0, x1);
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                        hi[u] = *reinterpret_cast<const uint32_t *>(&h);
-                        lo[u] = *reinterpret_cast<const uint32_t *>(&l);
+                        for (int u = 0; u < 4; ++u) {
+                            float x0 = fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u]), sc, -mxs));
+                            float x1 = fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u + 1]), sc, -mxs));
+                            if (!full) {                  // padding keys of the last 16-key step
+                                const int key = 64 * sl + 8 * c + 2 * u;
+                                if (key >= nk) x0 = 0.f;
+                                if (key + 1 >= nk) x1 = 0.f;
+                            }
+                            lsum += x0 + x1;
+                            const __half2 h = __floats2half2_rn(x0, x1);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                            hi[u] = *reinterpret_cast<const uint32_t *>(&h);
+                            lo[u] = *reinterpret_cast<const uint32_t *>(&l);
+                        }
+                        *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 fence_async_smem();                       // also publishes this thread's share of V^T before the first arrive
                 tc_fence_before();
                 mbar_arrive(b_pready);
             }
             // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the 64 channels of this thread's row
-            mbar_wait(b_ofull, ph_o);
-            tc_fence_after();
-            float y[QN_D];
-            {
-                uint32_t v[64];
-                tmem_ld64(lane_addr + COL_O, v);
-                tmem_ld_wait();
+            if (warp_live) {                              // warp-uniform: the tensor-memory loads are .sync.aligned
+                float y[QN_D];
+                {
+                    const int ii = i < L ? i : 0;
+                    const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[ii] * L + ii) * QN_D);
 #pragma unroll
-                for (int u = 0; u < QN_D; ++u) y[u] = __uint_as_float(v[u]);
-            }
-            tc_fence_before();
-            if (i < L) {
+                    for (int c = 0; c < QN_D / 4; ++c) {  // the residual row, in flight while the last MMAs finish
+                        const float4 x = __ldg(x4 + c);
+                        y[4 * c + 0] = x.x; y[4 * c + 1] = x.y; y[4 * c + 2] = x.z; y[4 * c + 3] = x.w;
+                    }
+                }
+                mbar_wait(b_ofull, ph_o);
+                tc_fence_after();
                 const float inv = net.vf_inv_scale / lsum;
-                const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[i] * L + i) * QN_D);
                 float s1 = 0.f;
 #pragma unroll
-                for (int c = 0; c < QN_D / 4; ++c) {
-                    const float4 x = __ldg(x4 + c);
-                    y[4 * c + 0] = fmaf(y[4 * c + 0], inv, x.x);
-                    y[4 * c + 1] = fmaf(y[4 * c + 1], inv, x.y);
-                    y[4 * c + 2] = fmaf(y[4 * c + 2], inv, x.z);
-                    y[4 * c + 3] = fmaf(y[4 * c + 3], inv, x.w);
-                    s1 += (y[4 * c + 0] + y[4 * c + 1]) + (y[4 * c + 2] + y[4 * c + 3]);
+                for (int c0 = 0; c0 < QN_D; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(lane_addr + COL_O + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        y[c0 + u] = fmaf(__uint_as_float(v[u]), inv, y[c0 + u]);
+                        s1 += y[c0 + u];
+                    }
                 }
+                tc_fence_before();
                 const float mu = s1 * (1.f / QN_D);
                 float s2 = 0.f;
 #pragma unroll
@@ -313,7 +400,9 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     s2 = fmaf(y[c], y[c], s2);
                 }
                 const float rstd = rsqrtf(s2 * (1.f / QN_D) + 1e-6f);          // LayerNorm(eps=1e-6), models.py:166
-                if (Z2out) {
+                if (i >= L) {
+                    // a padding row of the last tile: nothing to write
+                } else if (Z2out) {
                     __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D, *zl = zh + net.K;
 #pragma unroll
                     for (int c = 0; c < QN_D; c += 8) {
@@ -342,10 +431,10 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         ph_s ^= 1;
         ph_o ^= 1;
         if (n_slices & 1) ph_pready ^= 1;
-        if (warp == 4 && ((n_slices - 1) & 1)) ph_pfree ^= 1;
+        if (warp == mma_warp && ((n_slices - 1) & 1)) ph_pfree ^= 1;
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == mma_warp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
@@ -362,9 +451,12 @@ int launch_encode_tc(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, 
         GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         attr_set = true;
     }
-    const long long items = n_max * ((q->L + AT_ROWS - 1) / AT_ROWS);
+    const int n_tiles = (q->L + AT_M - 1) / AT_M;                     // even tiles of whole warps: 180 -> 2 x 96
+    const int TR = 32 * ((q->L + 32 * n_tiles - 1) / (32 * n_tiles));
+    const long long items = n_max * n_tiles;
     const long long grid = items < 2ll * GAD_NUM_SMS ? items : 2ll * GAD_NUM_SMS;
-    encode_tc_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, q->Z, q->Z2);
+    encode_tc_kernel<<<(unsigned)grid, TR + 32, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, TR, n_tiles, q->Z,
+                                                                q->Z2);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -24,6 +24,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
+    uint64_t t0 = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -32,7 +33,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (spin > (1u << 28)) __trap();            // a lost arrival must fail loudly, never hang the GPU
+        if ((spin & 1023u) == 1023u) {              // a lost arrival must fail loudly, never hang the GPU:
+            uint64_t now;                           // trap after 2 s of wall clock on this barrier
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
