@@ -38,7 +38,6 @@ namespace {
 
 constexpr int AT_M = 128;                    // UMMA M (rows of the accumulators; a tile uses the first TR of them)
 constexpr int AT_MAXK = 192;                 // keys
-constexpr int AT_MAX_THREADS = 160;
 constexpr int AT_TILE_Q = AT_M * 128;        // bytes of one [128][64] fp16 tile
 constexpr int AT_TILE_K = AT_MAXK * 128;
 constexpr int AT_ATOM_V = 64 * 128;          // [64 ch][64 keys]
@@ -112,11 +111,22 @@ __device__ __forceinline__ void warp_item_tokens(const gad_qnet &net, const uint
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(AT_MAX_THREADS, 2)
+// Thread roles of a CTA. Tensor-memory lanes 32q..32q+31 are only reachable from warps with (warp & 3) == q, so the two
+// threads of a row sit in warps q and q + 4; the first warp that owns no rows issues the MMAs.
+template <int TR> struct AtCfg {
+    static constexpr int RW = TR / 32;                             // row warps per half
+    static constexpr int MMA_WARP = TR < 128 ? RW : 8;
+    static constexpr int THREADS = TR < 128 ? (4 + RW) * 32 : 288;
+    static constexpr int NROW = 2 * TR;                            // row threads: two per query row
+};
+
+template <int TR>
+__global__ void __launch_bounds__(AtCfg<TR>::THREADS, 2)
 encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const int32_t *__restrict__ active,
-                 const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, const int TR, const int n_tiles,
+                 const int32_t *__restrict__ n_rows_ptr, long long n_rows_fixed, const int n_tiles,
                  float *__restrict__ Zout, __half *__restrict__ Z2out)
 {
+    using Cfg = AtCfg<TR>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
@@ -127,16 +137,18 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     __shared__ uint8_t tok_s[2][AT_MAXK + 64];
     __shared__ int nk_s[2];
     __shared__ float ln_g[QN_D], ln_b[QN_D];
+    __shared__ float xch[2][4][AT_M];                     // what the two threads of a row tell each other
 
     const int L = net.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mma_warp = TR >> 5;
+    const int q = warp & 3, h = warp >> 2;                // TMEM lane quarter, half of the columns
+    const bool is_row = q < Cfg::RW && h < 2, is_mma = warp == Cfg::MMA_WARP;
     const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
     const long long n_items = n_rows * n_tiles;
 
     if (threadIdx.x == 0) {
         mbar_init(b_sfull, 1);
-        mbar_init(b_pready, TR);
+        mbar_init(b_pready, Cfg::NROW);
         mbar_init(b_pfree, 1);
         mbar_init(b_ofull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,7 +162,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         *reinterpret_cast<uint4 *>(sm + OFF_QH + TR * 128 + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4 *>(sm + OFF_QL + TR * 128 + idx * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (warp == mma_warp) {
+    if (is_mma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -180,7 +192,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
 
         // ---- stage Q' (this tile's rows) and K' (the valid keys): cp.async 16-byte chunks into swizzled positions,
         // rows outside the state zero-filled through the src-size operand
-        for (int idx = threadIdx.x; idx < TR * 8; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < TR * 8; idx += Cfg::THREADS) {
             const int r = idx >> 3, c = idx & 7;
             const int i = t * TR + r;
             const int ii = i < L ? i : 0;
@@ -191,7 +203,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + sw128(r, c))),
                          "l"(net.Ql + src), "r"(nbytes) : "memory");
         }
-        for (int idx = threadIdx.x; idx < nk16 * 8; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < nk16 * 8; idx += Cfg::THREADS) {
             const int k = idx >> 3, c = idx & 7;
             const int j = kj[k < nk ? k : 0];
             const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
@@ -205,7 +217,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
 
-        if (warp == mma_warp) {
+        if (is_mma) {
             // ======================= MMA issuer + next item's tokens =======================
             const uint32_t idesc_s = make_idesc_f16(AT_M, nk16);
             const uint32_t idesc_o = make_idesc_f16(AT_M, QN_D);
@@ -245,13 +257,15 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     else umma_commit(b_ofull);                          // O complete
                 }
             }
-        } else {
-            // ======================= row threads: thread = query row =======================
-            const int r = warp * 32 + lane;               // row inside the tile = TMEM lane
+        } else if (is_row) {
+            // ============ row threads: two per query row, each owns every other 32-column block ============
+            const int r = q * 32 + lane;                  // row inside the tile = TMEM lane
+            const int rt = h * TR + r;                    // index among the row threads
             const int i = t * TR + r;                     // query position
-            const bool warp_live = t * TR + warp * 32 < L;                 // warps past the state's last row only stage
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const bool warp_live = t * TR + q * 32 < L;   // warps past the state's last row only stage and arrive
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
             const float sc = all_masked ? 0.f : net.s_inv_scale;           // fully masked: every p = ex2(0) = 1
+            auto row_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NROW) : "memory"); };
 
             // V^T into the K buffer: one task = 8 keys x 8 channels of one table - eight 16-byte loads (one per key),
             // an 8x8 transpose in registers, eight 16-byte stores (one per channel row). A task's loads are issued one
@@ -291,139 +305,146 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     *reinterpret_cast<uint4 *>(base + sw128(ch + 1, chunk)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
                 }
             };
-            uint32_t va[8][4], vb[8][4];
-            int task = threadIdx.x;
+            uint32_t va[8][4];
+            int task = rt;
             if (task < n_tasks) load_task(task, va);
             mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
             tc_fence_after();
-            while (task < n_tasks) {                      // two tasks per trip, ping-pong register sets
-                if (task + TR < n_tasks) load_task(task + TR, vb);
+            while (task < n_tasks) {
                 store_task(task, va);
-                task += TR;
-                if (task >= n_tasks) break;
-                if (task + TR < n_tasks) load_task(task + TR, va);
-                store_task(task, vb);
-                task += TR;
+                task += Cfg::NROW;
+                if (task < n_tasks) load_task(task, va);
             }
 
-            float mxs = 0.f, lsum = 0.f;
+            // pass 1: row maximum over the valid keys; this thread reads the 32-column blocks h, h + 2, h + 4
+            float mx = -INFINITY;
             if (warp_live) {
-                // pass 1: row maximum over the valid keys (64 columns per tensor-memory load)
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < nk16; c0 += 64) {
-                    uint32_t v[64];
-                    tmem_ld64(lane_addr + COL_S + c0, v);
+                for (int c0 = 32 * h; c0 < nk16; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + COL_S + c0, v);
                     tmem_ld_wait();
-                    if (c0 + 64 <= nk) {
+                    if (c0 + 32 <= nk) {
 #pragma unroll
-                        for (int u = 0; u < 64; ++u) mx = fmaxf(mx, __uint_as_float(v[u]));
+                        for (int u = 0; u < 32; ++u) mx = fmaxf(mx, __uint_as_float(v[u]));
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 64; ++u)
+                        for (int u = 0; u < 32; ++u)
                             if (c0 + u < nk) mx = fmaxf(mx, __uint_as_float(v[u]));
                     }
                 }
-                mxs = mx * sc;
             }
+            xch[h][0][r] = mx;
+            row_barrier();
+            mx = fmaxf(mx, xch[h ^ 1][0][r]);
+            const float mxs = mx * sc;
+            float lsum = 0.f;
             for (int sl = 0; sl < n_slices; ++sl) {
                 if (sl > 0) {                             // the previous slice's MMAs must have read the P tile
                     mbar_wait(b_pfree, ph_pfree);
                     ph_pfree ^= 1;
                 }
-                if (warp_live) {
-                    const int kend = min(64, nk16 - 64 * sl);
-                    uint32_t v[64];                       // columns beyond nk16 hold stale accumulator data: never used
-                    tmem_ld64(lane_addr + COL_S + 64 * sl, v);
+                const int c0 = 64 * sl + 32 * h;          // this thread's 32 keys of the slice: chunks 4h .. 4h+3
+                if (warp_live && c0 < nk16) {
+                    uint32_t v[32];                       // columns beyond nk16 hold stale accumulator data: never used
+                    tmem_ld32(lane_addr + COL_S + c0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {         // one 16-byte chunk = 8 keys
-                        if (8 * c >= kend) break;
-                        const bool full = 64 * sl + 8 * c + 8 <= nk;
+                    for (int c = 0; c < 4; ++c) {         // one 16-byte chunk = 8 keys
+                        if (c0 + 8 * c >= nk16) break;
+                        const bool full = c0 + 8 * c + 8 <= nk;
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float x0 = fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u]), sc, -mxs));
                             float x1 = fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u + 1]), sc, -mxs));
                             if (!full) {                  // padding keys of the last 16-key step
-                                const int key = 64 * sl + 8 * c + 2 * u;
+                                const int key = c0 + 8 * c + 2 * u;
                                 if (key >= nk) x0 = 0.f;
                                 if (key + 1 >= nk) x1 = 0.f;
                             }
                             lsum += x0 + x1;
-                            const __half2 h = __floats2half2_rn(x0, x1);
-                            const float2 hf = __half22float2(h);
-                            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                            hi[u] = *reinterpret_cast<const uint32_t *>(&h);
-                            lo[u] = *reinterpret_cast<const uint32_t *>(&l);
+                            const __half2 hh = __floats2half2_rn(x0, x1);
+                            const float2 hf = __half22float2(hh);
+                            const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                            hi[u] = *reinterpret_cast<const uint32_t *>(&hh);
+                            lo[u] = *reinterpret_cast<const uint32_t *>(&ll);
                         }
-                        *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, 4 * h + c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, 4 * h + c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
                 fence_async_smem();                       // also publishes this thread's share of V^T before the first arrive
                 tc_fence_before();
                 mbar_arrive(b_pready);
             }
-            // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the 64 channels of this thread's row
-            if (warp_live) {                              // warp-uniform: the tensor-memory loads are .sync.aligned
-                float y[QN_D];
-                {
-                    const int ii = i < L ? i : 0;
-                    const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[ii] * L + ii) * QN_D);
+            // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the row's 64 channels; this thread owns
+            // channels 32h .. 32h+31 and trades the partial sums with its partner
+            float y[32];
+            if (warp_live) {
+                const int ii = i < L ? i : 0;
+                const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[ii] * L + ii) * QN_D + 32 * h);
 #pragma unroll
-                    for (int c = 0; c < QN_D / 4; ++c) {  // the residual row, in flight while the last MMAs finish
-                        const float4 x = __ldg(x4 + c);
-                        y[4 * c + 0] = x.x; y[4 * c + 1] = x.y; y[4 * c + 2] = x.z; y[4 * c + 3] = x.w;
-                    }
+                for (int c = 0; c < 8; ++c) {             // the residual row, in flight while the last MMAs finish
+                    const float4 x = __ldg(x4 + c);
+                    y[4 * c + 0] = x.x; y[4 * c + 1] = x.y; y[4 * c + 2] = x.z; y[4 * c + 3] = x.w;
                 }
+            }
+            xch[h][1][r] = lsum;
+            row_barrier();
+            const float inv = net.vf_inv_scale / (lsum + xch[h ^ 1][1][r]);
+            float s1 = 0.f;
+            if (warp_live) {
                 mbar_wait(b_ofull, ph_o);
                 tc_fence_after();
-                const float inv = net.vf_inv_scale / lsum;
-                float s1 = 0.f;
-#pragma unroll
-                for (int c0 = 0; c0 < QN_D; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(lane_addr + COL_O + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) {
-                        y[c0 + u] = fmaf(__uint_as_float(v[u]), inv, y[c0 + u]);
-                        s1 += y[c0 + u];
-                    }
-                }
+                uint32_t v[32];
+                tmem_ld32(lane_addr + COL_O + 32 * h, v);
+                tmem_ld_wait();
                 tc_fence_before();
-                const float mu = s1 * (1.f / QN_D);
-                float s2 = 0.f;
 #pragma unroll
-                for (int c = 0; c < QN_D; ++c) {
-                    y[c] -= mu;
-                    s2 = fmaf(y[c], y[c], s2);
+                for (int u = 0; u < 32; ++u) {
+                    y[u] = fmaf(__uint_as_float(v[u]), inv, y[u]);
+                    s1 += y[u];
                 }
-                const float rstd = rsqrtf(s2 * (1.f / QN_D) + 1e-6f);          // LayerNorm(eps=1e-6), models.py:166
-                if (i >= L) {
-                    // a padding row of the last tile: nothing to write
-                } else if (Z2out) {
-                    __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D, *zl = zh + net.K;
+            }
+            xch[h][2][r] = s1;
+            row_barrier();
+            const float mu = (s1 + xch[h ^ 1][2][r]) * (1.f / QN_D);
+            float s2 = 0.f;
+            if (warp_live) {
 #pragma unroll
-                    for (int c = 0; c < QN_D; c += 8) {
+                for (int u = 0; u < 32; ++u) {
+                    y[u] -= mu;
+                    s2 = fmaf(y[u], y[u], s2);
+                }
+            }
+            xch[h][3][r] = s2;
+            row_barrier();
+            s2 += xch[h ^ 1][3][r];
+            const float rstd = rsqrtf(s2 * (1.f / QN_D) + 1e-6f);              // LayerNorm(eps=1e-6), models.py:166
+            if (warp_live && i < L) {
+                if (Z2out) {
+                    __half *zh = Z2out + (size_t)row * 2 * net.K + (size_t)i * QN_D + 32 * h, *zl = zh + net.K;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float z0 = y[c + 2 * u] * rstd * ln_g[c + 2 * u] + ln_b[c + 2 * u];
-                            const float z1 = y[c + 2 * u + 1] * rstd * ln_g[c + 2 * u + 1] + ln_b[c + 2 * u + 1];
-                            const __half2 h = __floats2half2_rn(z0, z1);
-                            const float2 hf = __half22float2(h);
-                            const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
-                            hi[u] = *reinterpret_cast<const uint32_t *>(&h);
-                            lo[u] = *reinterpret_cast<const uint32_t *>(&l);
+                            const int ch = 32 * h + c + 2 * u;
+                            const float z0 = y[c + 2 * u] * rstd * ln_g[ch] + ln_b[ch];
+                            const float z1 = y[c + 2 * u + 1] * rstd * ln_g[ch + 1] + ln_b[ch + 1];
+                            const __half2 hh = __floats2half2_rn(z0, z1);
+                            const float2 hf = __half22float2(hh);
+                            const __half2 ll = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
+                            hi[u] = *reinterpret_cast<const uint32_t *>(&hh);
+                            lo[u] = *reinterpret_cast<const uint32_t *>(&ll);
                         }
                         *reinterpret_cast<uint4 *>(zh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4 *>(zl + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 } else {
-                    float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D;
+                    float *z = Zout + (size_t)row * net.K + (size_t)i * QN_D + 32 * h;
 #pragma unroll
-                    for (int c = 0; c < QN_D; ++c) z[c] = y[c] * rstd * ln_g[c] + ln_b[c];
+                    for (int c = 0; c < 32; ++c) z[c] = y[c] * rstd * ln_g[32 * h + c] + ln_b[32 * h + c];
                 }
             }
         }
@@ -431,12 +452,29 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         ph_s ^= 1;
         ph_o ^= 1;
         if (n_slices & 1) ph_pready ^= 1;
-        if (warp == mma_warp && ((n_slices - 1) & 1)) ph_pfree ^= 1;
+        if (!is_row && ((n_slices - 1) & 1)) ph_pfree ^= 1;
     }
     __syncthreads();
-    if (warp == mma_warp) {
+    if (is_mma) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
+}
+
+template <int TR>
+int launch_tc(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const int32_t *n_ptr, long long n_max,
+              int n_tiles, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        attr_set = true;
+    }
+    const long long items = n_max * n_tiles;
+    const long long grid = items < 2ll * GAD_NUM_SMS ? items : 2ll * GAD_NUM_SMS;
+    encode_tc_kernel<TR><<<(unsigned)grid, AtCfg<TR>::THREADS, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, n_tiles,
+                                                                            q->Z, q->Z2);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
 }
 
 }  // namespace
@@ -446,17 +484,8 @@ int attn_tc_supported(const gad_qnet *q) { return q->L <= AT_MAXK && q->L >= 16;
 int launch_encode_tc(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const int32_t *n_ptr, long long n_max,
                      cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        attr_set = true;
-    }
-    const int n_tiles = (q->L + AT_M - 1) / AT_M;                     // even tiles of whole warps: 180 -> 2 x 96
-    const int TR = 32 * ((q->L + 32 * n_tiles - 1) / (32 * n_tiles));
-    const long long items = n_max * n_tiles;
-    const long long grid = items < 2ll * GAD_NUM_SMS ? items : 2ll * GAD_NUM_SMS;
-    encode_tc_kernel<<<(unsigned)grid, TR + 32, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, TR, n_tiles, q->Z,
-                                                                q->Z2);
-    GAD_LAUNCH_CHECK();
-    return GAD_OK;
+    const int n_tiles = (q->L + AT_M - 1) / AT_M;                     // even tiles: 186 positions -> 2 x 96 rows
+    const int per_tile = (q->L + n_tiles - 1) / n_tiles;
+    return per_tile <= 96 ? launch_tc<96>(q, tok_in, active, n_ptr, n_max, n_tiles, st)
+                          : launch_tc<128>(q, tok_in, active, n_ptr, n_max, n_tiles, st);
 }
