@@ -40,13 +40,12 @@ constexpr int AT_M = 128;                    // UMMA M (rows of the accumulators
 constexpr int AT_MAXK = 192;                 // keys
 constexpr int AT_TILE_Q = AT_M * 128;        // bytes of one [128][64] fp16 tile
 constexpr int AT_TILE_K = AT_MAXK * 128;
-constexpr int AT_ATOM_V = 64 * 128;          // [64 ch][64 keys]
+constexpr int AT_SLICE_V = 64 * 128;         // 64 keys of V rows
 constexpr int OFF_QH = 0;                    // Q' hi, later P hi
 constexpr int OFF_QL = OFF_QH + AT_TILE_Q;
 constexpr int OFF_KH = OFF_QL + AT_TILE_Q;   // K' hi, later V^T hi (3 atoms)
 constexpr int OFF_KL = OFF_KH + AT_TILE_K;
-constexpr int OFF_BAR = OFF_KL + AT_TILE_K;  // 81 920
-constexpr int AT_SMEM = OFF_BAR + 128 + 1024;
+constexpr int OFF_XR = OFF_KL + AT_TILE_K;   // 81 920: the tile's residual rows (fp32, 16-byte chunks swizzled), 96-row tiles
 constexpr int COL_S = 0, COL_O = 192;
 constexpr int TMEM_COLS = 256;
 
@@ -118,6 +117,9 @@ template <int TR> struct AtCfg {
     static constexpr int MMA_WARP = TR < 128 ? RW : 8;
     static constexpr int THREADS = TR < 128 ? (4 + RW) * 32 : 288;
     static constexpr int NROW = 2 * TR;                            // row threads: two per query row
+    static constexpr bool XSTAGE = TR < 128;                       // residual rows staged in shared memory (two CTAs still fit)
+    static constexpr int OFF_BAR = OFF_XR + (XSTAGE ? TR * 256 : 0);
+    static constexpr int SMEM = OFF_BAR + 128 + 1024;
 };
 
 template <int TR>
@@ -129,7 +131,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     using Cfg = AtCfg<TR>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + OFF_BAR);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + Cfg::OFF_BAR);
     // bars: s_full, p_ready, p_free, o_full, then the TMEM base address
     const uint32_t b_sfull = smem_u32(bars), b_pready = b_sfull + 8, b_pfree = b_pready + 8, b_ofull = b_pfree + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
@@ -203,6 +205,17 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + sw128(r, c))),
                          "l"(net.Ql + src), "r"(nbytes) : "memory");
         }
+        if (Cfg::XSTAGE) {
+            for (int idx = threadIdx.x; idx < TR * 16; idx += Cfg::THREADS) {
+                const int r = idx >> 4, c = idx & 15;
+                const int i = t * TR + r;
+                const int ii = i < L ? i : 0;
+                const uint32_t nbytes = i < L ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                 smem_u32(sm + OFF_XR + r * 256 + ((c ^ (r & 7)) << 4))),
+                             "l"(net.X + ((size_t)tok[ii] * L + ii) * QN_D + c * 4), "r"(nbytes) : "memory");
+            }
+        }
         for (int idx = threadIdx.x; idx < nk16 * 8; idx += Cfg::THREADS) {
             const int k = idx >> 3, c = idx & 7;
             const int j = kj[k < nk ? k : 0];
@@ -220,7 +233,9 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         if (is_mma) {
             // ======================= MMA issuer + next item's tokens =======================
             const uint32_t idesc_s = make_idesc_f16(AT_M, nk16);
-            const uint32_t idesc_o = make_idesc_f16(AT_M, QN_D);
+            // O's B operand: the V rows as staged, [key][64 ch], read as an MN-major operand (instruction descriptor bit 16):
+            // 8-key groups 1024 bytes apart, 16 keys = 2048 bytes per k-step - no transpose anywhere
+            const uint32_t idesc_o = make_idesc_f16(AT_M, QN_D) | (1u << 16);
             const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH)), dql = make_smem_desc(smem_u32(sm + OFF_QL));
             const uint32_t ds = tmem_base + COL_S, dout = tmem_base + COL_O;
             if (lane == 0) {
@@ -246,12 +261,12 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     mbar_wait(b_pready, php);
                     php ^= 1;
                     tc_fence_after();
-                    const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_KH + sl * AT_ATOM_V));
-                    const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_KL + sl * AT_ATOM_V));
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        umma_f16(dout, dql + 2 * ks, dvh + 2 * ks, idesc_o, (sl | ks) != 0);
-                        umma_f16(dout, dqh + 2 * ks, dvl + 2 * ks, idesc_o, 1u);
-                        umma_f16(dout, dqh + 2 * ks, dvh + 2 * ks, idesc_o, 1u);
+                    const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_KH + sl * AT_SLICE_V));
+                    const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_KL + sl * AT_SLICE_V));
+                    for (int ks = 0; ks < ksteps; ++ks) {                       // descriptor addresses count 16-byte units
+                        umma_f16(dout, dql + 2 * ks, dvh + 128 * ks, idesc_o, (sl | ks) != 0);
+                        umma_f16(dout, dqh + 2 * ks, dvl + 128 * ks, idesc_o, 1u);
+                        umma_f16(dout, dqh + 2 * ks, dvh + 128 * ks, idesc_o, 1u);
                     }
                     if (sl + 1 < n_slices) umma_commit(b_pfree);       // the P tile may be overwritten
                     else umma_commit(b_ofull);                          // O complete
@@ -267,53 +282,17 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             const float sc = all_masked ? 0.f : net.s_inv_scale;           // fully masked: every p = ex2(0) = 1
             auto row_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NROW) : "memory"); };
 
-            // V^T into the K buffer: one task = 8 keys x 8 channels of one table - eight 16-byte loads (one per key),
-            // an 8x8 transpose in registers, eight 16-byte stores (one per channel row). A task's loads are issued one
-            // task ahead; the first ones before S is waited for.
-            const int ng = nk16 >> 3;                     // groups of 8 keys
-            const int n_tasks = ng * 16;                  // x 8 channel groups x {hi, lo}
-            auto load_task = [&](int task, uint32_t (&in)[8][4]) {
-                const int lo_tab = task & 1, u = task >> 1;
-                const int c8 = u / ng, kg = u - c8 * ng;
-                const __half *tab = lo_tab ? net.VFl : net.VFh;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int k = kg * 8 + e;
-                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                    if (k < nk) {
-                        const int j = kj[k];
-                        x = __ldg(reinterpret_cast<const uint4 *>(tab + ((size_t)tok[j] * L + j) * QN_D + c8 * 8));
-                    }
-                    in[e][0] = x.x; in[e][1] = x.y; in[e][2] = x.z; in[e][3] = x.w;
-                }
-            };
-            auto store_task = [&](int task, const uint32_t (&in)[8][4]) {
-                const int lo_tab = task & 1, u = task >> 1;
-                const int c8 = u / ng, kg = u - c8 * ng;
-                const int atom = kg >> 3, chunk = kg & 7; // 8 keys = one 16-byte chunk of the [ch][64 keys] atom
-                uint8_t *base = sm + (lo_tab ? OFF_KL : OFF_KH) + atom * AT_ATOM_V;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {             // channel pair (2w, 2w+1) of this 8-channel group
-                    uint32_t even[4], odd[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {         // keys 2e, 2e+1
-                        even[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x5410);      // low halves  -> channel 2w
-                        odd[e] = __byte_perm(in[2 * e][w], in[2 * e + 1][w], 0x7632);       // high halves -> channel 2w+1
-                    }
-                    const int ch = c8 * 8 + 2 * w;
-                    *reinterpret_cast<uint4 *>(base + sw128(ch, chunk)) = make_uint4(even[0], even[1], even[2], even[3]);
-                    *reinterpret_cast<uint4 *>(base + sw128(ch + 1, chunk)) = make_uint4(odd[0], odd[1], odd[2], odd[3]);
-                }
-            };
-            uint32_t va[8][4];
-            int task = rt;
-            if (task < n_tasks) load_task(task, va);
             mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
             tc_fence_after();
-            while (task < n_tasks) {
-                store_task(task, va);
-                task += Cfg::NROW;
-                if (task < n_tasks) load_task(task, va);
+            for (int idx = rt; idx < nk16 * 8; idx += Cfg::NROW) {         // V rows into the K buffer, exactly like the K'
+                const int k = idx >> 3, c = idx & 7;                        // rows; they land while the row maxima are computed
+                const int j = kj[k < nk ? k : 0];
+                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
+                const uint32_t nbytes = k < nk ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KH + sw128(k, c))),
+                             "l"(net.VFh + src), "r"(nbytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KL + sw128(k, c))),
+                             "l"(net.VFl + src), "r"(nbytes) : "memory");
             }
 
             // pass 1: row maximum over the valid keys; this thread reads the 32-column blocks h, h + 2, h + 4
@@ -337,6 +316,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             row_barrier();
             mx = fmaxf(mx, xch[h ^ 1][0][r]);
             const float mxs = mx * sc;
+            asm volatile("cp.async.wait_all;" ::: "memory");             // V rows: published by the fence before the first arrive
             float lsum = 0.f;
             for (int sl = 0; sl < n_slices; ++sl) {
                 if (sl > 0) {                             // the previous slice's MMAs must have read the P tile
@@ -384,8 +364,10 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 const int ii = i < L ? i : 0;
                 const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[ii] * L + ii) * QN_D + 32 * h);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {             // the residual row, in flight while the last MMAs finish
-                    const float4 x = __ldg(x4 + c);
+                for (int c = 0; c < 8; ++c) {             // the residual row (global loads fly while the last MMAs finish)
+                    const float4 x = Cfg::XSTAGE ? *reinterpret_cast<const float4 *>(sm + OFF_XR + r * 256 +
+                                                                                     (((8 * h + c) ^ (r & 7)) << 4))
+                                                 : __ldg(x4 + c);
                     y[4 * c + 0] = x.x; y[4 * c + 1] = x.y; y[4 * c + 2] = x.z; y[4 * c + 3] = x.w;
                 }
             }
@@ -466,12 +448,12 @@ int launch_tc(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, const i
 {
     static bool attr_set = false;
     if (!attr_set) {
-        GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+        GAD_CUDA(cudaFuncSetAttribute(encode_tc_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<TR>::SMEM));
         attr_set = true;
     }
     const long long items = n_max * n_tiles;
     const long long grid = items < 2ll * GAD_NUM_SMS ? items : 2ll * GAD_NUM_SMS;
-    encode_tc_kernel<TR><<<(unsigned)grid, AtCfg<TR>::THREADS, AT_SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, n_tiles,
+    encode_tc_kernel<TR><<<(unsigned)grid, AtCfg<TR>::THREADS, AtCfg<TR>::SMEM, st>>>(*q, tok_in, active, n_ptr, n_max, n_tiles,
                                                                             q->Z, q->Z2);
     GAD_LAUNCH_CHECK();
     return GAD_OK;

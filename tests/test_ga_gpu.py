@@ -355,6 +355,33 @@ def test_qnet_encoder_variants_agree(gpu, weight_files, monkeypatch, variant):
         assert np.array_equal(a1, a0)
 
 
+@pytest.mark.parametrize("rows,cols", [(4, 30), (5, 30), (4, 20)])
+def test_qnet_tc_encoder_other_tilings(gpu, monkeypatch, rows, cols):
+    """The tcgen05 attention on windows whose tiling differs from the golden ones: 4x30 is one 128-row tile (two
+    threads per row in warps q and q+4 with the MMA issuer in a ninth warp), 5x30 two 96-row tiles with a short
+    second tile, 4x20 one 96-row tile. Random ragged states, fully padded rows included."""
+    from DPAMSA.dqn import QNet
+    sd = O.synth_qnet_weights(rows, cols, 11)
+    rng = np.random.default_rng(rows * 100 + cols)
+    L = rows * (cols + 1)
+    states = np.zeros((300, L), np.uint8)
+    for s in states:
+        pos = 0
+        for _ in range(rows):
+            rem = int(rng.integers(0, cols + 1))
+            s[pos:pos + rem] = rng.integers(1, 5, rem)
+            s[pos + rem] = 5
+            pos += rem + 1
+    max_value = cols * rows * (rows - 1) / 2 * 4
+    net = QNet(sd, rows, cols)
+    monkeypatch.delenv("GAD_QNET_ENCODER", raising=False)
+    q0, a0 = net.forward(states, max_value)
+    monkeypatch.setenv("GAD_QNET_ENCODER", "tc")
+    q1, a1 = net.forward(states, max_value)
+    assert np.all(np.abs(q1 - q0) <= 3e-5 * np.abs(q0) + 2e-6 * max_value), np.abs(q1 - q0).max()
+    assert np.array_equal(a1, a0)
+
+
 def test_dqn_and_environment_facade(gpu, weight_files, primitives):
     from DPAMSA.dqn import DQN
     from DPAMSA.env import Environment
