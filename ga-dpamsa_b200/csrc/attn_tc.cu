@@ -1,31 +1,32 @@
-// The encoder's attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
-// Same mathematics as encode_fa_kernel (qnet.cu) - S = Q'K'^T from split fp16 row tables, softmax in the
-// log2 domain, O = P V with the output projection folded into V, residual, LayerNorm - but both products run
-// as tcgen05.mma with the accumulators in tensor memory.
+// The encoder's attention on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only: the default encoder
+// for agent windows of 16..192 positions (launch_forward in qnet.cu; GAD_QNET_ENCODER=fa selects the mma.sync one).
+// Same mathematics as encode_fa_kernel - S = Q'K'^T from split fp16 row tables, softmax in the log2 domain,
+// O = P V with the output projection folded into V, residual, LayerNorm - with both products as tcgen05.mma and
+// the accumulators in tensor memory.
 //
-//   work item = (state, tile of TR query rows), TR = 96 or 128 chosen so that the tiles of a state are even
-//   (L = 180 -> two tiles of 96); persistent CTAs of TR + 32 threads, two CTAs per SM so that one CTA's
-//   staging and softmax overlap the other's MMAs:
-//     warps 0..TR/32-1   thread = query row = TMEM lane: softmax, LayerNorm, operand staging
-//     last warp          lane 0 issues every tcgen05.mma; while the row warps work on item n the whole warp
-//                        builds the tokens and the key list of item n+1 (double-buffered); it also owns the
-//                        256 TMEM columns
-//   shared memory: two buffers of K-major, 128-byte swizzled operand tiles, each used twice per item
+//   work item = (state, tile of TR query rows); TR = 96 when the state's rows split evenly into tiles of <= 96
+//   (186 positions -> two tiles of 96, 93 -> one), else 128. Persistent CTAs, two per SM, so that one CTA's staging
+//   and softmax overlap the other's MMAs. Warps of a CTA (TR = 96: seven):
+//     row warps    two threads per query row: tensor-memory lanes 32q..32q+31 are only reachable from warps with
+//                  (warp & 3) == q, so a row's threads sit in warps q and q+4; thread h of a row owns every other
+//                  32-key block of S and channels 32h..32h+31 of O, and trades max / sum / LayerNorm partials with
+//                  its partner through shared memory (named barrier 1)
+//     MMA warp     the first warp that owns no rows: lane 0 issues every tcgen05.mma; while the row warps work on
+//                  item n the whole warp builds the tokens and the key list of item n+1 (double-buffered); it also
+//                  owns the 256 TMEM columns
+//   shared memory: K-major 128-byte swizzled operand tiles, two of them used twice per item
 //     QP  hi|lo  [128 rows][64]      32 KB   Q' (A operand of S), then - once S is complete - the P slices
-//     KV  hi|lo  [<=192][64]         48 KB   K' (B operand of S), then V^T as 3 atoms [64 ch][64 keys] (B of O)
+//     KV  hi|lo  [<=192][64]         48 KB   K' rows (B operand of S), then the V rows of the same keys, which the
+//                                            second product reads as an MN-major B operand: no transpose anywhere
+//     XR  fp32   [96][64]            24 KB   the tile's residual rows (TR = 96 only; two CTAs still fit an SM)
 //   tensor memory: S at columns 0..191 (fp32, one column per key), O at 192..255.
 //
-//   item: cp.async Q', K' -> S = 12 MMAs (N = keys) -> commit
-//         row threads: (V rows of the first transpose task already in flight) wait S; transpose V rows into
-//                      KV; row max from TMEM; per 64-key slice: p = ex2(s - max) as hi|lo fp16 into QP,
-//                      fence.proxy.async, arrive
+//   item: cp.async Q', K', residual rows -> S = 12 MMAs (N = keys) -> commit
+//         row threads: wait S; cp.async the V rows over K'; row max from TMEM while they land; per 64-key slice:
+//                      p = ex2(s - max) as hi|lo fp16 into QP, fence.proxy.async, arrive
 //         MMA thread : per slice: wait P -> 12 MMAs O += P V (N = 64) -> commit (frees QP / completes O)
-//         row threads: residual row loaded, wait O; /sum, residual, LayerNorm over the row's 64 channels,
-//                      (hi|lo) store
-// Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi): fp32-class like the other encoders; a row's
-// softmax and LayerNorm need no cross-thread reduction at all.
-//
-// Status: opt-in (GAD_QNET_ENCODER=tc), parity-tested against the other encoders; see DESIGN.md for timings.
+//         row threads: wait O; /sum, residual, LayerNorm over the row's 64 channels, (hi|lo) store
+// Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi): fp32-class like the other encoders.
 #include "qnet.cuh"
 #include "tc_ptx.cuh"
 

@@ -1264,10 +1264,11 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
                    float max_value, float *Qout, int32_t *act_out, int32_t *next_active, int32_t *next_count,
                    cudaStream_t st)
 {
-    // GAD_QNET_ENCODER (A/B testing): unset = flash-attention style kernel, "mma" = table logits + mma.sync
-    // product, "simt" = table logits + fp32 register tiles
+    // GAD_QNET_ENCODER (A/B testing): unset or "tc" = attention on tcgen05 (attn_tc.cu; windows of 16..192 positions),
+    // "fa" = flash-attention style kernel on mma.sync (also what larger or tiny windows get), "mma" = table logits +
+    // mma.sync product, "simt" = table logits + fp32 register tiles
     const char *enc = getenv("GAD_QNET_ENCODER");
-    if (enc && enc[0] == 't' && attn_tc_supported(q)) {   // "tc": attention on tcgen05 (attn_tc.cu)
+    if ((!enc || !enc[0] || enc[0] == 't') && attn_tc_supported(q)) {
         int rc = launch_encode_tc(q, tok_in, active, n_ptr, n_max, st);
         if (rc) return rc;
     } else if (encode_fa_smem_bytes(q->L) <= 110 * 1024 && !(enc && (enc[0] == 'm' || enc[0] == 's'))) {

@@ -1,4 +1,4 @@
-"""Times one Q-network forward per encoder variant (GAD_QNET_ENCODER = fa default | tc) with bench.py's own
+"""Times one Q-network forward per encoder variant (GAD_QNET_ENCODER = tc default | fa) with bench.py's own
 CUDA-event timer. Usage: python scripts/encoder_timing.py [rows cols states] ; prints ms per forward."""
 import os
 import subprocess
@@ -13,7 +13,7 @@ import bench
 r, c, n = %d, %d, %d
 model, _ = bench.synth_weight_file(r, c, tag="_enc")
 bench.qnet_forward_ms(model, r, c, n)
-print(os.environ.get("GAD_QNET_ENCODER", "fa"), r, c, n, bench.qnet_forward_ms(model, r, c, n))
+print(os.environ.get("GAD_QNET_ENCODER", "tc"), r, c, n, bench.qnet_forward_ms(model, r, c, n))
 """
 
 
@@ -24,10 +24,7 @@ def main():
     for r, c, n in shapes:
         for enc in ("fa", "tc"):
             env = dict(os.environ)
-            if enc == "tc":
-                env["GAD_QNET_ENCODER"] = "tc"
-            else:
-                env.pop("GAD_QNET_ENCODER", None)
+            env["GAD_QNET_ENCODER"] = enc
             code = CHILD % (os.path.join(ROOT, "ga-dpamsa_b200"), ROOT, r, c, n)
             out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
             print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:])

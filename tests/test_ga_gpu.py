@@ -337,10 +337,10 @@ def test_qnet_tensor_core_l1_against_fp32_tiles(gpu, weight_files, monkeypatch):
         assert np.array_equal(q_big[:len(states)], net.forward(states, max_value)[0])
 
 
-@pytest.mark.parametrize("variant", ["tc", "mma", "simt"])
+@pytest.mark.parametrize("variant", ["fa", "mma", "simt"])
 def test_qnet_encoder_variants_agree(gpu, weight_files, monkeypatch, variant):
-    """The alternative encoders (attention on tcgen05; table logits + mma.sync; table logits + fp32 tiles) give
-    the default flash-attention style kernel's Q-values to fp32 rounding and the same greedy actions."""
+    """The alternative encoders (flash-attention style on mma.sync; table logits + mma.sync; table logits + fp32
+    tiles) give the default tcgen05 attention kernel's Q-values to fp32 rounding and the same greedy actions."""
     from DPAMSA.dqn import QNet
     z = np.load(os.path.join(GOLDEN, "qnet_vectors.npz"))
     for (rows, cols), (name, sd) in weight_files.items():
@@ -374,7 +374,7 @@ def test_qnet_tc_encoder_other_tilings(gpu, monkeypatch, rows, cols):
             pos += rem + 1
     max_value = cols * rows * (rows - 1) / 2 * 4
     net = QNet(sd, rows, cols)
-    monkeypatch.delenv("GAD_QNET_ENCODER", raising=False)
+    monkeypatch.setenv("GAD_QNET_ENCODER", "fa")
     q0, a0 = net.forward(states, max_value)
     monkeypatch.setenv("GAD_QNET_ENCODER", "tc")
     q1, a1 = net.forward(states, max_value)
