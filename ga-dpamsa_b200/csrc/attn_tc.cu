@@ -33,6 +33,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 using namespace tcptx;
 
 namespace {
@@ -329,16 +331,13 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                     uint32_t v[32];                       // columns beyond nk16 hold stale accumulator data: never used
                     tmem_ld32(lane_addr + COL_S + c0, v);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {         // one 16-byte chunk = 8 keys
-                        if (c0 + 8 * c >= nk16) break;
-                        const bool full = c0 + 8 * c + 8 <= nk;
+                    auto chunk = [&](int c, auto masked) {    // one 16-byte chunk = 8 keys
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float x0 = fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u]), sc, -mxs));
                             float x1 = fast_ex2(fmaf(__uint_as_float(v[8 * c + 2 * u + 1]), sc, -mxs));
-                            if (!full) {                  // padding keys of the last 16-key step
+                            if (decltype(masked)::value) {            // padding keys of the last 16-key step
                                 const int key = c0 + 8 * c + 2 * u;
                                 if (key >= nk) x0 = 0.f;
                                 if (key + 1 >= nk) x1 = 0.f;
@@ -352,6 +351,16 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                         }
                         *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, 4 * h + c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, 4 * h + c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    };
+                    if (c0 + 32 <= nk) {                  // the common case: all 32 keys are real
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) chunk(c, std::false_type{});
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c0 + 8 * c >= nk16) break;
+                            chunk(c, std::true_type{});
+                        }
                     }
                 }
                 fence_async_smem();                       // also publishes this thread's share of V^T before the first arrive

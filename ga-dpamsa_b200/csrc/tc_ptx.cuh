@@ -23,9 +23,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    uint32_t done = 0;
-    uint64_t t0 = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
+    auto try_wait = [&]() {
+        uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -33,12 +32,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if ((spin & 1023u) == 1023u) {              // a lost arrival must fail loudly, never hang the GPU:
-            uint64_t now;                           // trap after 2 s of wall clock on this barrier
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) __trap();
-        }
+        return done != 0;
+    };
+    uint64_t t0 = 0;
+    for (;;) {
+#pragma unroll 1
+        for (int spin = 0; spin < 4096; ++spin)
+            if (try_wait()) return;
+        uint64_t now;                               // a lost arrival must fail loudly, never hang the GPU:
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));          // trap after 2 s of wall clock on this barrier
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
