@@ -15,16 +15,18 @@
 //                  item n the whole warp builds the tokens and the key list of item n+1 (double-buffered); it also
 //                  owns the 256 TMEM columns
 //   shared memory: K-major 128-byte swizzled operand tiles, two of them used twice per item
-//     QP  hi|lo  [128 rows][64]      32 KB   Q' (A operand of S), then - once S is complete - the P slices
+//     QP  hi|lo  [128 rows][64]      32 KB   Q' (A operand of S), then - once S is complete - two buffers of P
+//                                            blocks, hi|lo [128][32 keys] each (64-byte swizzled rows), so that the
+//                                            softmax of block b+1 runs while the tensor core consumes block b
 //     KV  hi|lo  [<=192][64]         48 KB   K' rows (B operand of S), then the V rows of the same keys, which the
 //                                            second product reads as an MN-major B operand: no transpose anywhere
 //     XR  fp32   [96][64]            24 KB   the tile's residual rows (TR = 96 only; two CTAs still fit an SM)
 //   tensor memory: S at columns 0..191 (fp32, one column per key), O at 192..255.
 //
 //   item: cp.async Q', K', residual rows -> S = 12 MMAs (N = keys) -> commit
-//         row threads: wait S; cp.async the V rows over K'; row max from TMEM while they land; per 64-key slice:
-//                      p = ex2(s - max) as hi|lo fp16 into QP, fence.proxy.async, arrive
-//         MMA thread : per slice: wait P -> 12 MMAs O += P V (N = 64) -> commit (frees QP / completes O)
+//         row threads: wait S; cp.async the V rows over K'; row max from TMEM while they land; per 32-key block:
+//                      p = ex2(s - max) as hi|lo fp16 into the block's P buffer, fence.proxy.async, arrive
+//         MMA thread : per block: wait P -> 6 MMAs O += P V (N = 64) -> commit (frees the buffer / completes O)
 //         row threads: wait O; /sum, residual, LayerNorm over the row's 64 channels, (hi|lo) store
 // Every product is the 3-term fp16 split (lo.hi + hi.lo + hi.hi): fp32-class like the other encoders.
 #include "qnet.cuh"
@@ -43,7 +45,6 @@ constexpr int AT_M = 128;                    // UMMA M (rows of the accumulators
 constexpr int AT_MAXK = 192;                 // keys
 constexpr int AT_TILE_Q = AT_M * 128;        // bytes of one [128][64] fp16 tile
 constexpr int AT_TILE_K = AT_MAXK * 128;
-constexpr int AT_SLICE_V = 64 * 128;         // 64 keys of V rows
 constexpr int OFF_QH = 0;                    // Q' hi, later P hi
 constexpr int OFF_QL = OFF_QH + AT_TILE_Q;
 constexpr int OFF_KH = OFF_QL + AT_TILE_Q;   // K' hi, later V^T hi (3 atoms)
@@ -54,6 +55,9 @@ constexpr int TMEM_COLS = 256;
 
 // byte offset of the 16-byte chunk c of row r inside a K-major tile with 128-byte rows and 128B swizzle
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// the same for 64-byte rows with 64B swizzle (the P tiles: 32 keys per row)
+__device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ float fast_ex2(float x)
 {
@@ -135,9 +139,9 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + Cfg::OFF_BAR);
-    // bars: s_full, p_ready, p_free, o_full, then the TMEM base address
-    const uint32_t b_sfull = smem_u32(bars), b_pready = b_sfull + 8, b_pfree = b_pready + 8, b_ofull = b_pfree + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+    // bars: s_full, o_full, p_ready[2], p_free[2] (one pair per P buffer), then the TMEM base address
+    const uint32_t b_sfull = smem_u32(bars), b_ofull = b_sfull + 8, b_pready = b_sfull + 16, b_pfree = b_sfull + 32;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
     __shared__ int kj_s[2][AT_MAXK];
     __shared__ uint8_t tok_s[2][AT_MAXK + 64];
     __shared__ int nk_s[2];
@@ -153,9 +157,11 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
 
     if (threadIdx.x == 0) {
         mbar_init(b_sfull, 1);
-        mbar_init(b_pready, Cfg::NROW);
-        mbar_init(b_pfree, 1);
         mbar_init(b_ofull, 1);
+        mbar_init(b_pready, Cfg::NROW);
+        mbar_init(b_pready + 8, Cfg::NROW);
+        mbar_init(b_pfree, 1);
+        mbar_init(b_pfree + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < QN_D) {
@@ -180,8 +186,9 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // phase bits: s_full and o_full complete once per item, p_ready n_slices times, p_free n_slices - 1 times
-    uint32_t ph_s = 0, ph_o = 0, ph_pready = 0, ph_pfree = 0;
+    // s_full and o_full complete once per item; p_ready[b & 1] and p_free[b & 1] once per 32-key block b, so their
+    // phase is the running count of blocks of that parity
+    uint32_t ph_s = 0, ph_o = 0, done0 = 0, done1 = 0;
     int buf = 0;
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
@@ -193,7 +200,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         const bool all_masked = nk_s[buf] == 0;
         const int nk = all_masked ? L : nk_s[buf];
         const int nk16 = (nk + 15) & ~15;
-        const int n_slices = (nk16 + 63) >> 6;
+        const int n_blocks = (nk16 + 31) >> 5;           // 32-key blocks of P, alternating between two buffers
 
         // ---- stage Q' (this tile's rows) and K' (the valid keys): cp.async 16-byte chunks into swizzled positions,
         // rows outside the state zero-filled through the src-size operand
@@ -239,11 +246,11 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             // O's B operand: the V rows as staged, [key][64 ch], read as an MN-major operand (instruction descriptor bit 16):
             // 8-key groups 1024 bytes apart, 16 keys = 2048 bytes per k-step - no transpose anywhere
             const uint32_t idesc_o = make_idesc_f16(AT_M, QN_D) | (1u << 16);
-            const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH)), dql = make_smem_desc(smem_u32(sm + OFF_QL));
             const uint32_t ds = tmem_base + COL_S, dout = tmem_base + COL_O;
             if (lane == 0) {
                 tc_fence_after();
                 const uint64_t dkh = make_smem_desc(smem_u32(sm + OFF_KH)), dkl = make_smem_desc(smem_u32(sm + OFF_KL));
+                const uint64_t dqh = make_smem_desc(smem_u32(sm + OFF_QH)), dql = make_smem_desc(smem_u32(sm + OFF_QL));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {          // S = Q' K'^T : 4 k-steps x (lo.hi, hi.lo, hi.hi)
                     umma_f16(ds, dql + 2 * ks, dkh + 2 * ks, idesc_s, ks != 0);
@@ -258,21 +265,22 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 warp_item_tokens(net, tok_in, active, next / n_tiles, L, lane, tok_s[buf ^ 1], kj_s[buf ^ 1],
                                  &nk_s[buf ^ 1]);
             if (lane == 0) {
-                uint32_t php = ph_pready;
-                for (int sl = 0; sl < n_slices; ++sl) {   // O += P(slice) V(slice); P lives where Q' was, V^T where K' was
-                    const int ksteps = min(4, (nk16 - 64 * sl) >> 4);
-                    mbar_wait(b_pready, php);
-                    php ^= 1;
+                for (int b = 0; b < n_blocks; ++b) {      // O += P(block) V(block): P in the halves of the Q' buffer (64-byte
+                    const int pb = b & 1;                 // swizzled rows), V rows where K' was
+                    const int ksteps = min(2, (nk16 - 32 * b) >> 4);
+                    mbar_wait(b_pready + 8 * pb, ((pb ? done1 : done0) + (b >> 1)) & 1);
                     tc_fence_after();
-                    const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_KH + sl * AT_SLICE_V));
-                    const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_KL + sl * AT_SLICE_V));
+                    const uint64_t dph = make_smem_desc(smem_u32(sm + OFF_QH + pb * AT_TILE_Q), true);
+                    const uint64_t dpl = make_smem_desc(smem_u32(sm + OFF_QH + pb * AT_TILE_Q + AT_TILE_Q / 2), true);
+                    const uint64_t dvh = make_smem_desc(smem_u32(sm + OFF_KH + b * 32 * 128));
+                    const uint64_t dvl = make_smem_desc(smem_u32(sm + OFF_KL + b * 32 * 128));
                     for (int ks = 0; ks < ksteps; ++ks) {                       // descriptor addresses count 16-byte units
-                        umma_f16(dout, dql + 2 * ks, dvh + 128 * ks, idesc_o, (sl | ks) != 0);
-                        umma_f16(dout, dqh + 2 * ks, dvl + 128 * ks, idesc_o, 1u);
-                        umma_f16(dout, dqh + 2 * ks, dvh + 128 * ks, idesc_o, 1u);
+                        umma_f16(dout, dpl + 2 * ks, dvh + 128 * ks, idesc_o, (b | ks) != 0);
+                        umma_f16(dout, dph + 2 * ks, dvl + 128 * ks, idesc_o, 1u);
+                        umma_f16(dout, dph + 2 * ks, dvh + 128 * ks, idesc_o, 1u);
                     }
-                    if (sl + 1 < n_slices) umma_commit(b_pfree);       // the P tile may be overwritten
-                    else umma_commit(b_ofull);                          // O complete
+                    umma_commit(b_pfree + 8 * pb);                              // this P buffer may be overwritten
+                    if (b + 1 == n_blocks) umma_commit(b_ofull);                // O complete
                 }
             }
         } else if (is_row) {
@@ -321,16 +329,16 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             const float mxs = mx * sc;
             asm volatile("cp.async.wait_all;" ::: "memory");             // V rows: published by the fence before the first arrive
             float lsum = 0.f;
-            for (int sl = 0; sl < n_slices; ++sl) {
-                if (sl > 0) {                             // the previous slice's MMAs must have read the P tile
-                    mbar_wait(b_pfree, ph_pfree);
-                    ph_pfree ^= 1;
-                }
-                const int c0 = 64 * sl + 32 * h;          // this thread's 32 keys of the slice: chunks 4h .. 4h+3
+            for (int b = 0; b < n_blocks; ++b) {
+                const int pb = b & 1;
+                if (b >= 2)                               // block b-2's MMAs must have read this P buffer
+                    mbar_wait(b_pfree + 8 * pb, ((pb ? done1 : done0) + (b >> 1) - 1) & 1);
+                const int c0 = 32 * b + 16 * h;           // this thread's 16 keys of the block: chunks 2h, 2h+1
                 if (warp_live && c0 < nk16) {
-                    uint32_t v[32];                       // columns beyond nk16 hold stale accumulator data: never used
-                    tmem_ld32(lane_addr + COL_S + c0, v);
+                    uint32_t v[16];
+                    tmem_ld16(lane_addr + COL_S + c0, v);
                     tmem_ld_wait();
+                    uint8_t *pbase = sm + OFF_QH + pb * AT_TILE_Q;
                     auto chunk = [&](int c, auto masked) {    // one 16-byte chunk = 8 keys
                         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -349,23 +357,21 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                             hi[u] = *reinterpret_cast<const uint32_t *>(&hh);
                             lo[u] = *reinterpret_cast<const uint32_t *>(&ll);
                         }
-                        *reinterpret_cast<uint4 *>(sm + OFF_QH + sw128(r, 4 * h + c)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(sm + OFF_QL + sw128(r, 4 * h + c)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        const uint32_t off = sw64(r, 2 * h + c);
+                        *reinterpret_cast<uint4 *>(pbase + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(pbase + AT_TILE_Q / 2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     };
-                    if (c0 + 32 <= nk) {                  // the common case: all 32 keys are real
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) chunk(c, std::false_type{});
+                    if (c0 + 16 <= nk) {                  // the common case: all 16 keys are real
+                        chunk(0, std::false_type{});
+                        chunk(1, std::false_type{});
                     } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (c0 + 8 * c >= nk16) break;
-                            chunk(c, std::true_type{});
-                        }
+                        chunk(0, std::true_type{});
+                        chunk(1, std::true_type{});
                     }
                 }
-                fence_async_smem();                       // also publishes this thread's share of V^T before the first arrive
+                fence_async_smem();                       // also publishes this thread's share of the V rows (first arrive)
                 tc_fence_before();
-                mbar_arrive(b_pready);
+                mbar_arrive(b_pready + 8 * pb);
             }
             // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the row's 64 channels; this thread owns
             // channels 32h .. 32h+31 and trades the partial sums with its partner
@@ -443,8 +449,8 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         // per-item phase flips for the barriers a thread did not wait on itself
         ph_s ^= 1;
         ph_o ^= 1;
-        if (n_slices & 1) ph_pready ^= 1;
-        if (!is_row && ((n_slices - 1) & 1)) ph_pfree ^= 1;
+        done0 += (n_blocks + 1) >> 1;
+        done1 += n_blocks >> 1;
     }
     __syncthreads();
     if (is_mma) {
