@@ -215,17 +215,6 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + sw128(r, c))),
                          "l"(net.Ql + src), "r"(nbytes) : "memory");
         }
-        if (Cfg::XSTAGE) {
-            for (int idx = threadIdx.x; idx < TR * 16; idx += Cfg::THREADS) {
-                const int r = idx >> 4, c = idx & 15;
-                const int i = t * TR + r;
-                const int ii = i < L ? i : 0;
-                const uint32_t nbytes = i < L ? 16u : 0u;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                 smem_u32(sm + OFF_XR + r * 256 + ((c ^ (r & 7)) << 4))),
-                             "l"(net.X + ((size_t)tok[ii] * L + ii) * QN_D + c * 4), "r"(nbytes) : "memory");
-            }
-        }
         for (int idx = threadIdx.x; idx < nk16 * 8; idx += Cfg::THREADS) {
             const int k = idx >> 3, c = idx & 7;
             const int j = kj[k < nk ? k : 0];
@@ -293,6 +282,17 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             const float sc = all_masked ? 0.f : net.s_inv_scale;           // fully masked: every p = ex2(0) = 1
             auto row_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NROW) : "memory"); };
 
+            if (Cfg::XSTAGE) {                            // the residual rows: off the path to S, waited for with the V rows
+                for (int idx = rt; idx < TR * 16; idx += Cfg::NROW) {
+                    const int xr = idx >> 4, c = idx & 15;
+                    const int xi = t * TR + xr;
+                    const int ii = xi < L ? xi : 0;
+                    const uint32_t nbytes = xi < L ? 16u : 0u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                                     smem_u32(sm + OFF_XR + xr * 256 + ((c ^ (xr & 7)) << 4))),
+                                 "l"(net.X + ((size_t)tok[ii] * L + ii) * QN_D + c * 4), "r"(nbytes) : "memory");
+                }
+            }
             mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
             tc_fence_after();
             for (int idx = rt; idx < nk16 * 8; idx += Cfg::NROW) {         // V rows into the K buffer, exactly like the K'
@@ -376,20 +376,20 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             // ---- epilogue: O / sum * 2^-sv + residual, LayerNorm over the row's 64 channels; this thread owns
             // channels 32h .. 32h+31 and trades the partial sums with its partner
             float y[32];
+            xch[h][1][r] = lsum;
+            row_barrier();                                // also: every thread's share of the residual rows has landed
+            const float inv = net.vf_inv_scale / (lsum + xch[h ^ 1][1][r]);
             if (warp_live) {
                 const int ii = i < L ? i : 0;
                 const float4 *x4 = reinterpret_cast<const float4 *>(net.X + ((size_t)tok[ii] * L + ii) * QN_D + 32 * h);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {             // the residual row (global loads fly while the last MMAs finish)
+                for (int c = 0; c < 8; ++c) {
                     const float4 x = Cfg::XSTAGE ? *reinterpret_cast<const float4 *>(sm + OFF_XR + r * 256 +
                                                                                      (((8 * h + c) ^ (r & 7)) << 4))
                                                  : __ldg(x4 + c);
                     y[4 * c + 0] = x.x; y[4 * c + 1] = x.y; y[4 * c + 2] = x.z; y[4 * c + 3] = x.w;
                 }
             }
-            xch[h][1][r] = lsum;
-            row_barrier();
-            const float inv = net.vf_inv_scale / (lsum + xch[h ^ 1][1][r]);
             float s1 = 0.f;
             if (warp_live) {
                 mbar_wait(b_ofull, ph_o);
