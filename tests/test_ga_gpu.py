@@ -372,6 +372,9 @@ def test_qnet_tc_encoder_other_tilings(gpu, monkeypatch, rows, cols):
             s[pos:pos + rem] = rng.integers(1, 5, rem)
             s[pos + rem] = 5
             pos += rem + 1
+    for s in states[200:260]:                                   # padding between tokens: only reachable through predict()
+        s[rng.integers(0, L, 12)] = 0                           # with hand-made states; takes the kernel's gather path
+    states[260:264] = 0                                         # fully masked states
     max_value = cols * rows * (rows - 1) / 2 * 4
     net = QNet(sd, rows, cols)
     monkeypatch.setenv("GAD_QNET_ENCODER", "fa")
