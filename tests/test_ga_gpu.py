@@ -709,3 +709,44 @@ def test_benchmark_callers_thin_host_versions(gpu, weight_files, cfg, datasets_j
     answers = iter(["x", "7", "2"])
     monkeypatch.setattr("builtins.input", lambda _prompt: next(answers))
     assert utils.display_menu() == 2
+
+
+def test_training_loop_end_to_end(gpu, monkeypatch, tmp_path):
+    """DPAMSA.main.train (reference main.py:95-235) on a tiny set: episodes run through the device-scored environment,
+    the optimiser steps once the replay memory holds a batch, the saved file loads back into the device Q-net, and
+    the frozen device copy of the freshly trained weights takes the same greedy decisions as the torch network in
+    eval mode."""
+    import types
+    import torch
+    import config
+    import DPAMSA.main as dmain
+    from DPAMSA.dqn import DQN
+    from DPAMSA.env import Environment
+    for k, v in {"MAX_EPISODE": 4, "BATCH_SIZE": 8, "REPLAY_MEMORY_SIZE": 32, "UPDATE_ITERATION": 4,
+                 "DECREMENT_ITERATION": 2, "ALPHA": 1e-4}.items():
+        monkeypatch.setattr(config, k, v)
+    monkeypatch.setattr(config, "RUNS_PATH", str(tmp_path / "runs"))
+    monkeypatch.setattr(config, "DPAMSA_WEIGHTS_PATH", str(tmp_path))
+    seqs = ["ACGTAGCT", "AGTCAGT", "ACGAGCT"]
+    mod = types.SimpleNamespace(file_name="unit_train.py", datasets=["set0"], set0=seqs)
+    random.seed(3)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    history = dmain.train(mod, model_path="unit_trained")
+    log = history["set0"]
+    assert len(log) == 4 and all(e["steps"] >= 8 for e in log)
+    assert any(e["loss"] > 0 for e in log) and all(np.isfinite(e["loss"]) for e in log)
+    assert log[-1]["epsilon"] == pytest.approx(config.EPSILON - 2 * config.DELTA)
+    assert os.path.isdir(os.path.join(str(tmp_path), "runs", "unit_train", "set0"))
+    # the file goes straight back into the generation loop's loader
+    env = Environment(seqs)
+    agent = DQN(env.action_number, env.row, env.max_len, env.max_len * env.max_reward)
+    agent.load("unit_trained")
+    state = env.reset()
+    q_dev = agent.q_values(state)
+    agent._ensure_training()                                   # torch copy of the same file, dropout off
+    agent.eval_net.eval()
+    with torch.no_grad():
+        q_torch = agent.eval_net(torch.LongTensor(state).unsqueeze(0).to(agent.train_device))[0].cpu().numpy()
+    assert np.allclose(q_dev, q_torch, rtol=1e-3, atol=1e-3 * agent.max_value * 1e-2)
+    assert int(agent.predict(state)[0]) == int(np.argmax(q_torch))
