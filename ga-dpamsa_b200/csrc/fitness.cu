@@ -325,7 +325,11 @@ int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int str
     long long blocks = (P + groups_per_block - 1) / groups_per_block;
     const long long cap = (long long)GAD_NUM_SMS * 8 * 4;          // 8 resident CTAs/SM, <=4 passes each
     if (blocks > cap) blocks = cap;
-    if (R >= 8)
+    static const int force_paired = [] {                            // tuning override: GAD_FITNESS_PAIRED=0|1
+        const char *e = getenv("GAD_FITNESS_PAIRED");
+        return e ? atoi(e) : -1;
+    }();
+    if (force_paired < 0 ? R >= 8 : force_paired != 0)
         fitness_kernel<GS, true><<<(unsigned)blocks, threads, 0, st>>>(boards, rowlen, P, R, stride, match, mismatch,
                                                                         gap, sp, em, al, max_al);
     else
