@@ -53,10 +53,8 @@ constexpr int OFF_XR = OFF_KL + AT_TILE_K;   // 81 920: the tile's residual rows
 constexpr int COL_S = 0, COL_O = 192;
 constexpr int TMEM_COLS = 256;
 
-// byte offset of the 16-byte chunk c of row r inside a K-major tile with 128-byte rows and 128B swizzle
-__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
-
-// the same for 64-byte rows with 64B swizzle (the P tiles: 32 keys per row)
+// K-major tiles with 128-byte rows and 128B swizzle keep the 16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4);
+// the same for 64-byte rows with 64B swizzle (the P tiles: 32 keys per row):
 __device__ __forceinline__ uint32_t sw64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ float fast_ex2(float x)
@@ -203,27 +201,41 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         const int n_blocks = (nk16 + 31) >> 5;           // 32-key blocks of P, alternating between two buffers
 
         // ---- stage Q' (this tile's rows) and K' (the valid keys): cp.async 16-byte chunks into swizzled positions,
-        // rows outside the state zero-filled through the src-size operand
-        for (int idx = threadIdx.x; idx < TR * 8; idx += Cfg::THREADS) {
-            const int r = idx >> 3, c = idx & 7;
-            const int i = t * TR + r;
-            const int ii = i < L ? i : 0;
-            const size_t src = ((size_t)tok[ii] * L + ii) * QN_D + c * 8;
-            const uint32_t nbytes = i < L ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QH + sw128(r, c))),
-                         "l"(net.Qh + src), "r"(nbytes) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_QL + sw128(r, c))),
-                         "l"(net.Ql + src), "r"(nbytes) : "memory");
-        }
-        for (int idx = threadIdx.x; idx < nk16 * 8; idx += Cfg::THREADS) {
-            const int k = idx >> 3, c = idx & 7;
-            const int j = kj[k < nk ? k : 0];
-            const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
-            const uint32_t nbytes = k < nk ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KH + sw128(k, c))),
-                         "l"(net.Kh + src), "r"(nbytes) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KL + sw128(k, c))),
-                         "l"(net.Kl + src), "r"(nbytes) : "memory");
+        // rows outside the state zero-filled through the src-size operand. Row thread rt owns chunk rt & 7 of rows
+        // rt/8, rt/8 + NROW/8, ... : NROW/8 is a multiple of 8, so its swizzled chunk position is one constant and a
+        // row's table offset, computed once, serves the K' copy now and the V copy of the same key later.
+        constexpr int KIT = (AT_MAXK * 8 + Cfg::NROW - 1) / Cfg::NROW, RSTEP = Cfg::NROW / 8;
+        uint32_t koff[KIT];
+        const int st_c = (h * TR + q * 32 + lane) & 7, st_r0 = (h * TR + q * 32 + lane) >> 3;
+        const uint32_t st_swz = (uint32_t)((st_c ^ (st_r0 & 7)) << 4);
+        if (is_row) {
+#pragma unroll
+            for (int n = 0; n < TR * 8 / Cfg::NROW; ++n) {
+                const int r = st_r0 + RSTEP * n;
+                const int i = t * TR + r;
+                const int ii = i < L ? i : 0;
+                const uint32_t off = ((uint32_t)tok[ii] * L + ii) * QN_D + st_c * 8;
+                const uint32_t nbytes = i < L ? 16u : 0u;
+                const uint32_t dst = smem_u32(sm + OFF_QH) + r * 128 + st_swz;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(net.Qh + off), "r"(nbytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + AT_TILE_Q), "l"(net.Ql + off), "r"(nbytes)
+                             : "memory");
+            }
+#pragma unroll
+            for (int n = 0; n < KIT; ++n) {
+                const int k = st_r0 + RSTEP * n;
+                koff[n] = 0u;
+                if (k < nk16) {
+                    const int j = kj[k < nk ? k : 0];
+                    koff[n] = ((uint32_t)tok[j] * L + j) * QN_D + st_c * 8;
+                    const uint32_t nbytes = k < nk ? 16u : 0u;
+                    const uint32_t dst = smem_u32(sm + OFF_KH) + k * 128 + st_swz;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(net.Kh + koff[n]), "r"(nbytes)
+                                 : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + AT_TILE_K), "l"(net.Kl + koff[n]),
+                                 "r"(nbytes) : "memory");
+                }
+            }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -295,15 +307,17 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
             }
             mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
             tc_fence_after();
-            for (int idx = rt; idx < nk16 * 8; idx += Cfg::NROW) {         // V rows into the K buffer, exactly like the K'
-                const int k = idx >> 3, c = idx & 7;                        // rows; they land while the row maxima are computed
-                const int j = kj[k < nk ? k : 0];
-                const size_t src = ((size_t)tok[j] * L + j) * QN_D + c * 8;
-                const uint32_t nbytes = k < nk ? 16u : 0u;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KH + sw128(k, c))),
-                             "l"(net.VFh + src), "r"(nbytes) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(sm + OFF_KL + sw128(k, c))),
-                             "l"(net.VFl + src), "r"(nbytes) : "memory");
+#pragma unroll
+            for (int n = 0; n < KIT; ++n) {               // V rows over the K' rows, same thread -> (key, chunk) mapping and
+                const int k = st_r0 + RSTEP * n;          // table offsets; they land while the row maxima are computed
+                if (k < nk16) {
+                    const uint32_t nbytes = k < nk ? 16u : 0u;
+                    const uint32_t dst = smem_u32(sm + OFF_KH) + k * 128 + st_swz;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(net.VFh + koff[n]), "r"(nbytes)
+                                 : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + AT_TILE_K), "l"(net.VFl + koff[n]),
+                                 "r"(nbytes) : "memory");
+                }
             }
 
             // pass 1: row maximum over the valid keys; this thread reads the 32-column blocks h, h + 2, h + 4
