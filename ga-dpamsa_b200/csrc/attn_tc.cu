@@ -205,7 +205,7 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         // rt/8, rt/8 + NROW/8, ... : NROW/8 is a multiple of 8, so its swizzled chunk position is one constant and a
         // row's table offset, computed once, serves the K' copy now and the V copy of the same key later.
         constexpr int KIT = (AT_MAXK * 8 + Cfg::NROW - 1) / Cfg::NROW, RSTEP = Cfg::NROW / 8;
-        uint32_t koff[KIT];
+        uint32_t koff[KIT], qrow[TR * 8 / Cfg::NROW];     // table offsets (elements) of this thread's key / query rows
         const int st_c = (h * TR + q * 32 + lane) & 7, st_r0 = (h * TR + q * 32 + lane) >> 3;
         const uint32_t st_swz = (uint32_t)((st_c ^ (st_r0 & 7)) << 4);
         if (is_row) {
@@ -214,7 +214,8 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
                 const int r = st_r0 + RSTEP * n;
                 const int i = t * TR + r;
                 const int ii = i < L ? i : 0;
-                const uint32_t off = ((uint32_t)tok[ii] * L + ii) * QN_D + st_c * 8;
+                qrow[n] = ((uint32_t)tok[ii] * L + ii) * QN_D;
+                const uint32_t off = qrow[n] + st_c * 8;
                 const uint32_t nbytes = i < L ? 16u : 0u;
                 const uint32_t dst = smem_u32(sm + OFF_QH) + r * 128 + st_swz;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(net.Qh + off), "r"(nbytes) : "memory");
@@ -287,22 +288,22 @@ encode_tc_kernel(const gad_qnet net, const uint8_t *__restrict__ tok_in, const i
         } else if (is_row) {
             // ============ row threads: two per query row, each owns every other 32-column block ============
             const int r = q * 32 + lane;                  // row inside the tile = TMEM lane
-            const int rt = h * TR + r;                    // index among the row threads
             const int i = t * TR + r;                     // query position
             const bool warp_live = t * TR + q * 32 < L;   // warps past the state's last row only stage and arrive
             const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
             const float sc = all_masked ? 0.f : net.s_inv_scale;           // fully masked: every p = ex2(0) = 1
             auto row_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NROW) : "memory"); };
 
-            if (Cfg::XSTAGE) {                            // the residual rows: off the path to S, waited for with the V rows
-                for (int idx = rt; idx < TR * 16; idx += Cfg::NROW) {
-                    const int xr = idx >> 4, c = idx & 15;
-                    const int xi = t * TR + xr;
-                    const int ii = xi < L ? xi : 0;
-                    const uint32_t nbytes = xi < L ? 16u : 0u;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
-                                     smem_u32(sm + OFF_XR + xr * 256 + ((c ^ (xr & 7)) << 4))),
-                                 "l"(net.X + ((size_t)tok[ii] * L + ii) * QN_D + c * 4), "r"(nbytes) : "memory");
+            if (Cfg::XSTAGE) {                            // the residual rows: off the path to S, waited for with the V rows.
+#pragma unroll
+                for (int n = 0; n < TR * 8 / Cfg::NROW; ++n) {             // Same rows as this thread's Q' rows: chunks c, c + 8
+                    const int xr = st_r0 + RSTEP * n;
+                    const uint32_t nbytes = t * TR + xr < L ? 16u : 0u;
+                    const uint32_t dst = smem_u32(sm + OFF_XR) + xr * 256 + st_swz;
+                    const float *src = net.X + qrow[n] + st_c * 4;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 128), "l"(src + 32), "r"(nbytes)
+                                 : "memory");
                 }
             }
             mbar_wait(b_sfull, ph_s);                     // S complete: Q' and K' are dead, their buffers are free
