@@ -1483,7 +1483,7 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
         rc = GAD_ECUDA;
     }
     if (rc) {
-        delete q;
+        gad_qnet_destroy(q);                               // frees whatever was allocated before the failure
         return rc;
     }
     *out = q;

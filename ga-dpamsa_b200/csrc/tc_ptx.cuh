@@ -27,10 +27,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)        // suspend-time hint (ns): sleep in hardware, not in a spin loop
             : "memory");
         return done != 0;
     };
