@@ -379,8 +379,13 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
         }
         if world > 1:
             out["collective_bytes_received_per_generation_rank0"] = g.comm_bytes / (n_warm + n_gen)
+            peer = bool(getattr(g.backend, "peer_ready", False))
+            out["exchange"] = "peer" if peer else "allgather"
             out["parallelism"] = ("population sharded by logical index over %d ranks; per fitness pass an NCCL all-gather "
-                                  "of 32 B/individual, per generation an all-gather of the survivors' boards" % world)
+                                  "of the scores, per generation %s" % (world, (
+                                      "the crossover kernel reads each child's parent rows from the owning rank's "
+                                      "population over NVLink (symmetric memory)") if peer else
+                                      "an NCCL all-gather of the survivors' boards"))
         return out
     finally:
         for k, v in saved.items():
