@@ -16,6 +16,8 @@
 //                             to the stage's "empty" barrier and, per tile, to the accumulator's "full" barrier
 //     warps 2-9 epilogue      tcgen05.ld 32x32b from their TMEM lane quarter and column half into fp32 registers
 //                             per chunk; after the last chunk scale + bias + LeakyReLU and store
+// Tail: tiles are dealt round-robin; a last partial round that fits twice on the grid is dealt as column halves
+// (see `split` in the kernel).
 // Accumulation: tcgen05 adds each K=16 product block into the fp32 TMEM accumulator with truncation, a
 // bias that grows linearly with the number of accumulations (measured: 1e-4 relative after the 2232
 // MMAs of one 6x30 tile, 50x worse than fp32). The k-loop is therefore cut into chunks of CHUNK_KB
@@ -68,7 +70,7 @@ template <int BN, bool SPLIT_OUT, bool FUSED = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const float *__restrict__ bias, float out_scale, void *__restrict__ Cout, int ldc, int lo_offset,
-                      const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky)
+                      const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky, int tail_split)
 {
     using C_ = Cfg<BN, FUSED>;
     extern __shared__ uint8_t smem_raw[];
@@ -87,6 +89,28 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // k-blocks and chunk length of one tile in this kernel's own units
     const int total_kb = FUSED ? K / BKF : 3 * kblocks;
     constexpr int CHUNK = FUSED ? CHUNK_KB_F : CHUNK_KB;
+    // Wave quantisation: tiles are dealt round-robin to gridDim.x persistent CTAs, so a last, partial round of
+    // t_tail tiles costs a whole tile time on a few CTAs while the rest idle (l1 at 16 384 rows: 640 tiles on 148 CTAs
+    // = 4.32 rounds). When the partial round fits twice, its tiles are cut into two column halves and dealt to twice as
+    // many CTAs: a half unit loads the same operand tiles but issues MMAs of N = HN over B rows [0, HN) or
+    // [BN - HN, BN) and its epilogue keeps BN/2 of those columns. work unit u < t_full: tile u; otherwise tile
+    // t_full + (u - t_full) / 2, half (u - t_full) & 1.
+    constexpr bool CAN_SPLIT = FUSED && (BN / 2) % 8 == 0 && ((BN / 2 + 15) / 16 * 16) % 8 == 0;
+    constexpr int HN = (BN / 2 + 15) / 16 * 16;                   // UMMA N of a half unit (208 -> 112)
+    const long long t_full = (tiles / gridDim.x) * gridDim.x, t_tail = tiles - t_full;
+    const bool split = CAN_SPLIT && tail_split && t_tail > 0 && 2 * t_tail <= (long long)gridDim.x;
+    const long long units = split ? t_full + 2 * t_tail : tiles;
+    auto decode = [&](long long u, int &m_blk, int &n_blk) {      // returns -1 for a whole tile, else the column half
+        long long t = u;
+        int hsel = -1;
+        if (split && u >= t_full) {
+            t = t_full + ((u - t_full) >> 1);
+            hsel = (int)((u - t_full) & 1);
+        }
+        m_blk = (int)(t / tiles_n);
+        n_blk = (int)(t % tiles_n);
+        return hsel;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C_::STAGES; ++s) {
@@ -114,8 +138,9 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int m_blk = (int)(t / tiles_n), n_blk = (int)(t % tiles_n);
+            for (long long t = blockIdx.x; t < units; t += gridDim.x) {
+                int m_blk, n_blk;
+                decode(t, m_blk, n_blk);
                 if constexpr (FUSED) {
                     for (int kb = 0; kb < total_kb; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -156,7 +181,12 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             long long chunk = 0;                                                  // running chunk counter (buffer = chunk & 1)
-            for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (long long t = blockIdx.x; t < units; t += gridDim.x) {
+                int m_blk, n_blk;
+                const int hsel = decode(t, m_blk, n_blk);
+                const uint32_t idesc_u = hsel < 0 ? idesc : make_idesc(HN);
+                // B rows of a half unit start at row 0 or BN - HN: whole swizzle atoms of 8 rows (64-byte rows when fused)
+                const uint32_t b_skip = hsel > 0 ? (uint32_t)((BN - HN) * (FUSED ? BKF : BK) * 2) : 0u;
                 for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK, ++chunk) {
                     const int as = (int)(chunk & 1);
                     mbar_wait(tempty0 + 8 * as, (uint32_t)((chunk >> 1) & 1) ^ 1);    // epilogue has drained this buffer
@@ -170,12 +200,12 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if constexpr (FUSED) {
                             const uint32_t sal = sa + C_::A_BYTES, sb = sal + C_::A_BYTES, sbl = sb + C_::B_BYTES;
                             const uint64_t dah = make_smem_desc(sa, true), dal = make_smem_desc(sal, true);
-                            const uint64_t dbh = make_smem_desc(sb, true), dbl = make_smem_desc(sbl, true);
+                            const uint64_t dbh = make_smem_desc(sb + b_skip, true), dbl = make_smem_desc(sbl + b_skip, true);
 #pragma unroll
                             for (int k = 0; k < BKF / UMMA_K; ++k) {     // small terms first, hi.hi last
-                                umma_f16(tmem_d, dal + 2 * k, dbh + 2 * k, idesc, (kb > kb0) || k != 0);
-                                umma_f16(tmem_d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
-                                umma_f16(tmem_d, dah + 2 * k, dbh + 2 * k, idesc, 1u);
+                                umma_f16(tmem_d, dal + 2 * k, dbh + 2 * k, idesc_u, (kb > kb0) || k != 0);
+                                umma_f16(tmem_d, dah + 2 * k, dbl + 2 * k, idesc_u, 1u);
+                                umma_f16(tmem_d, dah + 2 * k, dbh + 2 * k, idesc_u, 1u);
                             }
                         } else {
                             const uint32_t sb = sa + C_::A_BYTES;
@@ -203,8 +233,18 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         static_assert(HALF % 8 == 0, "BN/2 must be a multiple of 8");
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         long long chunk = 0;
-        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int m_blk = (int)(t / tiles_n), n_blk = (int)(t % tiles_n);
+        for (long long t = blockIdx.x; t < units; t += gridDim.x) {
+            int m_blk, n_blk;
+            const int hsel = decode(t, m_blk, n_blk);
+            // columns of this warp: TMEM columns [col_t, col_t + ncols) of the accumulator = tile columns [col_o, ...)
+            int col_t = half * HALF, col_o = half * HALF, ncols = HALF;
+            if (hsel >= 0) {                               // half unit: BN/2 useful columns, dealt 8-aligned to the two warps
+                constexpr int FIRST = (HALF / 2 + 7) / 8 * 8;
+                const int sub = half ? FIRST : 0;
+                ncols = half ? HALF - FIRST : FIRST;
+                col_o = hsel * HALF + sub;                 // tile column
+                col_t = col_o - (hsel ? BN - HN : 0);      // accumulator column: the unit's B rows start at BN - HN
+            }
             float acc[HALF];
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
@@ -212,9 +252,10 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const int as = (int)(chunk & 1);
                 mbar_wait(tfull0 + 8 * as, (uint32_t)((chunk >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_COLS + half * HALF;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_COLS + col_t;
 #pragma unroll
                 for (int g = 0; g < NLD; ++g) {
+                    if (8 * g >= ncols) break;
                     uint32_t r[8];
                     tmem_ld8(taddr + 8 * g, r);
                     tmem_ld_wait();
@@ -226,10 +267,11 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (lane == 0) mbar_arrive(tempty0 + 8 * as);
             }
             const long long row = (long long)m_blk * BM + quarter * 32 + lane;
-            const int n0 = n_blk * BN + half * HALF;
+            const int n0 = n_blk * BN + col_o;
             if (row < M) {
 #pragma unroll
                 for (int j = 0; j < HALF; j += 8) {
+                    if (j >= ncols) break;
                     float x[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -387,20 +429,25 @@ int run_bn(const TcLayer *L, const float *d_bias, void *d_out, int ldc, int lo_o
 {
     const long long tiles = ((m_max + BM - 1) / BM) * ((L->N + BN - 1) / BN);
     if (tiles == 0) return GAD_OK;
-    const unsigned grid = (unsigned)(tiles < GAD_NUM_SMS ? tiles : GAD_NUM_SMS);
+    static const int tail_split = [] {                            // A/B switch: GAD_L1_TAILSPLIT=0 keeps whole tiles only
+        const char *e = getenv("GAD_L1_TAILSPLIT");
+        return e ? atoi(e) : 1;
+    }();
+    const long long want = L->fused && tail_split ? 2 * tiles : tiles;       // half units need up to two CTAs per tile
+    const unsigned grid = (unsigned)(want < GAD_NUM_SMS ? want : GAD_NUM_SMS);
     const CUtensorMap &ma = *(const CUtensorMap *)L->map_a, &mb = *(const CUtensorMap *)L->map_b;
     if (L->fused && split_out)
         gemm_split_f16_kernel<BN, true, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     else if (L->fused)
         gemm_split_f16_kernel<BN, false, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     else if (split_out)
         gemm_split_f16_kernel<BN, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     else
         gemm_split_f16_kernel<BN, false><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky);
+            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
