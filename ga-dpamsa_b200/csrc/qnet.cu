@@ -11,10 +11,12 @@
 //         X [6][L][64]      first-LayerNorm output (also the residual)
 //         T [6][L][6][L]    attention logit  (x_i Wq^T / sqrt(dk)) . (x_j Wk^T)  for every pair
 //         VF[6][L][64]      (x_j Wv^T) Wfc^T  - the value projection with the output projection folded in
-//     so one forward needs no QKV or fc GEMM: logits are gathers from T (L2-resident), the
-//     attention output is softmax(T) . VF.
-//   * what remains dense is l1 (L*64 -> h1, ~95 % of the weights), l2 and l3: l1/l2 run as one tiled
-//     GEMM over all active episodes; l3 + tanh + argmax + Environment.step are fused in one kernel.
+//     so one forward needs no QKV or fc GEMM. The fast encoders recompute the logits on the tensor cores
+//     from split-fp16 row tables (Q' = x M log2e, K' = x, V = VF): attn_tc.cu (tcgen05, the default for windows
+//     of 16..192 positions) and encode_fa_kernel below (mma.sync); the fallback encoders gather logits from T.
+//   * what remains dense is l1 (L*64 -> h1, ~95 % of the weights), l2 and l3: tcgen05 GEMMs over all active
+//     episodes (gemm_tc.cu; fp32 SIMT tiles below as the fallback); tanh + argmax + Environment.step are fused
+//     in one kernel.
 //   * episodes run in lock-step on device with an active list that shrinks as episodes finish; the
 //     host only polls the active count.
 #include "qnet.cuh"
