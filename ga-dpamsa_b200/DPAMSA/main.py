@@ -27,7 +27,34 @@ def output_parameters():
     print(f"Scores: match {config.MATCH_REWARD}, mismatch {config.MISMATCH_PENALTY}, gap {config.GAP_PENALTY}\n")
 
 
-def inference(dataset=None, start=0, end=-1, model_path=INFERENCE_MODEL, truncate_file=True):
+def _device_episodes(groups, model_path):
+    """Greedy full-board episodes of many sequence sets at once: every set whose
+    sequences all have the same length is a board whose agent window is the whole board, so the lock-step device
+    episodes of the mutation phase (gad_mutate: Environment.reset / step / padding, DQN.predict) align all sets of one
+    shape in a single call. groups: {(rows, cols): [(name, seqs), ...]}. Returns {name: aligned rows as code lists}."""
+    import torch
+    from DPAMSA.dqn import load_qnet
+    from DPAMSA.env import nucleotides_map
+    from population import DevicePopulation
+    out = {}
+    for (rows, cols), items in groups.items():
+        boards = [[[nucleotides_map[ch] for ch in seq] for seq in seqs] for _, seqs in items]
+        qnet = load_qnet(model_path, rows, cols)
+        pop = DevicePopulation.from_lists(boards, device=config.DEVICE)
+        n = len(boards)
+        idx = torch.arange(n, dtype=torch.int32, device=pop.device)
+        tile = torch.zeros((n, 2), dtype=torch.int32, device=pop.device)
+        max_reward = rows * (rows - 1) / 2 * config.MATCH_REWARD                   # env.py:79
+        pop.mutate(qnet, idx, tile, cols * max_reward, width=cols)
+        for (name, _), aligned in zip(items, pop.to_lists()):
+            out[name] = aligned
+    return out
+
+
+def inference(dataset=None, start=0, end=-1, model_path=INFERENCE_MODEL, truncate_file=True, batched=True):
+    """main.py:238-310. ``batched`` (default) aligns all equal-length sets of one shape in one lock-step device run;
+    sets with sequences of different lengths, and ``batched=False``, take the reference's one-step-at-a-time loop.
+    Both give the same alignments."""
     if dataset is None:
         raise ValueError("no dataset module given")
     output_parameters()
@@ -40,18 +67,30 @@ def inference(dataset=None, start=0, end=-1, model_path=INFERENCE_MODEL, truncat
         open(report_file_name, 'w').close()
         with open(csv_file_name, 'w', newline='') as fh:
             csv.writer(fh).writerow(utils.CSV_COLUMNS_QTY_FIRST)
-    for name in dataset.datasets[start:end if end != -1 else len(dataset.datasets)]:
-        if not hasattr(dataset, name):
-            continue
+    names = [n for n in dataset.datasets[start:end if end != -1 else len(dataset.datasets)] if hasattr(dataset, n)]
+    done_on_device = {}
+    if batched:
+        groups = {}
+        for name in names:
+            seqs = getattr(dataset, name)
+            lengths = {len(seq) for seq in seqs}
+            if len(seqs) >= 1 and len(lengths) == 1 and min(lengths) >= 1:
+                groups.setdefault((len(seqs), lengths.pop()), []).append((name, seqs))
+        done_on_device = _device_episodes(groups, model_path)
+    for name in names:
         env = Environment(getattr(dataset, name))
-        agent = DQN(env.action_number, env.row, env.max_len, env.max_len * env.max_reward)
-        agent.load(model_path)
-        state = env.reset()
-        while True:
-            _, state, done = env.step(agent.predict(state))
-            if done == 0:
-                break
-        env.padding()
+        if name in done_on_device:
+            env.aligned = done_on_device[name]
+            env.not_aligned = [[] for _ in range(env.row)]
+        else:
+            agent = DQN(env.action_number, env.row, env.max_len, env.max_len * env.max_reward)
+            agent.load(model_path)
+            state = env.reset()
+            while True:
+                _, state, done = env.step(agent.predict(state))
+                if done == 0:
+                    break
+            env.padding()
         m = utils.calculate_metrics(env)
         with open(report_file_name, 'a') as fh:
             fh.write(utils.report_block(name, m, env.get_alignment()))

@@ -750,3 +750,24 @@ def test_training_loop_end_to_end(gpu, monkeypatch, tmp_path):
         q_torch = agent.eval_net(torch.LongTensor(state).unsqueeze(0).to(agent.train_device))[0].cpu().numpy()
     assert np.allclose(q_dev, q_torch, rtol=1e-3, atol=1e-3 * agent.max_value * 1e-2)
     assert int(agent.predict(state)[0]) == int(np.argmax(q_torch))
+
+
+def test_dpamsa_inference_batched_equals_stepwise(gpu, weight_files, datasets_json):
+    """DPAMSA.main.inference: all equal-length sets of a module aligned in one lock-step device run give the very
+    report and CSV of the reference's one-step-at-a-time loop; a set with sequences of different lengths takes
+    that loop in both modes."""
+    import types
+    import DPAMSA.main as dmain
+    name, _ = weight_files[(3, 30)]
+    sets = datasets_json["synthetic_dataset_3x30bp"]
+    keys = list(sets)[:6]
+    data = {k: sets[k] for k in keys}
+    ragged = [sets[keys[0]][0], sets[keys[0]][1][:-2], sets[keys[0]][2][:-1]]     # 30, 28, 29 -> still a 3x30 model
+    data["ragged"] = ragged
+    mod = types.SimpleNamespace(file_name="unit_batched.py", datasets=keys[:3] + ["ragged"] + keys[3:], **data)
+    outs = []
+    for batched in (False, True):
+        report, csv_path = dmain.inference(mod, model_path=name, batched=batched)
+        outs.append((open(report).read(), open(csv_path).read()))
+    assert outs[0] == outs[1]
+    assert outs[0][0].count("File: ") == 7 and len(outs[0][1].strip().split("\n")) == 8
