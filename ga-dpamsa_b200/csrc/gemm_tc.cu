@@ -69,7 +69,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
 template <int BN, bool SPLIT_OUT, bool FUSED = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const float *__restrict__ bias, float out_scale, void *__restrict__ Cout, int ldc, int lo_offset,
+                      const __grid_constant__ CUtensorMap map_bh, const float *__restrict__ bias, float out_scale, void *__restrict__ Cout, int ldc, int lo_offset,
                       const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky, int tail_split)
 {
     using C_ = Cfg<BN, FUSED>;
@@ -92,8 +92,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // Wave quantisation: tiles are dealt round-robin to gridDim.x persistent CTAs, so a last, partial round of
     // t_tail tiles costs a whole tile time on a few CTAs while the rest idle (l1 at 16 384 rows: 640 tiles on 148 CTAs
     // = 4.32 rounds). When the partial round fits twice, its tiles are cut into two column halves and dealt to twice as
-    // many CTAs: a half unit loads the same operand tiles but issues MMAs of N = HN over B rows [0, HN) or
-    // [BN - HN, BN) and its epilogue keeps BN/2 of those columns. work unit u < t_full: tile u; otherwise tile
+    // many CTAs: a half unit loads the A tile and only the W rows [0, HN) or [BN - HN, BN) of its tile (second tensor
+    // map, box of HN rows), issues MMAs of N = HN and its epilogue keeps BN/2 of those columns. work unit u < t_full: tile u; otherwise tile
     // t_full + (u - t_full) / 2, half (u - t_full) & 1.
     constexpr bool CAN_SPLIT = FUSED && (BN / 2) % 8 == 0 && ((BN / 2 + 15) / 16 * 16) % 8 == 0;
     constexpr int HN = (BN / 2 + 15) / 16 * 16;                   // UMMA N of a half unit (208 -> 112)
@@ -140,17 +140,21 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             for (long long t = blockIdx.x; t < units; t += gridDim.x) {
                 int m_blk, n_blk;
-                decode(t, m_blk, n_blk);
+                const int hsel = decode(t, m_blk, n_blk);
                 if constexpr (FUSED) {
+                    // a half unit loads only its HN rows of W (box of map_bh), starting at row 0 or BN - HN of the tile
+                    const CUtensorMap *mb = hsel < 0 ? &map_b : &map_bh;
+                    const int b_row = n_blk * BN + (hsel > 0 ? BN - HN : 0);
+                    const uint32_t bytes = hsel < 0 ? (uint32_t)C_::STAGE_BYTES : (uint32_t)(2 * C_::A_BYTES + 2 * HN * BKF * 2);
                     for (int kb = 0; kb < total_kb; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES);
                         const uint32_t sal = sa + C_::A_BYTES, sb = sal + C_::A_BYTES, sbl = sb + C_::B_BYTES;
-                        mbar_expect_tx(full0 + 8 * stage, C_::STAGE_BYTES);
+                        mbar_expect_tx(full0 + 8 * stage, bytes);
                         tma_load_2d(sa, &map_a, full0 + 8 * stage, kb * BKF, m_blk * BM);          // Zh
                         tma_load_2d(sal, &map_a, full0 + 8 * stage, K + kb * BKF, m_blk * BM);     // Zl
-                        tma_load_2d(sb, &map_b, full0 + 8 * stage, kb * BKF, n_blk * BN);          // Wh
-                        tma_load_2d(sbl, &map_b, full0 + 8 * stage, K + kb * BKF, n_blk * BN);     // Wl
+                        tma_load_2d(sb, mb, full0 + 8 * stage, kb * BKF, b_row);                   // Wh
+                        tma_load_2d(sbl, mb, full0 + 8 * stage, K + kb * BKF, b_row);              // Wl
                         if (++stage == C_::STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -185,8 +189,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 int m_blk, n_blk;
                 const int hsel = decode(t, m_blk, n_blk);
                 const uint32_t idesc_u = hsel < 0 ? idesc : make_idesc(HN);
-                // B rows of a half unit start at row 0 or BN - HN: whole swizzle atoms of 8 rows (64-byte rows when fused)
-                const uint32_t b_skip = hsel > 0 ? (uint32_t)((BN - HN) * (FUSED ? BKF : BK) * 2) : 0u;
+                (void)n_blk;
                 for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK, ++chunk) {
                     const int as = (int)(chunk & 1);
                     mbar_wait(tempty0 + 8 * as, (uint32_t)((chunk >> 1) & 1) ^ 1);    // epilogue has drained this buffer
@@ -200,7 +203,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if constexpr (FUSED) {
                             const uint32_t sal = sa + C_::A_BYTES, sb = sal + C_::A_BYTES, sbl = sb + C_::B_BYTES;
                             const uint64_t dah = make_smem_desc(sa, true), dal = make_smem_desc(sal, true);
-                            const uint64_t dbh = make_smem_desc(sb + b_skip, true), dbl = make_smem_desc(sbl + b_skip, true);
+                            const uint64_t dbh = make_smem_desc(sb, true), dbl = make_smem_desc(sbl, true);
 #pragma unroll
                             for (int k = 0; k < BKF / UMMA_K; ++k) {     // small terms first, hi.hi last
                                 umma_f16(tmem_d, dal + 2 * k, dbh + 2 * k, idesc_u, (kb > kb0) || k != 0);
@@ -406,6 +409,8 @@ int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, 
     GAD_LAUNCH_CHECK();
     GAD_CUDA(cudaDeviceSynchronize());
     int rc = encode_map((CUtensorMap *)L->map_b, L->W2, L->Npad, 2ll * L->Kpad, BN, L->fused != 0);
+    if (!rc && L->fused)                                   // box of half a tile's rows, rounded up to a valid UMMA N
+        rc = encode_map((CUtensorMap *)L->map_bh, L->W2, L->Npad, 2ll * L->Kpad, (BN / 2 + 15) / 16 * 16, true);
     if (rc) return rc;
     if (BN == TC_BN_L1) return set_smem_attr<TC_BN_L1>();
     if (BN == TC_BN_L2) return set_smem_attr<TC_BN_L2>();
@@ -436,18 +441,19 @@ int run_bn(const TcLayer *L, const float *d_bias, void *d_out, int ldc, int lo_o
     const long long want = L->fused && tail_split ? 2 * tiles : tiles;       // half units need up to two CTAs per tile
     const unsigned grid = (unsigned)(want < GAD_NUM_SMS ? want : GAD_NUM_SMS);
     const CUtensorMap &ma = *(const CUtensorMap *)L->map_a, &mb = *(const CUtensorMap *)L->map_b;
+    const CUtensorMap &mh = *(const CUtensorMap *)(L->fused ? L->map_bh : L->map_b);
     if (L->fused && split_out)
         gemm_split_f16_kernel<BN, true, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     else if (L->fused)
         gemm_split_f16_kernel<BN, false, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     else if (split_out)
         gemm_split_f16_kernel<BN, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     else
         gemm_split_f16_kernel<BN, false><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
-            ma, mb, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

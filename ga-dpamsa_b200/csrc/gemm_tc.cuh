@@ -14,6 +14,7 @@ struct TcLayer {
     void *W2 = nullptr;                      // fp16 [Npad][2*Kpad] = (hi | lo), zero beyond N and K
     alignas(64) unsigned char map_a[128];    // CUtensorMap of the activations (hi | lo), rebound when they move
     alignas(64) unsigned char map_b[128];    // CUtensorMap of W2
+    alignas(64) unsigned char map_bh[128];   // fused layers: the same with a box of half a tile's rows (tail units)
 };
 
 // BN must be one of the TC_BN_* values. K is padded to a multiple of 64 (Kpad); the activation buffer
