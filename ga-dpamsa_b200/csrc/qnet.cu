@@ -1170,14 +1170,6 @@ int dev_alloc(T **p, size_t n)
     return GAD_OK;
 }
 
-int upload(float **dst, const std::vector<float> &src)
-{
-    int rc = dev_alloc(dst, src.size());
-    if (rc) return rc;
-    GAD_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
-    return GAD_OK;
-}
-
 int upload(float **dst, const float *src, size_t n)
 {
     int rc = dev_alloc(dst, n);

@@ -2,7 +2,7 @@
  * gadpamsa.h - C ABI of libgadpamsa: the GA-DPAMSA generation loop on B200 (sm_100a).
  *
  * The reference (FLaTNNBio/GA-DPAMSA) is pure Python and has NO FFI of its own;
- * its drop-in boundary is the module surface of GA.py / utils.py / DPAMSA/*.py.
+ * its drop-in boundary is the module surface of GA.py, utils.py and the DPAMSA package.
  * Every entry point below therefore names the reference function(s) whose
  * per-individual Python loop it replaces for a whole device-resident
  * population; the Python facade in ga-dpamsa_b200/ keeps the reference
