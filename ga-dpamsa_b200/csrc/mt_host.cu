@@ -7,7 +7,11 @@
 // so "identical seeds" gives identical populations and crossover plans at any population size.
 #include "gad_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -54,6 +58,39 @@ struct MT {
         return r;
     }
 };
+
+// One generated row (GA.py:86-91): `ng` gaps inserted one at a time at positions at[0..ng) (each drawn in the row as
+// it was then). Inserting at position a moves every earlier gap at or right of a one cell to the right, so the final
+// gap cells are known after O(ng^2) integer steps and the residues stream into the other cells in one pass.
+void emit_row(uint8_t *row, const uint8_t *seq, int len0, int ng, const int32_t *at, int *gaps, int stride)
+{
+    if (ng <= 8 || len0 <= 128) {                          // few gaps or a short row: shifting the tail is cheaper
+        memset(row, GAD_GAP, (size_t)stride);
+        memcpy(row, seq, (size_t)len0);
+        int len = len0;
+        for (int k = 0; k < ng; ++k, ++len) {
+            memmove(row + at[k] + 1, row + at[k], (size_t)(len - at[k]));
+            row[at[k]] = GAD_GAP;
+        }
+        return;
+    }
+    for (int k = 0; k < ng; ++k) {
+        const int a = at[k];
+        for (int q = 0; q < k; ++q)
+            if (gaps[q] >= a) ++gaps[q];
+        gaps[k] = a;
+    }
+    std::sort(gaps, gaps + ng);                            // distinct cells of the final row, left to right
+    memset(row, GAD_GAP, (size_t)stride);
+    int src = 0, dst = 0;
+    for (int k = 0; k < ng; ++k) {                         // residues fill the runs between consecutive gap cells
+        const int run = gaps[k] - dst;
+        memcpy(row + dst, seq + src, (size_t)run);
+        src += run;
+        dst = gaps[k] + 1;
+    }
+    memcpy(row + dst, seq + src, (size_t)(len0 - src));
+}
 
 }  // namespace
 
@@ -109,23 +146,75 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
     }
     MT g{mt_state, (int)mt_state[624]};
     GAD_REQUIRE(g.pos >= 0 && g.pos <= 624, "gad_mt_population_host: corrupt MT19937 position %d", g.pos);
-    memset(h_boards, GAD_GAP, (size_t)P * R * stride);
-    for (int64_t p = 0; p < P; ++p) {
-        for (int r = 0; r < R; ++r) {
-            uint8_t *row = h_boards + ((size_t)p * R + r) * stride;
-            int len = h_seqlen[r];
-            memcpy(row, h_seqs + (size_t)r * seq_stride, (size_t)len);
-            if (p >= n_clone) {
-                for (int k = 0; k < h_ngaps[r]; ++k) {
-                    const int at = (int)g.randbelow((uint32_t)len);      // randint(0, len - 1)
-                    memmove(row + at + 1, row + at, (size_t)(len - at));
-                    row[at] = GAD_GAP;
-                    ++len;
+    // The generator is sequential, the boards are not: the calling thread draws the insert positions of one block of
+    // individuals while worker threads build the boards of the previous block from its positions.
+    int per_board = 0, max_gaps = 0;
+    std::vector<int> first(R);
+    for (int r = 0; r < R; ++r) {
+        first[r] = per_board;
+        per_board += h_ngaps[r];
+        max_gaps = h_ngaps[r] > max_gaps ? h_ngaps[r] : max_gaps;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char *e = getenv("GAD_HOST_THREADS")) hw = (unsigned)(atoi(e) > 0 ? atoi(e) : 1);    // cap / pin the workers
+    const int n_workers = (int)(hw > 16 ? 16 : (hw < 1 ? 1 : hw));
+    int64_t block = per_board > 0 ? (4ll << 20) / per_board : 16384;        // <= 16 MB of positions per buffer
+    block = block > 16384 ? 16384 : (block < 256 ? 256 : block);
+    if (const char *e = getenv("GAD_HOST_BLOCK")) block = atoi(e) > 0 ? atoi(e) : block;          // test hook: small blocks
+    std::vector<int32_t> pos[2];
+    pos[0].resize((size_t)block * per_board + 1);
+    pos[1].resize((size_t)block * per_board + 1);
+    auto build = [&](int64_t p0, int64_t p1, const int32_t *at_all) {         // boards [p0, p1) from their positions
+        auto work = [&](int w) {
+            std::vector<int> gaps((size_t)max_gaps + 1);
+            const int64_t share = (p1 - p0 + n_workers - 1) / n_workers;         // contiguous boards per worker
+            const int64_t lo = p0 + share * w, hi = lo + share < p1 ? lo + share : p1;
+            for (int64_t p = lo; p < hi; ++p)
+                for (int r = 0; r < R; ++r) {
+                    uint8_t *row = h_boards + ((size_t)p * R + r) * stride;
+                    const uint8_t *seq = h_seqs + (size_t)r * seq_stride;
+                    const int len0 = h_seqlen[r], ng = p >= n_clone ? h_ngaps[r] : 0;
+                    if (ng) emit_row(row, seq, len0, ng, at_all + (size_t)(p - p0) * per_board + first[r], gaps.data(), stride);
+                    else {
+                        memset(row, GAD_GAP, (size_t)stride);
+                        memcpy(row, seq, (size_t)len0);
+                    }
+                    h_rowlen[(size_t)p * R + r] = len0 + ng;
                 }
-            }
-            h_rowlen[(size_t)p * R + r] = len;
+        };
+        if (n_workers == 1 || p1 - p0 < 64) {
+            for (int w = 0; w < n_workers; ++w) work(w);
+            return;
+        }
+        std::vector<std::thread> th;
+        int started = 1;
+        try {
+            for (; started < n_workers; ++started) th.emplace_back(work, started);
+        } catch (...) {                                    // thread limit reached: the remaining shares run here
+        }
+        work(0);
+        for (int w = started; w < n_workers; ++w) work(w);
+        for (auto &t : th) t.join();
+    };
+    std::thread builder;
+    int cur = 0;
+    for (int64_t p0 = 0; p0 < P; p0 += block, cur ^= 1) {
+        const int64_t p1 = p0 + block < P ? p0 + block : P;
+        int32_t *at = pos[cur].data();
+        for (int64_t p = p0; p < p1; ++p) {                                   // sequential: the reference's draw order
+            if (p < n_clone) continue;
+            int32_t *a = at + (size_t)(p - p0) * per_board;
+            for (int r = 0; r < R; ++r)
+                for (int k = 0; k < h_ngaps[r]; ++k) *a++ = (int32_t)g.randbelow((uint32_t)(h_seqlen[r] + k));
+        }
+        if (builder.joinable()) builder.join();                               // previous block done: its buffer is free again
+        try {
+            builder = std::thread(build, p0, p1, at);
+        } catch (...) {
+            build(p0, p1, at);
         }
     }
+    if (builder.joinable()) builder.join();
     mt_state[624] = (uint32_t)g.pos;
     return GAD_OK;
 }
@@ -155,6 +244,7 @@ extern "C" int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h
     MT g{mt_state, (int)mt_state[624]};
     GAD_REQUIRE(g.pos >= 0 && g.pos <= 624, "gad_mt_population_shard_host: corrupt MT19937 position %d", g.pos);
     std::vector<int> gaps((size_t)max_gaps + 1);
+    std::vector<int32_t> at((size_t)max_gaps + 1);
     int64_t out = 0;
     for (int64_t p = 0; p < P; ++p) {
         const bool mine = p % own_step == own_first;
@@ -167,27 +257,14 @@ extern "C" int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h
             }
             uint8_t *row = h_boards + ((size_t)out * R + r) * stride;
             const uint8_t *seq = h_seqs + (size_t)r * seq_stride;
-            for (int k = 0; k < ng; ++k) {
-                const int at = (int)g.randbelow((uint32_t)(len0 + k));      // randint(0, len - 1)
-                for (int q = 0; q < k; ++q)
-                    if (gaps[q] >= at) ++gaps[q];
-                gaps[k] = at;
-            }
-            // emit: gap positions are distinct cells of the final row
-            const int len = len0 + ng;
-            memset(row, GAD_GAP, (size_t)stride);
+            for (int k = 0; k < ng; ++k) at[k] = (int32_t)g.randbelow((uint32_t)(len0 + k));      // randint(0, len - 1)
             if (ng == 0) {
+                memset(row, GAD_GAP, (size_t)stride);
                 memcpy(row, seq, (size_t)len0);
             } else {
-                // mark gaps, then stream the residues into the other cells
-                for (int k = 0; k < ng; ++k) row[gaps[k]] = 0;
-                int src = 0;
-                for (int c = 0; c < len; ++c) {
-                    if (row[c] == 0) row[c] = GAD_GAP;
-                    else row[c] = seq[src++];
-                }
+                emit_row(row, seq, len0, ng, at.data(), gaps.data(), stride);
             }
-            h_rowlen[(size_t)out * R + r] = len;
+            h_rowlen[(size_t)out * R + r] = len0 + ng;
         }
         if (mine) ++out;
     }

@@ -66,6 +66,24 @@ def test_population_whole_and_sharded(native_lib, seed, R, C, P, gap_rate):
             assert random.random() == after              # every rank leaves the generator where the reference does
 
 
+def test_population_blocks_and_worker_threads(native_lib, monkeypatch):
+    """The board builders run on worker threads, one block of individuals behind the (sequential) generator: many
+    small blocks, every thread count, rows long enough for the run-copy emitter - same population as CPython's."""
+    rng = random.Random(7)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(300 - 7 * r)) for r in range(8)]
+    random.seed(11)
+    want = O.generate_population(seqs, 600, 0.25, 0.05)
+    after = random.random()
+    for threads, block in (("1", "100"), ("3", "100"), ("8", "64"), ("16", "1000")):
+        monkeypatch.setenv("GAD_HOST_THREADS", threads)
+        monkeypatch.setenv("GAD_HOST_BLOCK", block)
+        random.seed(11)
+        got, boards, rowlen = host_population(native_lib, seqs, 600, 0.25, 0.05)
+        assert got == want
+        assert random.random() == after
+        assert all((boards[p, r, rowlen[p, r]:] == 5).all() for p in range(0, 600, 37) for r in range(8))
+
+
 def test_crossover_plan_host(native_lib):
     for seed, (n_par, rows, n_child) in enumerate([(2, 2, 40), (3, 6, 100), (77, 20, 1000), (4096, 64, 5000)]):
         random.seed(seed)
