@@ -72,6 +72,7 @@ class GA:
             self._dev.hof.copy_(old.hof)
             self._dev.hof_valid = True
             self._dev.evals, self._dev.forwards = old.evals, old.forwards
+            self._dev.episodes, self._dev.unique_episodes, self._dev.states = old.episodes, old.unique_episodes, old.states
 
     @property
     def population(self):

@@ -67,6 +67,7 @@ SIGNATURES = {
     "gad_qnet_time_l1": (c_int, [c_vp, c_i64, c_int, ctypes.POINTER(ctypes.c_float),
                                  ctypes.POINTER(ctypes.c_double), c_vp]),
     "gad_mutate": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_i64p, c_vp]),
+    "gad_mutate_stats": (c_int, [c_vp, c_i64p]),
 }
 
 

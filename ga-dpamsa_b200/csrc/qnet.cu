@@ -1004,6 +1004,7 @@ head_step_kernel(const gad_qnet net, const float *__restrict__ H2, const int32_t
 {
     const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && active && net.d_stats) atomicAdd(net.d_stats, (unsigned long long)n_rows);
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
     const int h2 = net.h2, A = net.A;
@@ -1037,6 +1038,7 @@ head_from_logits_kernel(const gad_qnet net, const float *__restrict__ Zpre, int 
 {
     const long long n_rows = n_rows_ptr ? (long long)*n_rows_ptr : n_rows_fixed;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && active && net.d_stats) atomicAdd(net.d_stats, (unsigned long long)n_rows);
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
     const int A = net.A;
@@ -1087,8 +1089,75 @@ __global__ void episode_init_kernel(const gad_qnet net, const uint8_t *__restric
     if (threadIdx.x < rows) net.heads[(size_t)m * rows + threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         net.steps[m] = 0;
-        list[atomicAdd(&counts[0], 1)] = (int32_t)m;      // order inside the list is irrelevant: episodes are independent
+        if (list) list[atomicAdd(&counts[0], 1)] = (int32_t)m;      // order inside the list is irrelevant: episodes are independent
     }
+}
+
+// Duplicate-window elimination. The eval-mode network is a pure function of the window, so two episodes
+// that start from byte-identical R' x C' windows take the same actions and end with the same aligned rows
+// (GA.py:353-366 only ever looks at the window). One warp per episode: a Zobrist hash of the window picks a
+// slot of an open-addressing table of episode numbers; the first episode to claim a slot becomes the
+// representative that actually runs, later ones compare their bytes with it (a hash collision just probes on)
+// and record rep[m]. Which of several identical episodes becomes the representative depends on timing, the
+// result does not.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+dedup_kernel(const gad_qnet net, long long M, int32_t *__restrict__ table, unsigned int mask,
+             int32_t *__restrict__ rep, int32_t *__restrict__ uniq, int32_t *__restrict__ n_uniq, int enable)
+{
+    const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int rc = net.rows * net.cols;
+    if (net.steps[m] < 0) {                               // no tile fits: not mutated, nothing to share
+        if (lane == 0) rep[m] = (int32_t)m;
+        return;
+    }
+    const uint8_t *mine = net.sub + (size_t)m * rc;
+    if (!enable) {
+        if (lane == 0) {
+            rep[m] = (int32_t)m;
+            uniq[atomicAdd(n_uniq, 1)] = (int32_t)m;
+        }
+        return;
+    }
+    unsigned long long h = 0;
+    for (int i = lane; i < rc; i += 32) h ^= mix64(((unsigned long long)i << 8) | mine[i]);
+    for (int o = 16; o > 0; o >>= 1) h ^= __shfl_xor_sync(0xFFFFFFFFu, h, o);
+    unsigned int slot = (unsigned int)(h ^ (h >> 32)) & mask;
+    for (;;) {
+        int prev = 0;
+        if (lane == 0) prev = atomicCAS(&table[slot], -1, (int32_t)m);
+        prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
+        if (prev == -1) {                                 // first of its kind: this episode runs
+            if (lane == 0) {
+                rep[m] = (int32_t)m;
+                uniq[atomicAdd(n_uniq, 1)] = (int32_t)m;
+            }
+            return;
+        }
+        const uint8_t *other = net.sub + (size_t)prev * rc;
+        bool same = true;
+        for (int i = lane; i < rc; i += 32) same &= mine[i] == other[i];
+        if (__all_sync(0xFFFFFFFFu, same)) {
+            if (lane == 0) rep[m] = prev;
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void set_i32_kernel(int32_t *dst, int32_t v0, int32_t v1)
+{
+    dst[0] = v0;
+    dst[1] = v1;
 }
 
 // Environment.padding (env.py:344-351) + the splice of GA.py:369-373, one warp per episode.
@@ -1105,8 +1174,9 @@ splice_kernel(const gad_qnet net, uint8_t *__restrict__ boards, int32_t *__restr
     const int rows = net.rows, cols = net.cols, cap = rows * cols;
     const long long p = idx ? idx[m] : m;
     const int fr = tile[2 * m], fc = tile[2 * m + 1];
-    const uint8_t *hd = net.heads + (size_t)m * rows;
-    const int T = net.steps[m];
+    const long long e = net.rep[m];                 // the episode that ran for this window (m itself if unique)
+    const uint8_t *hd = net.heads + (size_t)e * rows;
+    const int T = net.steps[e];
     if (T < 0) return;
     int longest = 0;
     for (int r = 0; r < rows; ++r) longest = max(longest, cols - (int)hd[r]);
@@ -1138,8 +1208,8 @@ splice_kernel(const gad_qnet net, uint8_t *__restrict__ boards, int32_t *__restr
                 __syncwarp();
             }
         }
-        const uint8_t *al = net.aligned + ((size_t)m * rows + r) * cap;
-        const uint8_t *sub = net.sub + ((size_t)m * rows + r) * cols;
+        const uint8_t *al = net.aligned + ((size_t)e * rows + r) * cap;
+        const uint8_t *sub = net.sub + ((size_t)e * rows + r) * cols;
         const int h = hd[r];
         for (int c = lane; c < newlen; c += 32) {
             uint8_t v;
@@ -1216,8 +1286,11 @@ int ensure_episodes(gad_qnet *q, long long M)
 {
     if (M <= q->ecap) return GAD_OK;
     cudaFree(q->sub); cudaFree(q->heads); cudaFree(q->aligned); cudaFree(q->steps); cudaFree(q->list0); cudaFree(q->list1);
+    cudaFree(q->rep); cudaFree(q->uniq); cudaFree(q->table);
     q->sub = q->heads = q->aligned = nullptr; q->steps = q->list0 = q->list1 = nullptr;
+    q->rep = q->uniq = q->table = nullptr;
     q->ecap = 0;
+    q->tcap = 0;
     const size_t rc_ = (size_t)q->rows * q->cols;
     int rc;
     if ((rc = dev_alloc(&q->sub, (size_t)M * rc_))) return rc;
@@ -1226,6 +1299,12 @@ int ensure_episodes(gad_qnet *q, long long M)
     if ((rc = dev_alloc(&q->steps, (size_t)M))) return rc;
     if ((rc = dev_alloc(&q->list0, (size_t)M))) return rc;
     if ((rc = dev_alloc(&q->list1, (size_t)M))) return rc;
+    if ((rc = dev_alloc(&q->rep, (size_t)M))) return rc;
+    if ((rc = dev_alloc(&q->uniq, (size_t)M))) return rc;
+    long long slots = 1024;
+    while (slots < 2 * M) slots <<= 1;                     // load factor <= 0.5
+    if ((rc = dev_alloc(&q->table, (size_t)slots))) return rc;
+    q->tcap = slots;
     q->ecap = M;
     return GAD_OK;
 }
@@ -1472,6 +1551,7 @@ extern "C" int gad_qnet_create(gad_qnet **out, int rows, int cols, int d_k, int 
         if (!rc) rc = tc_layer_init(q->tc3, q->W3, h_weights[14], q->A, h2, TC_BN_L3, 0);
     }
     if (!rc) rc = dev_alloc(&q->counts, 2);
+    if (!rc) rc = dev_alloc(&q->d_stats, 2);
     if (!rc && cudaMallocHost((void **)&q->h_count, 2 * sizeof(int32_t)) != cudaSuccess) {
         gad_set_error("gad_qnet_create: cudaMallocHost failed");
         rc = GAD_ECUDA;
@@ -1504,6 +1584,7 @@ extern "C" int gad_qnet_destroy(gad_qnet *q)
     cudaFree(q->Qpre);
     cudaFree(q->tok); cudaFree(q->act); cudaFree(q->sub); cudaFree(q->heads); cudaFree(q->aligned);
     cudaFree(q->steps); cudaFree(q->list0); cudaFree(q->list1); cudaFree(q->counts);
+    cudaFree(q->rep); cudaFree(q->uniq); cudaFree(q->table); cudaFree(q->d_stats);
     if (q->h_count) cudaFreeHost(q->h_count);
     delete q;
     return GAD_OK;
@@ -1574,22 +1655,43 @@ extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int
     GAD_REQUIRE(M >= 0 && R >= q->rows && stride >= 16 && stride % 16 == 0, "gad_mutate: bad shape");
     cudaStream_t st = gad_stream(stream);
     int64_t forwards = 0;
-    for (int64_t m0 = 0; m0 < M; m0 += kMaxBatch) {
-        const long long nb = M - m0 < kMaxBatch ? M - m0 : kMaxBatch;
-        int rc = ensure_states(q, nb);
-        if (!rc) rc = ensure_episodes(q, nb);
-        if (rc) return rc;
-        const int32_t *idx = d_idx ? d_idx + m0 : nullptr;
-        const int32_t *tile = d_tile + 2 * m0;
-        GAD_CUDA(cudaMemsetAsync(q->counts, 0, 2 * sizeof(int32_t), st));
-        episode_init_kernel<<<(unsigned)nb, 64, 0, st>>>(*q, d_boards, R, stride, idx, tile, nb, q->list0, q->counts);
+    q->last_stats[0] = M; q->last_stats[1] = q->last_stats[2] = q->last_stats[3] = 0;
+    if (M == 0) {
+        if (h_forwards) *h_forwards = 0;
+        return GAD_OK;
+    }
+    GAD_REQUIRE(M < (1ll << 30), "gad_mutate: too many episodes in one call (%lld)", (long long)M);
+    // GAD_MUTATE_DEDUP=0 (A/B switch): every episode runs, identical windows included
+    const char *dd = getenv("GAD_MUTATE_DEDUP");
+    const int dedup = !(dd && dd[0] == '0');
+    int rc = ensure_episodes(q, M);
+    if (rc) return rc;
+    long long slots = 1024;
+    while (slots < 2 * M) slots <<= 1;
+    GAD_CUDA(cudaMemsetAsync(q->counts, 0, 2 * sizeof(int32_t), st));
+    GAD_CUDA(cudaMemsetAsync(q->d_stats, 0, 2 * sizeof(unsigned long long), st));
+    if (dedup) GAD_CUDA(cudaMemsetAsync(q->table, 0xFF, (size_t)slots * sizeof(int32_t), st));
+    // 1. every episode's window; 2. one representative per distinct window
+    episode_init_kernel<<<(unsigned)M, 64, 0, st>>>(*q, d_boards, R, stride, d_idx, d_tile, M, nullptr, nullptr);
+    GAD_LAUNCH_CHECK();
+    dedup_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(*q, M, q->table, (unsigned int)(slots - 1), q->rep, q->uniq,
+                                                            q->counts, dedup);
+    GAD_LAUNCH_CHECK();
+    GAD_CUDA(cudaMemcpyAsync(q->h_count, q->counts, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GAD_CUDA(cudaStreamSynchronize(st));
+    const long long n_unique = q->h_count[0];
+    // 3. the representatives' greedy episodes in lock-step chunks
+    for (long long u0 = 0; u0 < n_unique; u0 += kMaxBatch) {
+        const long long nb = n_unique - u0 < kMaxBatch ? n_unique - u0 : kMaxBatch;
+        if ((rc = ensure_states(q, nb))) return rc;
+        int32_t *lists[2] = {q->uniq + u0, q->list1};       // the chunk's slice of `uniq` doubles as the first active list
+        set_i32_kernel<<<1, 1, 0, st>>>(q->counts, (int32_t)nb, 0);
         GAD_LAUNCH_CHECK();
         long long n_max = nb;
         const int max_steps = q->rows * q->cols;            // every step consumes at least one token
         int cur = 0;
         for (int s = 0; s < max_steps && n_max > 0; ++s) {
-            int32_t *list = cur ? q->list1 : q->list0, *next = cur ? q->list0 : q->list1;
-            rc = launch_forward(q, nullptr, list, q->counts + cur, n_max, max_value, nullptr, nullptr, next,
+            rc = launch_forward(q, nullptr, lists[cur], q->counts + cur, n_max, max_value, nullptr, nullptr, lists[cur ^ 1],
                                 q->counts + (cur ^ 1), st);
             if (rc) return rc;
             GAD_CUDA(cudaMemsetAsync(q->counts + cur, 0, sizeof(int32_t), st));   // becomes the "next" counter of step s+1
@@ -1601,11 +1703,27 @@ extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int
                 n_max = q->h_count[0];
             }
         }
-        splice_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, st>>>(*q, d_boards, d_rowlen, R, stride, idx, tile, nb, d_status);
-        GAD_LAUNCH_CHECK();
     }
+    // 4. every individual takes the aligned rows of its window's representative
+    splice_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(*q, d_boards, d_rowlen, R, stride, d_idx, d_tile, M, d_status);
+    GAD_LAUNCH_CHECK();
+    unsigned long long h_stats[2] = {0, 0};
+    GAD_CUDA(cudaMemcpyAsync(h_stats, q->d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     GAD_CUDA(cudaStreamSynchronize(st));
+    q->last_stats[1] = n_unique;
+    q->last_stats[2] = forwards;
+    q->last_stats[3] = (long long)h_stats[0];
     if (h_forwards) *h_forwards = forwards;
+    return GAD_OK;
+}
+
+// Counters of the last gad_mutate call on this handle: out[0] = episodes (individuals mutated, the
+// reference-equivalent count), out[1] = episodes actually run (distinct windows), out[2] = lock-step
+// forwards, out[3] = states evaluated (sum over the forwards of their active episodes).
+extern "C" int gad_mutate_stats(const gad_qnet *q, int64_t *out4)
+{
+    GAD_REQUIRE(q && out4, "gad_mutate_stats: null pointer");
+    for (int i = 0; i < 4; ++i) out4[i] = q->last_stats[i];
     return GAD_OK;
 }
 

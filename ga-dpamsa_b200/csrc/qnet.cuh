@@ -33,6 +33,11 @@ struct gad_qnet {
     uint8_t *sub = nullptr, *heads = nullptr, *aligned = nullptr;
     int32_t *steps = nullptr, *list0 = nullptr, *list1 = nullptr, *counts = nullptr;   // counts[2]
     int32_t *h_count = nullptr;   // pinned
+    // duplicate-window elimination (gad_mutate): rep[m] = the episode whose result episode m re-uses
+    int32_t *rep = nullptr, *uniq = nullptr, *table = nullptr;
+    long long tcap = 0;                          // slots of `table` (power of two)
+    unsigned long long *d_stats = nullptr;       // [0] states evaluated (sum of the active counts of all forwards)
+    long long last_stats[4] = {0, 0, 0, 0};      // episodes, unique episodes, lock-step forwards, states evaluated
     // staging of gad_qnet_forward_host (DQN.predict from python)
     long long hcap = 0;
     uint8_t *hs_states = nullptr;

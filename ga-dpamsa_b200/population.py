@@ -108,6 +108,9 @@ class DevicePopulation:
         self.width_hint = 0                      # expected board width (lanes per board in the fitness pass)
         self.evals = 0                           # boards scored so far (reference-equivalent accounting)
         self.forwards = 0                        # lock-step Q-net forwards so far
+        self.episodes = 0                        # mutation episodes so far (reference-equivalent accounting)
+        self.unique_episodes = 0                 # of those, the ones that ran (distinct windows, see gad_mutate_stats)
+        self.states = 0                          # Q-net states evaluated so far
 
     # ------------------------------------------------------------------ construction / readback
     def _new_buffer(self, cap):
@@ -370,6 +373,11 @@ class DevicePopulation:
         nat.call("gad_mutate", qnet.handle, nat.ptr(b.boards), nat.ptr(b.rowlen), self.R, self.stride, nat.ptr(idx),
                  nat.ptr(tile), M, float(max_value), nat.ptr(self._status), ctypes.byref(fw), self._stream())
         self.forwards += fw.value
+        st = (ctypes.c_int64 * 4)()
+        nat.call("gad_mutate_stats", qnet.handle, st)
+        self.episodes += int(st[0])                 # what GA.py:331-373 would run
+        self.unique_episodes += int(st[1])          # what ran here (distinct windows)
+        self.states += int(st[3])                   # Net.forward evaluations
         if int(self._status.item()) & 1:
             raise nat.GadCapacityError("a mutated row outgrew the board stride")
 

@@ -5,8 +5,8 @@ same python type the reference returns (int SP, float CS, list of indices, ...).
 
 There is no CPU fallback: without the CUDA library or a GPU these functions raise.
 The callers' half of the reference's utils.py (utils.py:472-975) follows at the bottom: metrics, FASTA
-parsing and the CSV plumbing are host formatting around device-computed scores; the external-tool and
-plotting entry points are out of scope and raise NotImplementedError with the reference lines they stand for.
+parsing and the CSV plumbing are host formatting around device-computed scores; the external-tool runner is
+plain subprocess plumbing (the tools themselves are not shipped) and plot_metrics is a reduced version.
 """
 from __future__ import annotations
 

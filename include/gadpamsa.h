@@ -199,6 +199,11 @@ int gad_qnet_time_l1(gad_qnet *q, int64_t M, int reps, float *ms_per_launch, dou
 int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int R, int stride, const int32_t *d_idx,
                const int32_t *d_tile, int64_t M, float max_value, int32_t *d_status, int64_t *h_forwards,
                void *stream);
+/* Counters of the last gad_mutate on this handle: out4 = {episodes (= M, what GA.py:331-373 would run),
+ * episodes actually run, lock-step forwards, states evaluated}. Episodes that start from byte-identical
+ * windows are run once (the eval-mode network is a pure function of the window, GA.py:353-366) and share
+ * the result; GAD_MUTATE_DEDUP=0 in the environment runs every one. */
+int gad_mutate_stats(const gad_qnet *q, int64_t *out4);
 
 #ifdef __cplusplus
 }

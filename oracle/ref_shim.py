@@ -25,7 +25,15 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("GADPAMSA_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference in the build container; on the GPU box the byte-identical copy oracle/_ref/
+    (oracle/make_ref.py) that travels with the repository."""
+    if os.path.isfile("/root/reference/GA.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("GADPAMSA_REFERENCE_ROOT") or _default_root()
 
 _loaded = None
 
