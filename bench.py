@@ -290,10 +290,12 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
             import GA as ga_mod
             g = ga_mod.GA(seqs, mode)
             counters = lambda: (g._dev.evals, g._dev.forwards)
+            dedup = lambda: (g._dev.episodes, g._dev.unique_episodes, g._dev.states)
         else:
             import sharded
             g = sharded.ShardedGA(seqs, mode, sharded.DeviceBackend(config.DEVICE))
             counters = lambda: (g.backend.pop.evals, g.backend.pop.forwards)
+            dedup = lambda: (g.backend.pop.episodes, g.backend.pop.unique_episodes, g.backend.pop.states)
         t0 = time.perf_counter()
         g.generate_population()
         sync()
@@ -311,6 +313,7 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
         per_gen = []
         for it in range(n_warm + n_gen):
             e0, f0 = counters()
+            d0 = dedup()
             stamps = []
             for name, fn in (("mutation", lambda: g.mutation(model)), ("fitness", g.calculate_fitness_score),
                              ("selection", g.selection), ("crossover", g.horizontal_crossover)):
@@ -319,7 +322,9 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
                 fn()
                 sync()
                 stamps.append((name, time.perf_counter() - t0))
+            d1 = dedup()
             per_gen.append({"ms": round(1e3 * sum(dt for _, dt in stamps), 2), "forwards": counters()[1] - f0,
+                            "episodes": d1[0] - d0[0], "unique_episodes": d1[1] - d0[1], "states": d1[2] - d0[2],
                             "timed": it >= n_warm})
             if it >= n_warm:
                 for name, dt in stamps:

@@ -87,10 +87,12 @@ def load_qnet(filename, rows, cols, path=None):
     """Weights are read once per (file, mtime, window) instead of once per individual (GA.py:354-355)."""
     path = config.DPAMSA_WEIGHTS_PATH if path is None else path
     full = os.path.join(path, "{}.pth".format(filename))
-    key = (os.path.abspath(full), os.path.getmtime(full) if os.path.exists(full) else None, rows, cols)
+    device = torch.cuda.current_device() if torch.cuda.is_available() else -1      # a handle lives on one GPU
+    key = (os.path.abspath(full), os.path.getmtime(full) if os.path.exists(full) else None, rows, cols, device)
     if key not in _cache:
         sd = torch.load(full, map_location="cpu")           # FileNotFoundError like the reference
-        _cache.clear()
+        for old in [k for k in _cache if k[4] == device]:   # one resident agent per device
+            del _cache[old]
         _cache[key] = QNet(sd, rows, cols)
     return _cache[key]
 

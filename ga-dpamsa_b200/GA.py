@@ -17,6 +17,7 @@ Deliberate deviations:
 from __future__ import annotations
 
 import fractions
+import functools
 import random
 
 import numpy as np
@@ -40,6 +41,17 @@ def _mt_state():
 
 def _mt_restore(arr, meta):
     random.setstate((meta[0], tuple(int(x) for x in arr), meta[1]))
+
+
+def _on_device(fn):
+    """Run a GA phase with the population's GPU current: kernels are launched on that device's current stream
+    and the Q-net handle is created there, whatever device the caller (or another GA instance) selected last."""
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        nat.require_device()                      # no GPU: fail with this build's own error, not torch's
+        with torch.cuda.device(self._device):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 class GA:
@@ -184,14 +196,17 @@ class GA:
         _mt_restore(state, meta)
         return boards, rowlen
 
+    @_on_device
     def generate_population(self):
         """GA.py:71-94: n_clone exact copies, then gap-inserted individuals; uploaded to the device."""
         self._adopt(*self._generate_host())
 
     # ------------------------------------------------------------------ a4 + a8
+    @_on_device
     def update_hall_of_fame(self):
         self._dev.hof_update(self.mode)
 
+    @_on_device
     def calculate_fitness_score(self):
         """GA.py:154-181: pad, clean, score every board (one launch), then the hall of fame."""
         if self._dev is None or self._dev.n == 0:
@@ -200,6 +215,7 @@ class GA:
         self.update_hall_of_fame()
 
     # ------------------------------------------------------------------ a10 / a11
+    @_on_device
     def _find_pareto_front(self):
         """GA.py:195-211 (computed in O(P log P) on the device, same set, index order)."""
         keep, _ = self._dev.select_flags('mo', -1)
@@ -207,6 +223,7 @@ class GA:
         scores = self.population_score
         return [scores[i] for i in np.nonzero(flags)[0]]
 
+    @_on_device
     def selection(self):
         """GA.py:232-260"""
         top_n = int(self.population_size * config.SELECTION_RATE)
@@ -214,6 +231,7 @@ class GA:
         self.calculate_fitness_score()
 
     # ------------------------------------------------------------------ a12 / a13
+    @_on_device
     def _crossover(self, kind):
         dev = self._dev
         n_children = int(config.POPULATION_SIZE) - dev.n
@@ -239,6 +257,7 @@ class GA:
         self._crossover(1)
 
     # ------------------------------------------------------------------ a14
+    @_on_device
     def mutation(self, model_path):
         """GA.py:323-373 for all selected individuals at once."""
         dev = self._dev

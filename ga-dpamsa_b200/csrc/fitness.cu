@@ -10,7 +10,10 @@
 // actually change), 12 bytes of scores out.
 #include "gad_common.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
+
+#include <atomic>
 
 namespace {
 
@@ -140,12 +143,116 @@ __device__ __forceinline__ void count_unit(const uint8_t *__restrict__ board, in
     }
 }
 
+// One board by a group of GS lanes, cells read from global memory: width/raggedness from the row lengths (w, wmin
+// already reduced over the group), column counts, scores, and - when all-gap columns exist - the in-place
+// compaction of utils.py:408-428. `pre` (PRE only) holds this lane's first unit of rows 0..6, loaded before the row
+// lengths were known. Returns the cleaned width.
+template <int GS, bool PAIRED, bool PRE>
+__device__ __forceinline__ int board_pass_global(uint8_t *__restrict__ board, int32_t *__restrict__ rl, int R, int stride,
+                                                 int gl, uint32_t gmask, int w, int wmin, const uint4 (&pre)[7], bool have_pre,
+                                                 int match, int mismatch, int gap, int32_t *__restrict__ sp_p,
+                                                 int32_t *__restrict__ em_p, int32_t *__restrict__ al_p)
+{
+    const int nwords = (w + 3) >> 2;
+    const int nunits = (nwords + 3) >> 2;
+
+    BoardSums bs;
+    boardsums_clear(bs);
+    for (int u = gl; u < nunits; u += GS) {
+        ColCounts cc[4];
+        uint32_t valid[4];
+        if (PRE && have_pre && u == gl) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                colcounts_clear(cc[k]);
+                valid[k] = 4 * u + k < nwords ? GAD_MSB4 : 0u;
+            }
+#pragma unroll
+            for (int r = 0; r < 7; ++r)
+                if (r < R) {
+                    colcounts_add(cc[0], pre[r].x, pre[0].x);
+                    colcounts_add(cc[1], pre[r].y, pre[0].y);
+                    colcounts_add(cc[2], pre[r].z, pre[0].z);
+                    colcounts_add(cc[3], pre[r].w, pre[0].w);
+                }
+        } else {
+            count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) boardsums_fold_word(bs, cc[k], valid[k] != 0u);
+    }
+    bs.q2 = group_sum<GS>(bs.q2, gmask);
+    bs.s1 = group_sum<GS>(bs.s1, gmask);
+    bs.s2 = group_sum<GS>(bs.s2, gmask);
+    bs.kept = group_sum<GS>(bs.kept, gmask);
+    bs.exact = group_sum<GS>(bs.exact, gmask);
+    const int nk = (int)bs.kept;
+
+    if (nk != w) {
+        // utils.py:408-428: drop every all-gap column, keep the order. In place: chunk by chunk, each
+        // row's units are read by the whole group before any lane stores, and stores only land at or
+        // left of the columns just read.
+        int base = 0;
+        const int nchunks = (nunits + GS - 1) / GS;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int u = ch * GS + gl;
+            uint32_t keep[4] = {0u, 0u, 0u, 0u};
+            if (u < nunits) {
+                ColCounts cc[4];
+                uint32_t valid[4];
+                count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) keep[k] = nonzero_lanes(cc[k].c1 + cc[k].c2 + cc[k].c3 + cc[k].c4) & valid[k];
+            }
+            const int mine = __popc(keep[0]) + __popc(keep[1]) + __popc(keep[2]) + __popc(keep[3]);
+            int incl = mine;                                  // inclusive scan inside the group
+#pragma unroll
+            for (int o = 1; o < GS; o <<= 1) {
+                const int t = __shfl_up_sync(gmask, incl, o, GS);
+                if (gl >= o) incl += t;
+            }
+            const int total = __shfl_sync(gmask, incl, GS - 1, GS);
+            const int dst0 = base + incl - mine;
+            for (int r = 0; r < R; ++r) {
+                uint8_t *row = board + (size_t)r * stride;
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (u < nunits) x = reinterpret_cast<const uint4 *>(row)[u];
+                __syncwarp(gmask);
+                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+                int d = dst0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (keep[k] & (0x80u << (8 * b))) row[d++] = (uint8_t)(xs[k] >> (8 * b));
+                __syncwarp(gmask);
+            }
+            base += total;
+        }
+        // restore the padding invariant for the shrunken board
+        const int pad_to = (nk + 3) & ~3;
+        for (int i = gl; i < R * 4; i += GS) {
+            const int r = i >> 2, c = nk + (i & 3);
+            if (c < pad_to) board[(size_t)r * stride + c] = GAD_GAP;
+        }
+    }
+    if (nk != w || wmin != w)
+        for (int r = gl; r < R; r += GS) rl[r] = nk;
+
+    if (gl == 0) {
+        *sp_p = (int32_t)sum_of_pairs_closed_form(bs, R, match, mismatch, gap);
+        *em_p = (int32_t)bs.exact;
+        *al_p = nk;
+    }
+    return nk;
+}
+
 // GS lanes own one board; lane l owns the 16-byte units l, l+GS, ... of every row.
 template <int GS, bool PAIRED>
 __global__ void __launch_bounds__(256, 3)
 fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long long P, int R, int stride,
                int match, int mismatch, int gap, int32_t *__restrict__ sp, int32_t *__restrict__ em,
-               int32_t *__restrict__ al, int32_t *__restrict__ max_al)
+               int32_t *__restrict__ al, unsigned long long *__restrict__ max_al, unsigned long long max_tag)
 {
     const uint32_t gmask = group_mask<GS>();
     const int gl = threadIdx.x & (GS - 1);                       // lane inside the group
@@ -182,102 +289,13 @@ fitness_kernel(uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, long 
         }
         w = group_max<GS>(w, gmask);
         wmin = -group_max<GS>(-wmin, gmask);
-        const int nwords = (w + 3) >> 2;
-        const int nunits = (nwords + 3) >> 2;
-
-        BoardSums bs;
-        boardsums_clear(bs);
-        for (int u = gl; u < nunits; u += GS) {
-            ColCounts cc[4];
-            uint32_t valid[4];
-            if (!PAIRED && have_pre && u == gl) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    colcounts_clear(cc[k]);
-                    valid[k] = 4 * u + k < nwords ? GAD_MSB4 : 0u;
-                }
-#pragma unroll
-                for (int r = 0; r < 7; ++r)
-                    if (r < R) {
-                        colcounts_add(cc[0], pre[r].x, pre[0].x);
-                        colcounts_add(cc[1], pre[r].y, pre[0].y);
-                        colcounts_add(cc[2], pre[r].z, pre[0].z);
-                        colcounts_add(cc[3], pre[r].w, pre[0].w);
-                    }
-            } else {
-                count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) boardsums_fold_word(bs, cc[k], valid[k] != 0u);
-        }
-        bs.q2 = group_sum<GS>(bs.q2, gmask);
-        bs.s1 = group_sum<GS>(bs.s1, gmask);
-        bs.s2 = group_sum<GS>(bs.s2, gmask);
-        bs.kept = group_sum<GS>(bs.kept, gmask);
-        bs.exact = group_sum<GS>(bs.exact, gmask);
-        const int nk = (int)bs.kept;
-
-        if (nk != w) {
-            // utils.py:408-428: drop every all-gap column, keep the order. In place: chunk by chunk, each
-            // row's units are read by the whole group before any lane stores, and stores only land at or
-            // left of the columns just read.
-            int base = 0;
-            const int nchunks = (nunits + GS - 1) / GS;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int u = ch * GS + gl;
-                uint32_t keep[4] = {0u, 0u, 0u, 0u};
-                if (u < nunits) {
-                    ColCounts cc[4];
-                    uint32_t valid[4];
-                    count_unit<PAIRED>(board, R, stride, u, nwords, cc, valid);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) keep[k] = nonzero_lanes(cc[k].c1 + cc[k].c2 + cc[k].c3 + cc[k].c4) & valid[k];
-                }
-                const int mine = __popc(keep[0]) + __popc(keep[1]) + __popc(keep[2]) + __popc(keep[3]);
-                int incl = mine;                                  // inclusive scan inside the group
-#pragma unroll
-                for (int o = 1; o < GS; o <<= 1) {
-                    const int t = __shfl_up_sync(gmask, incl, o, GS);
-                    if (gl >= o) incl += t;
-                }
-                const int total = __shfl_sync(gmask, incl, GS - 1, GS);
-                const int dst0 = base + incl - mine;
-                for (int r = 0; r < R; ++r) {
-                    uint8_t *row = board + (size_t)r * stride;
-                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
-                    if (u < nunits) x = reinterpret_cast<const uint4 *>(row)[u];
-                    __syncwarp(gmask);
-                    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-                    int d = dst0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            if (keep[k] & (0x80u << (8 * b))) row[d++] = (uint8_t)(xs[k] >> (8 * b));
-                    __syncwarp(gmask);
-                }
-                base += total;
-            }
-            // restore the padding invariant for the shrunken board
-            const int pad_to = (nk + 3) & ~3;
-            for (int i = gl; i < R * 4; i += GS) {
-                const int r = i >> 2, c = nk + (i & 3);
-                if (c < pad_to) board[(size_t)r * stride + c] = GAD_GAP;
-            }
-        }
-        if (nk != w || wmin != w)
-            for (int r = gl; r < R; r += GS) rl[r] = nk;
-
-        if (gl == 0) {
-            sp[p] = (int32_t)sum_of_pairs_closed_form(bs, R, match, mismatch, gap);
-            em[p] = (int32_t)bs.exact;
-            al[p] = nk;
-        }
+        const int nk = board_pass_global<GS, PAIRED, !PAIRED>(board, rl, R, stride, gl, gmask, w, wmin, pre, have_pre, match,
+                                                             mismatch, gap, sp + p, em + p, al + p);
         local_max = max(local_max, nk);
     }
     if (max_al != nullptr) {
         local_max = group_max<32>(local_max, 0xFFFFFFFFu);
-        if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(max_al, local_max);
+        if ((threadIdx.x & 31) == 0) atomicMax(max_al, max_tag | (unsigned long long)local_max);
     }
 }
 
@@ -316,9 +334,559 @@ window_score_kernel(const uint8_t *__restrict__ board, int stride, int fr, int t
     }
 }
 
+// =============================================================================================
+// TMA-staged variant (the default for boards up to 256 columns): the board cells never pass through registers
+// on their way from HBM. One persistent CTA per SM; a producer thread streams boxes of NB boards x R rows x BW
+// bytes (BW = the live width rounded to 16, not the stride) through a 3-D tensor map into a ring of shared-memory
+// stages, all stages in flight from the first cycle (c3: the 14 boxes of an SM's share are requested at once =
+// 170 KB in flight per SM, which a register-staged kernel cannot hold). Teams of NB x GS consumer threads take the
+// boxes in turn; GS lanes own one board and read its rows from shared memory (16 bytes per lane and row).
+//   NIB (R <= 15): two 4-column words are packed into one register of eight 4-bit lanes (x_hi * 16 + x_lo), so
+//   one LOP3 per symbol class covers 8 columns of a row and the per-column counters are nibbles that cannot
+//   overflow - half the integer work per cell of the byte-lane counters.
+//   R >= 16: byte-lane counters with two rows per word (colcounts_add2), flushed every 14 row pairs.
+// All-gap columns (utils.py:408-428) are compacted from the shared-memory copy straight to global memory (no
+// in-place hazard); boards wider than the box, or with more units than lanes when they need compaction, take the
+// global-memory path of the register kernel (board_pass_global) inside the same launch.
+// =============================================================================================
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t ft_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ft_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ft_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint64_t t0 = 0;
+    for (;;) {
+#pragma unroll 1
+        for (int spin = 0; spin < 4096; ++spin) {
+            uint32_t done;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity), "r"(10000u)
+                : "memory");
+            if (done) return;
+        }
+        uint64_t now;                               // a lost arrival must fail loudly, never hang the GPU
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void ft_tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// nibble-lane counters of 8 columns (two packed words) over the rows of one unit half
+struct NibCounts {
+    uint32_t n1, n2, n3, n4, diff;
+};
+__device__ __forceinline__ void nib_clear(NibCounts &n) { n.n1 = n.n2 = n.n3 = n.n4 = n.diff = 0u; }
+__device__ __forceinline__ void nib_add(NibCounts &n, uint32_t z, uint32_t z_first)
+{
+    const uint32_t b0 = z & GAD_LSN8;
+    const uint32_t b1 = (z >> 1) & GAD_LSN8;
+    const uint32_t b2 = (z >> 2) & GAD_LSN8;
+    n.n1 += b0 & ~b1 & ~b2;
+    n.n2 += b1 & ~b0;
+    n.n3 += b0 & b1;
+    n.n4 += b2 & ~b0;
+    n.diff |= z ^ z_first;
+}
+// low (hi = 0) or high (hi = 1) nibbles of the counters as byte-lane ColCounts of one 4-column word
+__device__ __forceinline__ void nib_unpack(const NibCounts &n, int hi, ColCounts &c)
+{
+    const int sh = hi * 4;
+    c.c1 = (n.n1 >> sh) & GAD_NIB4;
+    c.c2 = (n.n2 >> sh) & GAD_NIB4;
+    c.c3 = (n.n3 >> sh) & GAD_NIB4;
+    c.c4 = (n.n4 >> sh) & GAD_NIB4;
+    c.diff = (n.diff >> sh) & GAD_NIB4;
+}
+
+// Column counts of unit u (16 columns = words 4u..4u+3) of a board in shared memory: `sb` = shared address of the
+// board's first row, `pitch` = bytes between rows. Same outputs as count_unit.
+template <bool NIB>
+__device__ __forceinline__ void count_unit_smem(uint32_t sb, int R, int pitch, int u, int nwords, ColCounts (&cc)[4],
+                                                uint32_t (&valid)[4])
+{
+    const uint32_t a0 = sb + 16u * u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = 4 * u + k < nwords ? GAD_MSB4 : 0u;
+    const uint4 first = lds128(a0);
+    if constexpr (NIB) {
+        NibCounts na, nb;
+        nib_clear(na);
+        nib_clear(nb);
+        // words at or beyond nwords hold stale bytes of any value: a stale high word must not carry into the valid
+        // low word it is packed with, so its multiplier is 0 instead of 16 (a stale low word implies a stale high one)
+        const uint32_t my = valid[1] ? 16u : 0u, mw = valid[3] ? 16u : 0u;
+        const uint32_t fa = first.y * my + first.x, fb = first.w * mw + first.z;
+#pragma unroll 3
+        for (int r = 0; r < R; ++r) {
+            const uint4 x = lds128(a0 + (uint32_t)(r * pitch));
+            nib_add(na, x.y * my + x.x, fa);
+            nib_add(nb, x.w * mw + x.z, fb);
+        }
+        nib_unpack(na, 0, cc[0]);
+        nib_unpack(na, 1, cc[1]);
+        nib_unpack(nb, 0, cc[2]);
+        nib_unpack(nb, 1, cc[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) colcounts_clear(cc[k]);
+        const uint32_t f2[4] = {first.x * 17u, first.y * 17u, first.z * 17u, first.w * 17u};
+        ColCounts nn[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) colcounts_clear(nn[k]);
+        int r = 0, pairs = 0;
+        for (; r + 2 <= R; r += 2) {
+            const uint4 x0 = lds128(a0 + (uint32_t)(r * pitch)), x1 = lds128(a0 + (uint32_t)((r + 1) * pitch));
+            colcounts_add2(nn[0], x0.x, x1.x, f2[0]);
+            colcounts_add2(nn[1], x0.y, x1.y, f2[1]);
+            colcounts_add2(nn[2], x0.z, x1.z, f2[2]);
+            colcounts_add2(nn[3], x0.w, x1.w, f2[3]);
+            if (++pairs >= 14) {                              // 4-bit counters hold at most 15
+#pragma unroll
+                for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
+                pairs = 0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
+        if (r < R) {
+            const uint4 x0 = lds128(a0 + (uint32_t)(r * pitch));
+            colcounts_add(cc[0], x0.x, first.x);
+            colcounts_add(cc[1], x0.y, first.y);
+            colcounts_add(cc[2], x0.z, first.z);
+            colcounts_add(cc[3], x0.w, first.w);
+        }
+    }
+}
+
+// consumer threads per CTA (+ one producer warp): the nibble path fits 64 registers, the row-paired byte path needs more
+template <bool NIB> struct FtThreads { static constexpr int CONSUMERS = NIB ? 896 : 480; };
+constexpr int FT_MAX_STAGES = 32;
+
+// Launch geometry, computed on the host so that the kernel does no division (a thread scores only two or three boards
+// per launch at c3: a 64-bit divide in its prologue costs as much as a board).
+struct FtGeom {
+    int BW;            // bytes of a row inside a box (multiple of 16, <= 256, <= stride)
+    int NB;            // boards per box (power of two)
+    int stages;        // ring depth, a multiple of nteams
+    int stage_bytes;   // NB * R * BW rounded up to 128
+    int nteams;        // teams of NB * GS consumer threads
+    int spt;           // stages per team = stages / nteams
+    int team_shift;    // log2(NB * GS)
+    int nboxes;        // ceil(P / NB)
+};
+
+// Fold the nibble counters of 8 columns (words w and w + 1 of the board; w even) into the board sums.
+// hi_valid = word w + 1 is inside the board. Returns nothing; keep masks are recomputed when a board needs compaction.
+__device__ __forceinline__ void nib_fold(BoardSums &b, const NibCounts &n, bool hi_valid)
+{
+    // nibble-level: non-gap cells per column (<= 15), kept = columns with any, exact = kept and no differing row
+    const uint32_t s = n.n1 + n.n2 + n.n3 + n.n4;
+    const uint32_t vmask = hi_valid ? 0x88888888u : 0x08080808u;
+    const uint32_t kept = (((s & 0x77777777u) + 0x77777777u) | s) & vmask;
+    const uint32_t differ = (((n.diff & 0x77777777u) + 0x77777777u) | n.diff) & 0x88888888u;
+    b.kept += __popc(kept);
+    b.exact += __popc(kept & ~differ);
+    // squares need byte lanes: low nibbles = word w, high nibbles = word w + 1 (zero counts when that word is invalid
+    // because its multiplier was 0 - except codes of word w + 1 read as 0 never count as a symbol)
+    const uint32_t m = hi_valid ? 0xFFFFFFFFu : 0u;
+    const uint32_t a1 = n.n1 & GAD_NIB4, a2 = n.n2 & GAD_NIB4, a3 = n.n3 & GAD_NIB4, a4 = n.n4 & GAD_NIB4;
+    const uint32_t h1 = (n.n1 >> 4) & GAD_NIB4 & m, h2 = (n.n2 >> 4) & GAD_NIB4 & m, h3 = (n.n3 >> 4) & GAD_NIB4 & m,
+                   h4 = (n.n4 >> 4) & GAD_NIB4 & m;
+    b.q2 = __dp4a(a1, a1, b.q2);
+    b.q2 = __dp4a(a2, a2, b.q2);
+    b.q2 = __dp4a(a3, a3, b.q2);
+    b.q2 = __dp4a(a4, a4, b.q2);
+    b.q2 = __dp4a(h1, h1, b.q2);
+    b.q2 = __dp4a(h2, h2, b.q2);
+    b.q2 = __dp4a(h3, h3, b.q2);
+    b.q2 = __dp4a(h4, h4, b.q2);
+    const uint32_t sl = a1 + a2 + a3 + a4, sh = h1 + h2 + h3 + h4;
+    b.s1 = __dp4a(sl, GAD_LSB4, b.s1);
+    b.s1 = __dp4a(sh, GAD_LSB4, b.s1);
+    b.s2 = __dp4a(sl, sl, b.s2);
+    b.s2 = __dp4a(sh, sh, b.s2);
+}
+
+// keep mask (bit 7 per byte lane) of one 4-column word from nibble counters; hi selects the high nibbles
+__device__ __forceinline__ uint32_t nib_keep_word(const NibCounts &n, int hi)
+{
+    const int sh = hi * 4;
+    const uint32_t s = ((n.n1 >> sh) & GAD_NIB4) + ((n.n2 >> sh) & GAD_NIB4) + ((n.n3 >> sh) & GAD_NIB4) + ((n.n4 >> sh) & GAD_NIB4);
+    return nonzero_lanes(s);
+}
+
+// RT > 0: the row count is RT (loops fully unrolled, row lengths read as vectors); RT = 0: any R
+template <int GS, bool NIB, int RT>
+__global__ void __launch_bounds__(FtThreads<NIB>::CONSUMERS + 32, 1)
+fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen,
+                   int P, int R_rt, int stride, FtGeom geo, int match, int mismatch, int gap,
+                   int32_t *__restrict__ sp, int32_t *__restrict__ em, int32_t *__restrict__ al,
+                   unsigned long long *__restrict__ max_al, unsigned long long max_tag)
+{
+    extern __shared__ uint8_t ft_smem_raw[];
+    const int R = RT > 0 ? RT : R_rt;
+    const uint32_t smem0 = (ft_smem_u32(ft_smem_raw) + 127u) & ~127u;
+    const uint32_t full0 = smem0 + (uint32_t)(geo.stages * geo.stage_bytes), empty0 = full0 + 8u * geo.stages;
+    const int tid = threadIdx.x;
+    const int n_consumers = geo.nteams << geo.team_shift;
+    // boxes of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ... (32-bit: P < 2^31)
+    const int nk = geo.nboxes > (int)blockIdx.x ? (int)((unsigned)(geo.nboxes - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    // Programmatic dependent launch: the next launch in the stream may start its prologue (CTA launch, barrier
+    // set-up) while this grid is still running; it blocks at its own griddepcontrol.wait until this grid has
+    // completed and its writes are visible. Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        for (int s2 = 0; s2 < geo.stages; ++s2) {
+            ft_mbar_init(full0 + 8u * s2, 1);
+            ft_mbar_init(empty0 + 8u * s2, 1u << (geo.team_shift - 5));          // one arrival per warp of the owning team
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");            // nothing before this line touched global memory
+
+    if (tid >= n_consumers) {
+        // ===================== producer: one thread streams this CTA's boxes =====================
+        if (tid == n_consumers) {
+            const uint32_t box_bytes = (uint32_t)(geo.NB * R * geo.BW);
+            int stage = 0, round = 0;
+            for (int k = 0; k < nk; ++k) {
+                if (round > 0) ft_mbar_wait(empty0 + 8u * stage, (uint32_t)((round - 1) & 1));
+                const int box = blockIdx.x + k * gridDim.x;
+                ft_mbar_expect_tx(full0 + 8u * stage, box_bytes);
+                ft_tma_load_3d(smem0 + (uint32_t)(stage * geo.stage_bytes), &map, full0 + 8u * stage, 0, 0, box * geo.NB);
+                if (++stage == geo.stages) {
+                    stage = 0;
+                    ++round;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const uint32_t gmask = group_mask<GS>();
+    const int team = tid >> geo.team_shift, tt = tid & ((1 << geo.team_shift) - 1);
+    const int b = tt / GS, gl = tt & (GS - 1);          // GS is a power of two: a shift
+    const int lane = tid & 31;
+    const int pitch = geo.BW;
+    int local_max = 0;
+    // Stage s always belongs to team s % nteams (stages is a multiple of nteams), and a team walks its stages round
+    // by round: nobody ever waits on a barrier phase that is more than one completion away (an mbarrier parity
+    // wait cannot tell phase n from phase n + 2).
+    // (width, shortest row) of this thread's board in the team's box k, from the row lengths in global memory.
+    // Called one box ahead, so the DRAM round trip overlaps the previous box's arithmetic (and, for the first box,
+    // the flight of the box itself).
+    auto load_widths = [&](int k, int &w, int &wmin) {
+        w = 0;
+        wmin = 0x7fffffff;
+        if (k >= nk) return;
+        const int p = (blockIdx.x + k * gridDim.x) * geo.NB + b;
+        if (p >= P) return;
+        const int32_t *rl = rowlen + (size_t)p * R;
+        if constexpr (RT > 0 && RT % 2 == 0) {                    // every lane reads all of them: no shuffles
+            const int2 *rl2 = reinterpret_cast<const int2 *>(rl);
+#pragma unroll
+            for (int r = 0; r < RT / 2; ++r) {
+                const int2 v = rl2[r];
+                w = max(w, max(v.x, v.y));
+                wmin = min(wmin, min(v.x, v.y));
+            }
+        } else if constexpr (RT > 0) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const int v = rl[r];
+                w = max(w, v);
+                wmin = min(wmin, v);
+            }
+        } else {
+            for (int r = gl; r < R; r += GS) {
+                const int v = rl[r];
+                w = max(w, v);
+                wmin = min(wmin, v);
+            }
+            w = group_max<GS>(w, gmask);
+            wmin = -group_max<GS>(-wmin, gmask);
+        }
+    };
+    int idx = 0, round = 0;
+    int w_next, wmin_next;
+    load_widths(team, w_next, wmin_next);
+    for (;;) {
+        const int stage = team + idx * geo.nteams;
+        const int k = round * geo.stages + stage;
+        if (k >= nk) break;                                       // k grows monotonically: nothing left for this team
+        const uint32_t parity = (uint32_t)(round & 1);
+        if (++idx == geo.spt) {
+            idx = 0;
+            ++round;
+        }
+        const int box = blockIdx.x + k * gridDim.x;
+        const int p = box * geo.NB + b;
+        const bool live = p < P;
+        int32_t *rl = rowlen + (size_t)(live ? p : 0) * R;
+        const int w = w_next, wmin = wmin_next;
+        load_widths(round * geo.stages + team + idx * geo.nteams, w_next, wmin_next);      // the team's next box
+        ft_mbar_wait(full0 + 8u * stage, parity);
+        if (live) {
+            uint8_t *board = boards + (size_t)p * R * stride;
+            const uint32_t sb = smem0 + (uint32_t)(stage * geo.stage_bytes) + (uint32_t)(b * R * pitch);
+            const int nwords = (w + 3) >> 2;
+            const int nunits = (nwords + 3) >> 2;
+            int nk_cols;
+            if (w <= geo.BW) {
+                BoardSums bs;
+                boardsums_clear(bs);
+                if constexpr (NIB) {
+                    for (int u = gl; u < nunits; u += GS) {
+                        const uint32_t a0 = sb + 16u * u;
+                        // words at or beyond nwords hold stale bytes of any value: a stale high word must not carry into
+                        // the valid low word it is packed with, so its multiplier is 0 instead of 16
+                        const bool v1 = 4 * u + 1 < nwords, v2 = 4 * u + 2 < nwords, v3 = 4 * u + 3 < nwords;
+                        const uint32_t my = v1 ? 16u : 0u, mw = v3 ? 16u : 0u;
+                        const uint4 first = lds128(a0);
+                        const uint32_t fa = first.y * my + first.x, fb = first.w * mw + first.z;
+                        NibCounts na, nb;
+                        nib_clear(na);
+                        nib_clear(nb);
+                        if constexpr (RT > 0) {
+#pragma unroll
+                            for (int r = 0; r < RT; ++r) {
+                                const uint4 x = lds128(a0 + (uint32_t)(r * pitch));
+                                nib_add(na, x.y * my + x.x, fa);
+                                nib_add(nb, x.w * mw + x.z, fb);
+                            }
+                        } else {
+#pragma unroll 2
+                            for (int r = 0; r < R; ++r) {
+                                const uint4 x = lds128(a0 + (uint32_t)(r * pitch));
+                                nib_add(na, x.y * my + x.x, fa);
+                                nib_add(nb, x.w * mw + x.z, fb);
+                            }
+                        }
+                        nib_fold(bs, na, v1);                     // word 4u is valid because u < nunits
+                        if (v2) nib_fold(bs, nb, v3);
+                    }
+                } else {
+                    for (int u = gl; u < nunits; u += GS) {
+                        ColCounts cc[4];
+                        uint32_t valid[4];
+                        count_unit_smem<false>(sb, R, pitch, u, nwords, cc, valid);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) boardsums_fold_word(bs, cc[kk], valid[kk] != 0u);
+                    }
+                }
+                // group reduction of the five sums, packed into two words while they fit 16 bits (narrow boards, few rows)
+                if (NIB) {
+                    uint32_t pa = bs.q2 | (bs.s2 << 16), pb = bs.s1 | (bs.kept << 12) | (bs.exact << 22);
+                    pa = group_sum<GS>(pa, gmask);
+                    pb = group_sum<GS>(pb, gmask);
+                    bs.q2 = pa & 0xFFFFu;
+                    bs.s2 = pa >> 16;
+                    bs.s1 = pb & 0xFFFu;
+                    bs.kept = (pb >> 12) & 0x3FFu;
+                    bs.exact = pb >> 22;
+                } else {
+                    bs.q2 = group_sum<GS>(bs.q2, gmask);
+                    bs.s1 = group_sum<GS>(bs.s1, gmask);
+                    bs.s2 = group_sum<GS>(bs.s2, gmask);
+                    bs.kept = group_sum<GS>(bs.kept, gmask);
+                    bs.exact = group_sum<GS>(bs.exact, gmask);
+                }
+                nk_cols = (int)bs.kept;
+                if (nk_cols != w && nunits > GS) {
+                    // more units than lanes and columns to drop: the in-place path on global memory (rare, wide boards)
+                    const uint4 none[7] = {};
+                    nk_cols = board_pass_global<GS, !NIB, false>(board, rl, R, stride, gl, gmask, w, wmin, none, false, match,
+                                                                mismatch, gap, sp + p, em + p, al + p);
+                } else {
+                    if (nk_cols != w) {
+                        // utils.py:408-428 from the shared-memory copy: every lane owns one unit; kept bytes go to
+                        // their final place in global memory (no in-place hazard)
+                        const int u = gl;
+                        uint32_t keep[4] = {0u, 0u, 0u, 0u};
+                        if (u < nunits) {
+                            ColCounts cc[4];
+                            uint32_t valid[4];
+                            count_unit_smem<NIB>(sb, R, pitch, u, nwords, cc, valid);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                keep[kk] = nonzero_lanes(cc[kk].c1 + cc[kk].c2 + cc[kk].c3 + cc[kk].c4) & valid[kk];
+                        }
+                        const int mine = __popc(keep[0]) + __popc(keep[1]) + __popc(keep[2]) + __popc(keep[3]);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < GS; o <<= 1) {
+                            const int t = __shfl_up_sync(gmask, incl, o, GS);
+                            if (gl >= o) incl += t;
+                        }
+                        const int dst0 = incl - mine;
+                        if (u < nunits) {
+                            for (int r = 0; r < R; ++r) {
+                                const uint4 x = lds128(sb + (uint32_t)(r * pitch) + 16u * u);
+                                uint8_t *row = board + (size_t)r * stride;
+                                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+                                int d = dst0;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                                    for (int bb = 0; bb < 4; ++bb)
+                                        if (keep[kk] & (0x80u << (8 * bb))) row[d++] = (uint8_t)(xs[kk] >> (8 * bb));
+                            }
+                        }
+                        __syncwarp(gmask);
+                        const int pad_to = (nk_cols + 3) & ~3;      // the padding invariant of the shrunken board
+                        for (int i = gl; i < R * 4; i += GS) {
+                            const int r = i >> 2, c = nk_cols + (i & 3);
+                            if (c < pad_to) board[(size_t)r * stride + c] = GAD_GAP;
+                        }
+                    }
+                    if (nk_cols != w || wmin != w)
+                        for (int r = gl; r < R; r += GS) rl[r] = nk_cols;
+                    if (gl == 0) {
+                        sp[p] = (int32_t)sum_of_pairs_closed_form(bs, R, match, mismatch, gap);
+                        em[p] = (int32_t)bs.exact;
+                        al[p] = nk_cols;
+                    }
+                }
+            } else {
+                // wider than the box (the width hint was too small): everything from global memory
+                const uint4 none[7] = {};
+                nk_cols = board_pass_global<GS, !NIB, false>(board, rl, R, stride, gl, gmask, w, wmin, none, false, match, mismatch,
+                                                            gap, sp + p, em + p, al + p);
+            }
+            local_max = max(local_max, nk_cols);
+        }
+        __syncwarp();
+        if (lane == 0) ft_mbar_arrive(empty0 + 8u * stage);          // this warp is done with the stage
+    }
+    if (max_al != nullptr) {
+        local_max = group_max<32>(local_max, 0xFFFFFFFFu);
+        if (lane == 0) atomicMax(max_al, max_tag | (unsigned long long)local_max);
+    }
+}
+
+typedef CUresult (*FtEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Returns GAD_OK after launching, or 1 when the shape is outside the TMA path (the caller launches the register kernel).
+template <int GS, bool NIB>
+int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int stride, int width, int match, int mismatch,
+                       int gap, int32_t *sp, int32_t *em, int32_t *al, unsigned long long *max_al, unsigned long long max_tag, cudaStream_t st)
+{
+    static FtEncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess || !fp ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        encode = (FtEncodeTiledFn)fp;
+    }
+    if (P >= (1ll << 30)) return 1;                                  // the kernel indexes boards with 32-bit integers
+    FtGeom g;
+    g.BW = (width + 15) / 16 * 16;
+    if (g.BW > stride) g.BW = stride;
+    const int board_bytes = R * g.BW;
+    int nb = 32 / GS > 1 ? 32 / GS : 1;                              // a team is whole warps
+    static const int box_target = [] { const char *e = getenv("GAD_FT_BOX_BYTES"); return e && atoi(e) > 0 ? atoi(e) : 6144; }();
+    while (nb * 2 * board_bytes <= box_target && nb * 2 <= 256 && nb * 2 * GS <= 256) nb *= 2;
+    g.NB = nb;
+    g.stage_bytes = (nb * board_bytes + 127) / 128 * 128;
+    // tuning knobs (A/B): CTAs per SM, shared memory and consumer threads per CTA
+    static const int ctas_per_sm = [] { const char *e = getenv("GAD_FT_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+    static const int smem_kb = [] { const char *e = getenv("GAD_FT_SMEM_KB"); return e && atoi(e) > 0 ? atoi(e) : 200; }();
+    static const int max_cons = [] { const char *e = getenv("GAD_FT_CONSUMERS"); return e && atoi(e) > 0 ? atoi(e) : 1 << 20; }();
+    g.stages = (smem_kb * 1024 / ctas_per_sm) / g.stage_bytes;
+    if (g.stages > FT_MAX_STAGES) g.stages = FT_MAX_STAGES;
+    int cons = FtThreads<NIB>::CONSUMERS / ctas_per_sm / 32 * 32;
+    if (cons > max_cons) cons = max_cons;
+    g.nteams = cons / (nb * GS);
+    if (g.stages < 2 || g.nteams < 1 || (nb * GS) % 32 != 0) return 1;
+    g.nboxes = (int)((P + nb - 1) / nb);
+    // fewer boxes than teams x SMs: shrink the team count so that the CTAs stay balanced
+    const int max_grid = GAD_NUM_SMS * ctas_per_sm;
+    const int grid = g.nboxes < max_grid ? g.nboxes : max_grid;
+    const int per_cta = (g.nboxes + grid - 1) / grid;
+    if (per_cta < g.nteams) g.nteams = per_cta;
+    if (g.nteams > g.stages) g.nteams = g.stages;
+    g.stages = g.stages / g.nteams * g.nteams;                     // every stage has one owning team (see the kernel)
+    g.spt = g.stages / g.nteams;
+    g.team_shift = 0;
+    while ((1 << g.team_shift) < nb * GS) ++g.team_shift;
+
+    alignas(64) CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)stride, (cuuint64_t)R, (cuuint64_t)P};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)stride * R};
+    const cuuint32_t box[3] = {(cuuint32_t)g.BW, (cuuint32_t)R, (cuuint32_t)nb};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, boards, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return 1;
+    const int smem = g.stages * g.stage_bytes + 16 * g.stages + 128;
+    const int threads = g.nteams * nb * GS + 32;
+    static const int use_pdl = [] { const char *e = getenv("GAD_FT_PDL"); return e ? atoi(e) : 1; }();      // A/B switch
+#define GAD_FT_LAUNCH(RT)                                                                                                  \
+    do {                                                                                                                   \
+        GAD_CUDA(cudaFuncSetAttribute(fitness_tma_kernel<GS, NIB, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      227 * 1024 - 1024));                                                                 \
+        cudaLaunchConfig_t cfg = {};                                                                                       \
+        cfg.gridDim = dim3((unsigned)grid);                                                                                \
+        cfg.blockDim = dim3((unsigned)threads);                                                                            \
+        cfg.dynamicSmemBytes = (size_t)smem;                                                                               \
+        cfg.stream = st;                                                                                                   \
+        cudaLaunchAttribute attr[1];                                                                                       \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                   \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                                                            \
+        cfg.attrs = attr;                                                                                                  \
+        cfg.numAttrs = use_pdl ? 1 : 0;                                                                                    \
+        GAD_CUDA(cudaLaunchKernelEx(&cfg, fitness_tma_kernel<GS, NIB, RT>, map, boards, rowlen, (int)P, R, stride, g,      \
+                                    match, mismatch, gap, sp, em, al, max_al, max_tag));                                   \
+    } while (0)
+    if (NIB && R == 6) GAD_FT_LAUNCH(NIB ? 6 : 0);
+    else if (NIB && R == 4) GAD_FT_LAUNCH(NIB ? 4 : 0);
+    else if (NIB && R == 3) GAD_FT_LAUNCH(NIB ? 3 : 0);
+    else GAD_FT_LAUNCH(0);
+#undef GAD_FT_LAUNCH
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
 template <int GS>
 int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int stride, int match, int mismatch,
-                   int gap, int32_t *sp, int32_t *em, int32_t *al, int32_t *max_al, cudaStream_t st)
+                   int gap, int32_t *sp, int32_t *em, int32_t *al, unsigned long long *max_al, unsigned long long max_tag, cudaStream_t st)
 {
     const int threads = 256;
     const long long groups_per_block = threads / GS;
@@ -331,10 +899,10 @@ int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int str
     }();
     if (force_paired < 0 ? R >= 8 : force_paired != 0)
         fitness_kernel<GS, true><<<(unsigned)blocks, threads, 0, st>>>(boards, rowlen, P, R, stride, match, mismatch,
-                                                                        gap, sp, em, al, max_al);
+                                                                        gap, sp, em, al, max_al, max_tag);
     else
         fitness_kernel<GS, false><<<(unsigned)blocks, threads, 0, st>>>(boards, rowlen, P, R, stride, match, mismatch,
-                                                                         gap, sp, em, al, max_al);
+                                                                         gap, sp, em, al, max_al, max_tag);
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
@@ -343,7 +911,7 @@ int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int str
 
 extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
                            int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
-                           int32_t *d_max_al, void *stream)
+                           int64_t *d_max_al, void *stream)
 {
     GAD_REQUIRE(P >= 0 && R >= 1 && R <= 255, "gad_fitness: need P >= 0 and 1 <= R <= 255 (got P=%lld R=%d)",
                 (long long)P, R);
@@ -353,7 +921,12 @@ extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int 
     GAD_REQUIRE(d_boards && d_rowlen && d_sp && d_em && d_al, "gad_fitness: null device pointer");
     if (P == 0) return GAD_OK;
     cudaStream_t st = gad_stream(stream);
-    if (d_max_al) GAD_CUDA(cudaMemsetAsync(d_max_al, 0, sizeof(int32_t), st));
+    // max(al) without a memset per pass: every launch ORs a fresh, growing tag into the bits above the width, so the
+    // atomicMax of this pass beats whatever an earlier pass left behind (44-bit tag: never wraps in practice)
+    static std::atomic<unsigned long long> launch_tag{0};
+    unsigned long long *max_al = reinterpret_cast<unsigned long long *>(d_max_al);
+    const unsigned long long max_tag = max_al ? (++launch_tag) << GAD_MAX_AL_BITS : 0ull;
+    GAD_REQUIRE(!max_al || stride < (1 << GAD_MAX_AL_BITS), "gad_fitness: stride %d does not fit the max_al encoding", stride);
     // lanes per board from the expected width (a performance hint only: wider boards take more trips)
     int width = width_hint > 0 && width_hint < stride ? width_hint : stride;
     int units = (width + 15) / 16;
@@ -361,7 +934,26 @@ extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int 
     // per-board reduction overhead) - measured on c4: 56.5 % -> 62.6 % of the HBM peak
     if (units >= 8 && P >= 4096) units = (units + 1) / 2;
     if (const char *g = getenv("GAD_FITNESS_GS")) units = atoi(g) > 0 ? atoi(g) : units;      // tuning override: lanes per board
-#define GAD_FIT(GS) launch_fitness<GS>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, d_max_al, st)
+    // TMA-staged kernel (default): live width up to 256 bytes, 16-byte aligned board base, enough boards to fill the SMs.
+    // GAD_FITNESS_TMA=0 keeps the register-staged kernel (A/B).
+    const char *tma_env = getenv("GAD_FITNESS_TMA");
+    const int use_tma = tma_env ? atoi(tma_env) : 1;
+    if (use_tma && width <= 256 && ((uintptr_t)d_boards & 15) == 0 && P >= 2048) {
+        int rc = 1;
+#define GAD_FIT_TMA(GS)                                                                                                   \
+    rc = R <= 15 ? launch_fitness_tma<GS, true>(d_boards, d_rowlen, P, R, stride, width, match, mismatch, gap, d_sp, d_em, \
+                                                d_al, max_al, max_tag, st)                                                        \
+                 : launch_fitness_tma<GS, false>(d_boards, d_rowlen, P, R, stride, width, match, mismatch, gap, d_sp,      \
+                                                 d_em, d_al, max_al, max_tag, st)
+        if (units <= 1) GAD_FIT_TMA(1);
+        else if (units <= 2) GAD_FIT_TMA(2);
+        else if (units <= 4) GAD_FIT_TMA(4);
+        else if (units <= 8) GAD_FIT_TMA(8);
+        else GAD_FIT_TMA(16);
+#undef GAD_FIT_TMA
+        if (rc <= 0) return rc;                            // launched (0) or failed (< 0); 1 = shape outside the TMA path
+    }
+#define GAD_FIT(GS) launch_fitness<GS>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, max_al, max_tag, st)
     if (units <= 1) return GAD_FIT(1);
     if (units <= 2) return GAD_FIT(2);
     if (units <= 4) return GAD_FIT(4);
@@ -369,6 +961,55 @@ extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int 
     if (units <= 16) return GAD_FIT(16);
     return GAD_FIT(32);
 #undef GAD_FIT
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measurement hook (bench.py): what a launch that only READS the live cells of the population costs.
+// One uint4 (16 columns) per thread and trip, consecutive threads on consecutive units of a row, every
+// SM full, no arithmetic beyond an XOR, one 16-byte result per block - the speed of light of a single
+// pass over these bytes at this launch size. The fitness kernel is reported against it next to the
+// HBM peak: at c3 a launch carries only 25 MB, which the memory system can stream in about 4 us, so
+// launch ramp and drain (several microseconds per launch whatever the kernel does) set the floor.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256, 8)
+probe_read_kernel(const uint8_t *__restrict__ boards, long long n_items, int units, int row_units, uint4 *__restrict__ sink)
+{
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += step) {
+        const long long row = i / units;
+        const int u = (int)(i - row * units);
+        const uint4 x = reinterpret_cast<const uint4 *>(boards)[row * row_units + u];
+        acc.x ^= x.x;
+        acc.y ^= x.y;
+        acc.z ^= x.z;
+        acc.w ^= x.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x ^= __shfl_xor_sync(0xFFFFFFFFu, acc.x, o);
+        acc.y ^= __shfl_xor_sync(0xFFFFFFFFu, acc.y, o);
+        acc.z ^= __shfl_xor_sync(0xFFFFFFFFu, acc.z, o);
+        acc.w ^= __shfl_xor_sync(0xFFFFFFFFu, acc.w, o);
+    }
+    if ((threadIdx.x & 31) == 0 && sink) atomicXor(reinterpret_cast<unsigned int *>(sink) + ((threadIdx.x >> 5) & 3), acc.x ^ acc.y ^ acc.z ^ acc.w);
+}
+}  // namespace
+
+extern "C" int gad_probe_read(const uint8_t *d_boards, int64_t P, int R, int stride, int width, void *d_sink16, void *stream)
+{
+    GAD_REQUIRE(d_boards && P >= 0 && R >= 1 && stride >= 16 && stride % 16 == 0 && width >= 1 && width <= stride,
+                "gad_probe_read: bad argument");
+    if (P == 0) return GAD_OK;
+    const int units = (width + 15) / 16;
+    const long long n_items = (long long)P * R * units;
+    long long blocks = (n_items + 255) / 256;
+    const long long cap = (long long)GAD_NUM_SMS * 8;
+    if (blocks > cap) blocks = cap;
+    probe_read_kernel<<<(unsigned)blocks, 256, 0, gad_stream(stream)>>>(d_boards, n_items, units, stride >> 4, (uint4 *)d_sink16);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

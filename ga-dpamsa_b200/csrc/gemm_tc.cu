@@ -24,6 +24,15 @@
 // k-blocks (32 MMAs): each chunk accumulates into one of two TMEM buffers (2 x 256 columns) from zero
 // and the epilogue warps add the finished chunk into fp32 registers with round-to-nearest while the
 // next chunk runs in the other buffer - the same promotion DeepGEMM applies to FP8 on Hopper.
+// Canonical summation order and split-K (fused layers = l1): the k-loop is cut into K_SLICES fixed slices of
+// whole chunks; a slice's chunks are folded left to right into a partial p_s and the result is
+// ((p_0 + p_1) + p_2) + p_3 - for EVERY launch shape, so a state's Q-values do not depend on the batch it is
+// evaluated in (duplicate elimination and sharding change the batches; greedy actions must not move).
+// Large batches: one unit runs all slices and keeps the running total in an L2-resident scratch tile between
+// slices. Small batches (fewer tiles than SMs: the lock-step episodes after duplicate elimination) are latency-bound by
+// the 372 k-blocks of one tile: there ksplit = 2 or 4 units per column half each run K_SLICES / ksplit slices
+// and write their partials to a workspace that splitk_reduce_kernel folds in the same order (+ bias,
+// LeakyReLU, fp16 split).
 #include "gad_common.cuh"
 
 #include <cuda.h>
@@ -47,6 +56,7 @@ constexpr int EPI_WARPS = 8;                // 2 per TMEM lane quarter, each own
 // of two - a third less L2 -> shared-memory traffic for the same MMAs.
 constexpr int BKF = 32;
 constexpr int CHUNK_KB_F = 6;               // fused k-blocks per TMEM accumulation chunk = 36 MMAs
+constexpr int K_SLICES = 4;                 // canonical k-slices of a fused layer (see the header comment)
 
 template <int BN, bool FUSED = false> struct Cfg {
     static constexpr int A_BYTES = FUSED ? BM * BKF * 2 : BM * BK * 2;          // one tile (hi or lo)
@@ -70,7 +80,8 @@ template <int BN, bool SPLIT_OUT, bool FUSED = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_bh, const float *__restrict__ bias, float out_scale, void *__restrict__ Cout, int ldc, int lo_offset,
-                      const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky, int tail_split)
+                      const int32_t *__restrict__ m_ptr, long long m_fixed, int N, int K, int leaky, int tail_split,
+                      float *__restrict__ ws, long long ws_rows, int ws_ld, float *__restrict__ scratch, int ksplit)
 {
     using C_ = Cfg<BN, FUSED>;
     extern __shared__ uint8_t smem_raw[];
@@ -99,17 +110,44 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int HN = (BN / 2 + 15) / 16 * 16;                   // UMMA N of a half unit (208 -> 112)
     const long long t_full = (tiles / gridDim.x) * gridDim.x, t_tail = tiles - t_full;
     const bool split = CAN_SPLIT && tail_split && t_tail > 0 && 2 * t_tail <= (long long)gridDim.x;
-    const long long units = split ? t_full + 2 * t_tail : tiles;
-    auto decode = [&](long long u, int &m_blk, int &n_blk) {      // returns -1 for a whole tile, else the column half
+    // split-K launches (ksplit > 1, fused only): every tile is dealt as 2 column halves x ksplit k-slice groups
+    const int ks = FUSED ? ksplit : 1;
+    constexpr int HS = CAN_SPLIT ? 2 : 1;
+    const long long units = ks > 1 ? tiles * HS * ks : (split ? t_full + 2 * t_tail : tiles);
+    const int nchunks = (total_kb + CHUNK - 1) / CHUNK;
+    auto slice_chunk0 = [&](int sl) { return (int)(((long long)nchunks * sl) / K_SLICES); };      // first chunk of slice sl
+    // returns -1 for a whole tile, else the column half; [s0, s1) = the canonical k-slices the unit covers
+    auto decode = [&](long long u, int &m_blk, int &n_blk, int &s0, int &s1) {
         long long t = u;
         int hsel = -1;
-        if (split && u >= t_full) {
+        s0 = 0;
+        s1 = FUSED ? K_SLICES : 1;
+        if (ks > 1) {
+            t = u / (HS * ks);
+            const int rem = (int)(u % (HS * ks));
+            if (CAN_SPLIT) hsel = rem / ks;
+            const int per = K_SLICES / ks;
+            s0 = (rem % ks) * per;
+            s1 = s0 + per;
+        } else if (split && u >= t_full) {
             t = t_full + ((u - t_full) >> 1);
             hsel = (int)((u - t_full) & 1);
         }
         m_blk = (int)(t / tiles_n);
         n_blk = (int)(t % tiles_n);
         return hsel;
+    };
+    // k-block range of slices [s0, s1) (fused) or of the whole tile
+    auto kb_range = [&](int s0, int s1, int &kb_lo, int &kb_hi) {
+        if (!FUSED) {
+            kb_lo = 0;
+            kb_hi = total_kb;
+            return;
+        }
+        kb_lo = slice_chunk0(s0) * CHUNK;
+        kb_hi = slice_chunk0(s1) * CHUNK;
+        if (kb_hi > total_kb) kb_hi = total_kb;
+        if (kb_lo > kb_hi) kb_lo = kb_hi;
     };
 
     if (threadIdx.x == 0) {
@@ -139,14 +177,15 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             for (long long t = blockIdx.x; t < units; t += gridDim.x) {
-                int m_blk, n_blk;
-                const int hsel = decode(t, m_blk, n_blk);
+                int m_blk, n_blk, s0, s1, kb_lo, kb_hi;
+                const int hsel = decode(t, m_blk, n_blk, s0, s1);
+                kb_range(s0, s1, kb_lo, kb_hi);
                 if constexpr (FUSED) {
                     // a half unit loads only its HN rows of W (box of map_bh), starting at row 0 or BN - HN of the tile
                     const CUtensorMap *mb = hsel < 0 ? &map_b : &map_bh;
                     const int b_row = n_blk * BN + (hsel > 0 ? BN - HN : 0);
                     const uint32_t bytes = hsel < 0 ? (uint32_t)C_::STAGE_BYTES : (uint32_t)(2 * C_::A_BYTES + 2 * HN * BKF * 2);
-                    for (int kb = 0; kb < total_kb; ++kb) {
+                    for (int kb = kb_lo; kb < kb_hi; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_u32(smem + stage * C_::STAGE_BYTES);
                         const uint32_t sal = sa + C_::A_BYTES, sb = sal + C_::A_BYTES, sbl = sb + C_::B_BYTES;
@@ -186,16 +225,17 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             long long chunk = 0;                                                  // running chunk counter (buffer = chunk & 1)
             for (long long t = blockIdx.x; t < units; t += gridDim.x) {
-                int m_blk, n_blk;
-                const int hsel = decode(t, m_blk, n_blk);
+                int m_blk, n_blk, s0, s1, kb_lo, kb_hi;
+                const int hsel = decode(t, m_blk, n_blk, s0, s1);
+                kb_range(s0, s1, kb_lo, kb_hi);
                 const uint32_t idesc_u = hsel < 0 ? idesc : make_idesc(HN);
                 (void)n_blk;
-                for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK, ++chunk) {
+                for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += CHUNK, ++chunk) {
                     const int as = (int)(chunk & 1);
                     mbar_wait(tempty0 + 8 * as, (uint32_t)((chunk >> 1) & 1) ^ 1);    // epilogue has drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tmem_d = tmem_base + as * ACC_COLS;
-                    const int kb1 = kb0 + CHUNK < total_kb ? kb0 + CHUNK : total_kb;
+                    const int kb1 = kb0 + CHUNK < kb_hi ? kb0 + CHUNK : kb_hi;
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(full0 + 8 * stage, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -237,8 +277,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         long long chunk = 0;
         for (long long t = blockIdx.x; t < units; t += gridDim.x) {
-            int m_blk, n_blk;
-            const int hsel = decode(t, m_blk, n_blk);
+            int m_blk, n_blk, s0, s1;
+            const int hsel = decode(t, m_blk, n_blk, s0, s1);
             // columns of this warp: TMEM columns [col_t, col_t + ncols) of the accumulator = tile columns [col_o, ...)
             int col_t = half * HALF, col_o = half * HALF, ncols = HALF;
             if (hsel >= 0) {                               // half unit: BN/2 useful columns, dealt 8-aligned to the two warps
@@ -251,26 +291,80 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             float acc[HALF];
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
-            for (int kb0 = 0; kb0 < total_kb; kb0 += CHUNK, ++chunk) {
-                const int as = (int)(chunk & 1);
-                mbar_wait(tfull0 + 8 * as, (uint32_t)((chunk >> 1) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_COLS + col_t;
-#pragma unroll
-                for (int g = 0; g < NLD; ++g) {
-                    if (8 * g >= ncols) break;
-                    uint32_t r[8];
-                    tmem_ld8(taddr + 8 * g, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[8 * g + u] += __uint_as_float(r[u]);       // fp32 RN promotion
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * as);
-            }
             const long long row = (long long)m_blk * BM + quarter * 32 + lane;
             const int n0 = n_blk * BN + col_o;
+            // Where this thread parks slice partials, as float4 units laid out [column / 4][tile row] so that the 32
+            // lanes of a warp (32 consecutive rows) store 512 contiguous bytes: the split-K workspace
+            // ws[slice][m tile][column / 4][tile row] (ksplit > 1), or this CTA's running-total tile (whole-K units).
+            float4 *park = nullptr;
+            size_t park_slice = 0;
+            if constexpr (FUSED) {
+                if (ks > 1) {
+                    park = reinterpret_cast<float4 *>(ws) + ((size_t)m_blk * (ws_ld >> 2) + (n0 >> 2)) * BM + quarter * 32 + lane;
+                    park_slice = (size_t)(ws_rows / BM) * (ws_ld >> 2) * BM;
+                } else {
+                    park = reinterpret_cast<float4 *>(scratch) + ((size_t)blockIdx.x * (BN >> 2) + (col_o >> 2)) * BM + quarter * 32 + lane;
+                }
+            }
+            for (int sl = s0; sl < s1; ++sl) {
+                int c_lo = 0, c_hi = nchunks;
+                if constexpr (FUSED) {
+                    c_lo = slice_chunk0(sl);
+                    c_hi = slice_chunk0(sl + 1);
+                }
+                for (int c = c_lo; c < c_hi; ++c, ++chunk) {
+                    const int as = (int)(chunk & 1);
+                    mbar_wait(tfull0 + 8 * as, (uint32_t)((chunk >> 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * ACC_COLS + col_t;
+#pragma unroll
+                    for (int g = 0; g < NLD; ++g) {
+                        if (8 * g >= ncols) break;
+                        uint32_t r[8];
+                        tmem_ld8(taddr + 8 * g, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc[8 * g + u] += __uint_as_float(r[u]);       // fp32 RN promotion
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+                }
+                if constexpr (FUSED) {
+                    if (ks > 1) {                                  // p_sl goes to the workspace; splitk_reduce_kernel folds
+                        float4 *dst = park + (size_t)sl * park_slice;
+#pragma unroll
+                        for (int j = 0; j < HALF; j += 4) {
+                            if (j >= ncols) break;
+                            dst[(size_t)(j >> 2) * BM] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+                    } else if (sl > 0) {                           // running total ((p_0 + p_1) + p_2) + p_3, in this order
+#pragma unroll
+                        for (int j = 0; j < HALF; j += 4) {
+                            if (j >= ncols) break;
+                            const float4 t = park[(size_t)(j >> 2) * BM];         // this thread's own earlier store
+                            acc[j] = t.x + acc[j];
+                            acc[j + 1] = t.y + acc[j + 1];
+                            acc[j + 2] = t.z + acc[j + 2];
+                            acc[j + 3] = t.w + acc[j + 3];
+                        }
+                    }
+                    if (ks == 1 && sl + 1 < K_SLICES) {            // park the running total, start the next slice from zero
+#pragma unroll
+                        for (int j = 0; j < HALF; j += 4) {
+                            if (j >= ncols) break;
+                            park[(size_t)(j >> 2) * BM] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+                    }
+                }
+            }
+            if constexpr (FUSED) {
+                if (ks > 1) continue;
+            }
             if (row < M) {
 #pragma unroll
                 for (int j = 0; j < HALF; j += 8) {
@@ -322,6 +416,59 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// Second half of a split-K launch: out = act((((p_0 + p_1) + p_2) + p_3) * 2^-s + bias) as (hi | lo) fp16, the
+// same fold the whole-K units do through their running total. One thread per (row, 8 columns); partials are
+// float4 units laid out [slice][m tile][column / 4][tile row].
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float *__restrict__ ws, long long ws_rows, int ws_ld, const int32_t *__restrict__ m_ptr,
+                     long long m_fixed, int N, const float *__restrict__ bias, float out_scale, int leaky,
+                     __half *__restrict__ out, int ldc, int lo_offset)
+{
+    const long long M = m_ptr ? (long long)*m_ptr : m_fixed;
+    const int groups = (N + 7) / 8;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r_in = (int)(i % BM);                       // consecutive threads = consecutive rows of one tile: coalesced reads
+    const long long rest = i / BM;
+    const int n0 = (int)(rest % groups) * 8;
+    const long long m_blk = rest / groups;
+    const long long row = m_blk * BM + r_in;
+    if (row >= M) return;
+    const size_t slice = (size_t)(ws_rows / BM) * (ws_ld >> 2) * BM;
+    const float4 *src = reinterpret_cast<const float4 *>(ws) + ((size_t)m_blk * (ws_ld >> 2) + (n0 >> 2)) * BM + r_in;
+    float t[8];
+#pragma unroll
+    for (int sl = 0; sl < K_SLICES; ++sl) {
+        const float4 a = src[sl * slice];
+        const float4 b = src[sl * slice + BM];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = sl == 0 ? v[u] : t[u] + v[u];
+    }
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        float x = 0.f;
+        if (n0 + u < N) {
+            x = fmaf(t[u], out_scale, bias[n0 + u]);
+            if (leaky) x = x > 0.f ? x : 0.01f * x;
+        }
+        hi[u] = __float2half_rn(x);
+        lo[u] = __float2half_rn(x - __half2float(hi[u]));
+    }
+    __half *dh = out + (size_t)row * ldc + n0;
+    if (n0 + 7 < N) {
+        *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(dh + lo_offset) = *reinterpret_cast<const uint4 *>(lo);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (n0 + u < N) {
+                dh[u] = hi[u];
+                dh[lo_offset + u] = lo[u];
+            }
     }
 }
 
@@ -412,6 +559,12 @@ int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, 
     if (!rc && L->fused)                                   // box of half a tile's rows, rounded up to a valid UMMA N
         rc = encode_map((CUtensorMap *)L->map_bh, L->W2, L->Npad, 2ll * L->Kpad, (BN / 2 + 15) / 16 * 16, true);
     if (rc) return rc;
+    if (L->fused) {
+        // split-K workspace (K_SLICES partial tiles for up to TC_SPLITK_MAX_ROWS rows) and the whole-K units'
+        // scratch (one running-total tile of 128 x BN per CTA); both stay L2-resident
+        GAD_CUDA(cudaMalloc((void **)&L->ws, (size_t)K_SLICES * TC_SPLITK_MAX_ROWS * L->Npad * sizeof(float)));
+        GAD_CUDA(cudaMalloc((void **)&L->scratch, (size_t)GAD_NUM_SMS * BM * BN * sizeof(float)));
+    }
     if (BN == TC_BN_L1) return set_smem_attr<TC_BN_L1>();
     if (BN == TC_BN_L2) return set_smem_attr<TC_BN_L2>();
     return set_smem_attr<TC_BN_L3>();
@@ -420,7 +573,10 @@ int tc_layer_init(TcLayer *L, const float *d_W, const float *h_W, int N, int K, 
 void tc_layer_free(TcLayer *L)
 {
     if (L->W2) cudaFree(L->W2);
+    if (L->ws) cudaFree(L->ws);
+    if (L->scratch) cudaFree(L->scratch);
     L->W2 = nullptr;
+    L->ws = L->scratch = nullptr;
 }
 
 int tc_layer_bind_a(TcLayer *L, const void *d_A2, long long rows)
@@ -438,23 +594,53 @@ int run_bn(const TcLayer *L, const float *d_bias, void *d_out, int ldc, int lo_o
         const char *e = getenv("GAD_L1_TAILSPLIT");
         return e ? atoi(e) : 1;
     }();
-    const long long want = L->fused && tail_split ? 2 * tiles : tiles;       // half units need up to two CTAs per tile
+    static const int ksplit_max = [] {                            // A/B switch: GAD_L1_KSPLIT=1 never splits K
+        const char *e = getenv("GAD_L1_KSPLIT");
+        return e ? atoi(e) : K_SLICES;
+    }();
+    // small launches of a fused layer: 2 column halves x ksplit k-slice groups per tile, until about two rounds of units
+    // Cost model in tile-times: whole tiles take ceil(tiles / SMs) rounds (a partial last round that fits twice
+    // runs as column halves: half a round); split units are 1 / (2 ksplit) of a tile each. Split when that saves
+    // at least 15 % (the fold kernel and the workspace round trip are not free).
+    int ksplit = 1;
+    if (L->fused && split_out && L->ws && (m_max + BM - 1) / BM * BM <= TC_SPLITK_MAX_ROWS) {
+        const long long full = tiles / GAD_NUM_SMS, tail = tiles % GAD_NUM_SMS;
+        double best = (double)full + (tail == 0 ? 0.0 : (tail_split && 2 * tail <= GAD_NUM_SMS ? 0.5 : 1.0));
+        best *= 0.85;
+        for (int s = 2; s <= K_SLICES && s <= ksplit_max; s *= 2) {
+            const long long units = tiles * 2 * s;
+            const double cost = (double)((units + GAD_NUM_SMS - 1) / GAD_NUM_SMS) / (2.0 * s);
+            if (cost < best) {
+                best = cost;
+                ksplit = s;
+            }
+        }
+    }
+    const long long ws_rows = (m_max + BM - 1) / BM * BM;
+    long long want = L->fused && tail_split ? 2 * tiles : tiles;       // half units need up to two CTAs per tile
+    if (ksplit > 1) want = 2 * tiles * ksplit;
     const unsigned grid = (unsigned)(want < GAD_NUM_SMS ? want : GAD_NUM_SMS);
     const CUtensorMap &ma = *(const CUtensorMap *)L->map_a, &mb = *(const CUtensorMap *)L->map_b;
     const CUtensorMap &mh = *(const CUtensorMap *)(L->fused ? L->map_bh : L->map_b);
     if (L->fused && split_out)
         gemm_split_f16_kernel<BN, true, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
-            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split, L->ws, ws_rows, L->Npad, L->scratch, ksplit);
     else if (L->fused)
         gemm_split_f16_kernel<BN, false, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN, true>::SMEM, st>>>(
-            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split, L->ws, ws_rows, L->Npad, L->scratch, ksplit);
     else if (split_out)
         gemm_split_f16_kernel<BN, true><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
-            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split, L->ws, ws_rows, L->Npad, L->scratch, ksplit);
     else
         gemm_split_f16_kernel<BN, false><<<grid, 64 + 32 * EPI_WARPS, Cfg<BN>::SMEM, st>>>(
-            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split);
+            ma, mb, mh, d_bias, L->inv_scale, d_out, ldc, lo_offset, d_m, m_max, L->N, L->Kpad, leaky, tail_split, L->ws, ws_rows, L->Npad, L->scratch, ksplit);
     GAD_LAUNCH_CHECK();
+    if (ksplit > 1) {
+        const long long threads = ws_rows * ((L->N + 7) / 8);
+        splitk_reduce_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+            L->ws, ws_rows, L->Npad, d_m, m_max, L->N, d_bias, L->inv_scale, leaky, (__half *)d_out, ldc, lo_offset);
+        GAD_LAUNCH_CHECK();
+    }
     return GAD_OK;
 }
 

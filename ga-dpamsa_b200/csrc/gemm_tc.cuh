@@ -6,12 +6,15 @@
 #define TC_BN_L1 208       // l1: 1028 outputs pad to 5 x 208 = 1040 (1.2 % waste)
 #define TC_BN_L2 128       // l2: 512 outputs = 4 x 128
 #define TC_BN_L3 64        // l3: 2^rows - 1 <= 64 outputs
+#define TC_SPLITK_MAX_ROWS 4096   // launches of a fused layer with at most this many rows may split K over CTAs
 
 struct TcLayer {
     int N = 0, K = 0, Kpad = 0, BN = 0, Npad = 0;
     int fused = 0;                           // 1: hi and lo tiles of a 32-wide k-block share a stage (64B swizzle)
     float scale = 1.f, inv_scale = 1.f;      // weights are stored as w * 2^s; the epilogue multiplies by 2^-s
     void *W2 = nullptr;                      // fp16 [Npad][2*Kpad] = (hi | lo), zero beyond N and K
+    float *ws = nullptr;                     // fused layers: split-K partials [K_SLICES][rows][Npad]
+    float *scratch = nullptr;                // fused layers: parked slice partials of whole-K units, per CTA
     alignas(64) unsigned char map_a[128];    // CUtensorMap of the activations (hi | lo), rebound when they move
     alignas(64) unsigned char map_b[128];    // CUtensorMap of W2
     alignas(64) unsigned char map_bh[128];   // fused layers: the same with a box of half a tile's rows (tail units)

@@ -11,6 +11,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <new>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 
@@ -132,9 +135,9 @@ extern "C" int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents,
 // GA.py:71-94: n_clone exact copies first, then every row of every other individual gets h_ngaps[r] gaps
 // inserted one at a time at randint(0, len_now - 1) (the row grows with every insert; never appended).
 // Output in the library's layout: uint8 boards[P][R][stride] (gap code beyond each row), int32 rowlen[P][R].
-extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
-                                      int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
-                                      uint8_t *h_boards, int32_t *h_rowlen, int stride)
+static int population_host_impl(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
+                                int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
+                                uint8_t *h_boards, int32_t *h_rowlen, int stride)
 {
     GAD_REQUIRE(mt_state && h_seqs && h_seqlen && h_ngaps && h_boards && h_rowlen, "gad_mt_population_host: null pointer");
     GAD_REQUIRE(R >= 1 && P >= 0 && n_clone >= 0 && n_clone <= P && stride >= 1, "gad_mt_population_host: bad sizes");
@@ -161,11 +164,13 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
     int64_t block = per_board > 0 ? (4ll << 20) / per_board : 16384;        // <= 16 MB of positions per buffer
     block = block > 16384 ? 16384 : (block < 256 ? 256 : block);
     if (const char *e = getenv("GAD_HOST_BLOCK")) block = atoi(e) > 0 ? atoi(e) : block;          // test hook: small blocks
+    std::atomic<int> worker_failed{0};
     std::vector<int32_t> pos[2];
     pos[0].resize((size_t)block * per_board + 1);
     pos[1].resize((size_t)block * per_board + 1);
     auto build = [&](int64_t p0, int64_t p1, const int32_t *at_all) {         // boards [p0, p1) from their positions
         auto work = [&](int w) {
+          try {                                            // nothing may escape a std::thread body (std::terminate)
             std::vector<int> gaps((size_t)max_gaps + 1);
             const int64_t share = (p1 - p0 + n_workers - 1) / n_workers;         // contiguous boards per worker
             const int64_t lo = p0 + share * w, hi = lo + share < p1 ? lo + share : p1;
@@ -181,6 +186,9 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
                     }
                     h_rowlen[(size_t)p * R + r] = len0 + ng;
                 }
+          } catch (...) {
+            worker_failed.store(1);
+          }
         };
         if (n_workers == 1 || p1 - p0 < 64) {
             for (int w = 0; w < n_workers; ++w) work(w);
@@ -197,6 +205,10 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
         for (auto &t : th) t.join();
     };
     std::thread builder;
+    struct Joiner {                                        // an exception on the calling thread must not leave a joinable thread
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } joiner{builder};
     int cur = 0;
     for (int64_t p0 = 0; p0 < P; p0 += block, cur ^= 1) {
         const int64_t p1 = p0 + block < P ? p0 + block : P;
@@ -215,6 +227,10 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
         }
     }
     if (builder.joinable()) builder.join();
+    if (worker_failed.load()) {
+        gad_set_error("gad_mt_population_host: a board-building worker ran out of memory");
+        return GAD_ENOMEM;
+    }
     mt_state[624] = (uint32_t)g.pos;
     return GAD_OK;
 }
@@ -224,10 +240,10 @@ extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs,
 // are materialised, densely, into h_boards / h_rowlen (ceil((P - own_first) / own_step) boards).
 // Gap positions are tracked instead of shifting the row at every insert: inserting at position a moves every
 // earlier gap at or right of a one cell to the right - O(gaps^2) per row instead of O(gaps * length).
-extern "C" int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
-                                            int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
-                                            int64_t own_first, int64_t own_step, uint8_t *h_boards, int32_t *h_rowlen,
-                                            int stride)
+static int population_shard_host_impl(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
+                                      int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
+                                      int64_t own_first, int64_t own_step, uint8_t *h_boards, int32_t *h_rowlen,
+                                      int stride)
 {
     GAD_REQUIRE(mt_state && h_seqs && h_seqlen && h_ngaps && h_boards && h_rowlen, "gad_mt_population_shard_host: null pointer");
     GAD_REQUIRE(R >= 1 && P >= 0 && n_clone >= 0 && n_clone <= P && stride >= 1 && own_step >= 1 && own_first >= 0 &&
@@ -270,4 +286,43 @@ extern "C" int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h
     }
     mt_state[624] = (uint32_t)g.pos;
     return GAD_OK;
+}
+
+// C-ABI entry points: no C++ exception may cross them (std::bad_alloc from the position buffers, std::system_error
+// from thread creation) - they become GAD_ENOMEM / GAD_ECUDA through gad_last_error().
+template <typename F>
+static int guarded(const char *who, F &&f)
+{
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        gad_set_error("%s: out of host memory", who);
+        return GAD_ENOMEM;
+    } catch (const std::exception &e) {
+        gad_set_error("%s: %s", who, e.what());
+        return GAD_ECUDA;
+    } catch (...) {
+        gad_set_error("%s: unknown C++ exception", who);
+        return GAD_ECUDA;
+    }
+}
+
+extern "C" int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
+                                      int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
+                                      uint8_t *h_boards, int32_t *h_rowlen, int stride)
+{
+    return guarded("gad_mt_population_host", [&] {
+        return population_host_impl(mt_state, h_seqs, h_seqlen, seq_stride, h_ngaps, R, P, n_clone, h_boards, h_rowlen, stride);
+    });
+}
+
+extern "C" int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen,
+                                            int seq_stride, const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone,
+                                            int64_t own_first, int64_t own_step, uint8_t *h_boards, int32_t *h_rowlen,
+                                            int stride)
+{
+    return guarded("gad_mt_population_shard_host", [&] {
+        return population_shard_host_impl(mt_state, h_seqs, h_seqlen, seq_stride, h_ngaps, R, P, n_clone, own_first, own_step,
+                                          h_boards, h_rowlen, stride);
+    });
 }

@@ -1346,11 +1346,8 @@ int launch_forward(gad_qnet *q, const uint8_t *tok_in, const int32_t *active, co
         if (rc) return rc;
     } else if (encode_fa_smem_bytes(q->L) <= 110 * 1024 && !(enc && (enc[0] == 'm' || enc[0] == 's'))) {
         const int bytes = encode_fa_smem_bytes(q->L);
-        static int fa_attr_bytes = 0;                      // opt in to > 48 KB of dynamic shared memory once per size
-        if (bytes > 48 * 1024 && bytes != fa_attr_bytes) {
+        if (bytes > 48 * 1024)                             // per device and cheap: set on every launch, like the other encoders
             GAD_CUDA(cudaFuncSetAttribute(encode_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            fa_attr_bytes = bytes;
-        }
         long long per_sm = (224 * 1024) / (bytes + 1024);
         if (per_sm > 4) per_sm = 4;
         const long long grid = n_max < (long long)GAD_NUM_SMS * per_sm ? n_max : (long long)GAD_NUM_SMS * per_sm;
@@ -1665,6 +1662,9 @@ extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int
     const char *dd = getenv("GAD_MUTATE_DEDUP");
     const int dedup = !(dd && dd[0] == '0');
     int rc = ensure_episodes(q, M);
+    // activation buffers for the largest chunk that can occur (not for this call's distinct windows: their number
+    // changes from generation to generation and re-allocating in between costs more than the memory)
+    if (!rc) rc = ensure_states(q, M < kMaxBatch ? M : kMaxBatch);
     if (rc) return rc;
     long long slots = 1024;
     while (slots < 2 * M) slots <<= 1;

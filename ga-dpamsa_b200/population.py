@@ -16,6 +16,7 @@ import torch
 import _native as nat
 
 GAP = 5
+MAX_AL_MASK = (1 << 20) - 1          # include/gadpamsa.h GAD_MAX_AL_MASK
 MODE_ID = nat.MODE_ID
 
 
@@ -94,7 +95,7 @@ class DevicePopulation:
             self.cur.rowlen[:self.n].copy_(rowlen)
         self.alt = None                          # second buffer, allocated by the first selection
         dev = self.device
-        self.max_al = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.max_al = torch.zeros(1, dtype=torch.int64, device=dev)     # tagged: low 20 bits = widest cleaned board
         self.hof_board = torch.full((self.R, self.stride), GAP, dtype=torch.uint8, device=dev)
         self.hof = torch.zeros(8, dtype=torch.int32, device=dev)
         self.hof_valid = False
@@ -163,6 +164,10 @@ class DevicePopulation:
     @property
     def al(self):
         return self.cur.al[:self.n]
+
+    def widest(self) -> int:
+        """Width of the widest board after the last fitness pass (one 8-byte read)."""
+        return int(self.max_al.item()) & MAX_AL_MASK
 
     def scores_numpy(self):
         s = torch.stack((self.cur.sp[:self.n], self.cur.em[:self.n], self.cur.al[:self.n])).cpu().numpy()
@@ -280,9 +285,9 @@ class DevicePopulation:
                  nat.ptr(self._keep), nat.ptr(self._dst), self.n, self.R, self.stride, nat.ptr(d.boards),
                  nat.ptr(d.rowlen), nat.ptr(d.sp), nat.ptr(d.em), nat.ptr(d.al), self._stream())
         self.cur, self.alt = d, s
-        both = torch.stack((self._count[0], self.max_al[0])).cpu()       # one small read: survivor count + widest board
+        both = torch.stack((self._count[0].to(torch.int64), self.max_al[0])).cpu()   # one small read: survivor count + widest board
         self.n = int(both[0])
-        self.width_hint = int(both[1])
+        self.width_hint = int(both[1]) & MAX_AL_MASK
         return self.n
 
     # ------------------------------------------------------------------ a12 / a13

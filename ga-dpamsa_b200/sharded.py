@@ -293,7 +293,14 @@ class DeviceBackend:
     def adopt(self, boards, rowlen, capacity):
         from population import DevicePopulation
         extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
-        need = -(-(int(rowlen.max()) + extra) // 16) * 16
+        # from the global width when this rank owns no individual (population smaller than the world): every
+        # rank must arrive at the same stride, peers read each other's rows with it
+        widest = int(rowlen.max()) if rowlen.size else 0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            w = torch.tensor([widest], dtype=torch.int64, device=self.device if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            widest = int(w.item())
+        need = max(-(-(widest + extra) // 16) * 16, boards.shape[2])
         if boards.shape[2] < need:
             wide = np.full((boards.shape[0], boards.shape[1], need), 5, dtype=np.uint8)
             wide[:, :, :boards.shape[2]] = boards

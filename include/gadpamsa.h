@@ -66,12 +66,21 @@ int gad_stream_sync(void *stream);                         /* synchronises */
  * Outputs (device, int32[P]): sp = sum-of-pairs, em = exact-match columns,
  * al = alignment length after cleaning; the facade forms CS = em / al as a
  * Python float so it is bit-identical to utils.py:128.
- * d_max_al (optional, device int32[1], zeroed by the call) receives
- * max(al) by atomicMax. width_hint (0 = unknown) is the expected board width: it only selects how
- * many lanes share a board, any width up to `stride` stays correct. Requires R <= 255. */
+ * d_max_al (optional, device int64[1], zero-initialised once by the caller) receives max(al) in its low
+ * GAD_MAX_AL_BITS bits: the bits above hold a per-launch tag that grows with every call, so the pass's
+ * atomicMax overrides the previous pass without a memset (read it as value & GAD_MAX_AL_MASK).
+ * width_hint (0 = unknown) is the expected board width: it selects how many lanes share a board and how
+ * many bytes of a row are staged; any width up to `stride` stays correct. Requires R <= 255. */
+#define GAD_MAX_AL_BITS 20
+#define GAD_MAX_AL_MASK ((1ll << GAD_MAX_AL_BITS) - 1)
 int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
                 int match, int mismatch, int gap,
-                int32_t *d_sp, int32_t *d_em, int32_t *d_al, int32_t *d_max_al, void *stream);
+                int32_t *d_sp, int32_t *d_em, int32_t *d_al, int64_t *d_max_al, void *stream);
+
+/* Measurement hook (bench.py): a launch that only reads the live cells (`width` bytes of every row, as
+ * 16-byte units) of P boards and folds them into d_sink16 (device, 16 bytes). What a single pass over
+ * these bytes costs at this launch size, whatever it computes. Asynchronous on `stream`. */
+int gad_probe_read(const uint8_t *d_boards, int64_t P, int R, int stride, int width, void *d_sink16, void *stream);
 
 /* Same pass through HOST buffers (pinned or pageable): H2D of boards+rowlen,
  * the kernel, D2H of sp/em/al and of the cleaned boards+rowlen when

@@ -41,7 +41,7 @@ def assert_parity(pop, weights=(4, -4, -4), stride=None):
     assert np.array_equal(em, oem)
     assert np.array_equal(al, oal)
     assert dev.to_lists() == oboards
-    assert int(dev.max_al.item()) == (int(oal.max()) if len(oal) else 0)
+    assert dev.widest() == (int(oal.max()) if len(oal) else 0)
     return sp, em, al
 
 
@@ -218,3 +218,81 @@ def test_randomized_shape_sweep(gpu):
         pop = O.to_lists(boards, rowlen)
         for weights in ((4, -4, -4), (7, -2, -11)):
             assert_parity(copy.deepcopy(pop), weights=weights, stride=stride)
+
+
+def _ragged_population(rng, P, R, W, stride, gap_p=0.2, stale=True):
+    """P ragged boards with all-gap columns, laid out with the library's invariant: gap code from each row's
+    length up to roundup4(board width); beyond that arbitrary stale bytes (kernels must mask them)."""
+    w = rng.integers(max(1, W - 20), W + 1, size=P)
+    n = np.minimum(w[:, None], np.maximum(0, w[:, None] - rng.integers(0, 10, size=(P, R))))
+    n[np.arange(P), rng.integers(0, R, size=P)] = w                      # at least one row has the full width
+    boards = rng.integers(1, 5, size=(P, R, stride), dtype=np.uint8)
+    boards[rng.random((P, R, stride)) < gap_p] = 5
+    allgap = rng.random((P, 1, stride)) < 0.04
+    boards[np.broadcast_to(allgap, boards.shape)] = 5
+    col = np.arange(stride)[None, None, :]
+    pad_to = ((w + 3) // 4 * 4)[:, None, None]
+    boards[(col >= n[:, :, None]) & (col < pad_to)] = 5
+    if stale:
+        junk = rng.integers(0, 256, size=boards.shape, dtype=np.uint8)
+        boards = np.where(col >= pad_to, junk, boards)
+    else:
+        boards[np.broadcast_to(col >= pad_to, boards.shape)] = 5
+    return boards, n.astype(np.int32)
+
+
+@pytest.mark.parametrize("R,W,stride,hint", [
+    (6, 63, 224, None),      # c3 shape: nibble counters, 4 lanes per board, one unit per lane
+    (3, 32, 64, None),       # 3x30 data
+    (2, 9, 16, None),        # one lane per board
+    (12, 150, 208, None),    # 12x150 (supplement table A6), two units per lane: compaction falls back to global memory
+    (15, 100, 128, None),    # largest nibble-counter row count
+    (16, 100, 128, None),    # smallest byte-counter row count
+    (20, 210, 288, None),    # c4 shape
+    (40, 250, 256, None),    # widest box (256 columns), several flush epochs
+    (6, 120, 224, 63),       # width hint too small: boards wider than the box take the global path inside the launch
+    (6, 63, 224, 500),       # hint larger than the stride
+])
+def test_tma_staged_kernel_against_oracle(gpu, R, W, stride, hint):
+    """The TMA-staged fitness kernel (fitness.cu, populations of at least 2 048 boards) on ragged boards with
+    all-gap columns and stale bytes beyond the board width: scores, cleaned boards and row lengths == the C oracle.
+    Two passes: the second one sees clean boards (nothing to compact) and must change nothing."""
+    import torch
+    from population import DevicePopulation
+    rng = np.random.default_rng(R * 1000 + W)
+    P = 4099                                                        # not a multiple of the box: the last box is partial
+    boards, rowlen = _ragged_population(rng, P, R, W, stride)
+    dev = DevicePopulation.from_numpy(boards.copy(), rowlen.copy())
+    if hint is not None:
+        dev.width_hint = hint
+    for weights in ((4, -4, -4), (7, -2, -11)):
+        sp, em, al = [t.cpu().numpy() for t in dev.fitness(*weights)]
+        torch.cuda.synchronize()
+        ob, orl = boards.copy(), rowlen.copy()
+        osp, oem, oal = O.fitness_population_c(ob, orl, O.Weights(*weights))
+        assert np.array_equal(sp, osp) and np.array_equal(em, oem) and np.array_equal(al, oal)
+        gb, grl = dev.to_numpy()
+        assert np.array_equal(grl, orl)
+        assert O.to_lists(gb, grl) == O.to_lists(ob, orl)
+        assert dev.widest() == int(oal.max())
+
+
+def test_tma_and_register_kernels_agree_at_baseline_shapes(gpu, monkeypatch):
+    """c3 and c4 shaped populations through both fitness kernels (GAD_FITNESS_TMA=0 selects the register-staged
+    one): identical scores and boards."""
+    import torch
+    from population import DevicePopulation
+    rng = np.random.default_rng(11)
+    for R, W, stride, P in ((6, 63, 224, 65536), (20, 210, 288, 16384)):
+        boards, rowlen = _ragged_population(rng, P, R, W, stride, gap_p=0.1)
+        out = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("GAD_FITNESS_TMA", flag)
+            dev = DevicePopulation.from_numpy(boards.copy(), rowlen.copy())
+            sp, em, al = [t.cpu().numpy() for t in dev.fitness(4, -4, -4)]
+            torch.cuda.synchronize()
+            b, r = dev.to_numpy()
+            out[flag] = (sp, em, al, r, O.to_lists(b[:512], r[:512]))
+        for x, y in zip(out["1"][:4], out["0"][:4]):
+            assert np.array_equal(x, y)
+        assert out["1"][4] == out["0"][4]

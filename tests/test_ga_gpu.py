@@ -529,6 +529,73 @@ def test_vertical_crossover_run(gpu, weight_files, cfg, datasets_json):
     assert len({len(r) for r in out}) == 1
 
 
+def test_vertical_crossover_known_answers(gpu, native_lib):
+    """a13: hand-written cases from the written specification (tests/golden/vertical_crossover.json): the device
+    kernel, the oracle's restatement and the specification sentence agree; the cut rule of the plan generator
+    is randint(1, min(width1, width2) - 1) on the same `random` stream as a python restatement."""
+    import json
+    import GA as ga_mod
+    from population import DevicePopulation
+    with open(os.path.join(GOLDEN, "vertical_crossover.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"]:
+        p1, p2, cut, want = case["p1"], case["p2"], case["cut"], case["child"]
+        assert [a[:cut] + b[cut:] for a, b in zip(p1, p2)] == want          # the specification sentence itself
+        assert O.vertical_child(p1, p2, cut) == want
+        dev = DevicePopulation.from_lists([copy.deepcopy(p1), copy.deepcopy(p2)], capacity=4, extra_capacity=8)
+        dev.crossover(np.array([[0, 1, cut]], np.int32), 1)
+        assert dev.to_lists()[2] == want
+        assert dev.to_lists()[:2] == [p1, p2]                                # parents untouched
+    for rule in gold["cut_rule"]:
+        widths = np.array([rule["w1"], rule["w2"]], np.int32)
+        seen = set()
+        for seed in range(40):
+            random.seed(seed)
+            plan = np.empty((8, 3), np.int32)
+            state, meta = ga_mod._mt_state()
+            native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, 2, 3, 8, widths.ctypes.data, plan.ctypes.data)
+            ga_mod._mt_restore(state, meta)
+            after = random.random()
+            random.seed(seed)
+            want = []
+            while len(want) < 8:                                             # GA.py:281-293 with the vertical cut rule
+                a, b = random.choice(range(2)), random.choice(range(2))
+                if a == b:
+                    continue
+                want.append([a, b, random.randint(1, min(int(widths[a]), int(widths[b])) - 1)])
+            assert plan.tolist() == want and random.random() == after
+            seen.update(int(c) for c in plan[:, 2])
+        assert seen == set(rule["cuts"])
+
+
+def test_debug_mode_prints_like_the_reference(gpu, weight_files, cfg, datasets_json, capsys):
+    """a22: GA.run(model, debug_mode=True) materialises the device population for print_population /
+    print_hall_of_fame (GA.py:375-441) after every phase; what it prints is the population the oracle holds."""
+    import GA as ga_mod
+    name, sd = weight_files[(3, 30)]
+    cfg.POPULATION_SIZE, cfg.GA_ITERATIONS = 5, 1
+    seqs = datasets_json["dataset1_6x30bp"]["test0"]
+    random.seed(4)
+    g = ga_mod.GA(seqs, "mo")
+    out = g.run(name, debug_mode=True)
+    text = capsys.readouterr().out
+    random.seed(4)
+    want, score = O.ga_run(seqs, "mo", sd, O.Knobs(POPULATION_SIZE=5, GA_ITERATIONS=1), fast_pareto=True)
+    assert out == want
+    assert text.count("CURRENT POPULATION (Iteration") == 4          # initial + after mutation, selection, crossover
+    assert text.count("Individual 1:") == 4 and "Iteration 1/1..." in text
+    assert "HALL OF FAME - BEST INDIVIDUAL SO FAR:" in text and "Population entirely printed." in text
+    last = text[text.rindex("HALL OF FAME"):]
+    for row in want:
+        assert row in last
+    assert "SP Score: %s" % (score[1],) in last and "CS Score: %s" % (score[2],) in last
+    g2 = ga_mod.GA(seqs, "sp")
+    g2.print_hall_of_fame()
+    g2.print_population()
+    text = capsys.readouterr().out
+    assert "Hall of Fame is empty!" in text and "Empty Population!" in text
+
+
 # ------------------------------------------------------------------------------------------- multi-GPU (section 8(e))
 def _run_sharded_check(world):
     import subprocess
