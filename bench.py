@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py - fitness evals/sec (SP+CS) of the GA-DPAMSA generation loop on B200.
+"""bench.py - fitness evals/sec (SP+CS) and GA generations/sec of the GA-DPAMSA generation loop on B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|c2]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -10,11 +10,23 @@ the named BASELINE.json workload; an "eval" is one board fully scored. Every ste
 FRESH replica of the population (the pass cleans boards in place, so re-scoring the same buffer
 would skip the write-back work); with the replicas the per-step input is also never L2-resident.
 
-One JSON line on rank 0 (see the contract in the task statement): value = device-resident
-throughput, e2e = the same pass through gad_fitness_host with pinned HOST buffers (H2D of the
-boards, D2H of the scores inside the timed region), roofline = algorithmic bytes / measured
-kernel time against the measured HBM copy peak, cpu_baseline = the oracle on the host cores.
---impl reference times the CPU port of the reference's path on the same workload.
+One JSON line on rank 0 (the contract is in the task statement):
+  value         N = 1: the device-resident pass (fitness kernel on boards in HBM). N > 1: the SHARDED pass,
+                ShardedGA.calculate_fitness_score = kernel + all-gather of the scores + the hall-of-fame
+                decision on every rank (`fitness_pass` carries the same measurement at N = 1, so the passes
+                compare like for like; `fitness_kernel_only` carries the bare kernels at N > 1).
+  e2e           the same pass through gad_fitness_host with pinned HOST buffers (H2D of the boards, D2H of
+                the scores inside the timed region).
+  roofline      algorithmic bytes / measured kernel time against the measured HBM copy peak, next to what a
+                launch that only reads the same bytes costs (`stream_read_us`).
+  generation    whole generations/s of GA.run's loop body with the duplicate-episode counters, the
+                duplicate-free workload, GA.run end to end; at N > 1 the sharded loop (weak scaling) with
+                per-rank counters, `strong_scaling_c4` and, on 8 GPUs, `c5`.
+  parity        N = 1: duplicate elimination on == off (score hashes per pass, hall of fame).
+                N > 1: the sharded loop (both exchanges) == the single-GPU facade on the same total population;
+                a mismatch makes the run fail (exit code 3).
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref through oracle/ref_bench.py) on the host cores.
+--impl reference times the reference's own GA.calculate_fitness_score / GA.mutation on the same workload.
 """
 from __future__ import annotations
 
@@ -262,19 +274,59 @@ def seq_strings(rows, cols, seed):
     return ["".join("ATCG-"[v - 1] for v in row) for row in synth_sequences(rows, cols, seed)]
 
 
-def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
+def workload_config(name, stride=None):
+    """The `config` object of the JSON line - identical for both arms (`--impl ours|reference`)."""
+    rows, cols, P, mode, desc = WORKLOADS[name]
+    return {"workload": "%s: %s" % (name, desc), "rows": rows, "cols": cols, "population_per_gpu": P, "mode": mode,
+            "scores": [MATCH, MISMATCH, GAPW], "agent_window": list(AGENTS[name]),
+            "clone_rate": CLONE_RATE, "gap_rate": GAP_RATE, "selection_rate": 0.5, "mutation_rate": 0.25,
+            "l2": "every timed step scores a fresh replica of the population (the replicas together exceed the "
+                  "126 MB L2); the CPU arm scores a bounded sample per step"}
+
+
+def score_hash(sp, em, al):
+    import hashlib
+    import torch
+    return hashlib.sha256(torch.stack((sp, em, al)).to(torch.int32).cpu().numpy().tobytes()).hexdigest()[:16]
+
+
+def duplicate_free_population(rows, cols, P, seed):
+    """A population without duplicate windows: every individual is built from its OWN random base sequences
+    (CLONE_RATE = 0), so every mutation episode is distinct and the Q-net kernels see full batches."""
+    rng = np.random.default_rng(seed)
+    n_gap = max(1, round(cols * GAP_RATE))
+    width = cols + n_gap
+    stride = -(-width // 16) * 16
+    base = rng.integers(1, 5, size=(P, rows, cols), dtype=np.uint8)
+    keys = rng.random((P, rows, width - 1))
+    slots = np.argsort(keys, axis=2)[:, :, :n_gap]
+    is_gap = np.zeros((P, rows, width), dtype=bool)
+    np.put_along_axis(is_gap, slots, True, axis=2)
+    src = np.clip(np.cumsum(~is_gap, axis=2) - 1, 0, cols - 1)
+    vals = np.take_along_axis(base, src, axis=2)
+    vals[is_gap] = 5
+    boards = np.full((P, rows, stride), 5, dtype=np.uint8)
+    boards[:, :, :width] = vals
+    return boards, np.full((P, rows), width, dtype=np.int32)
+
+
+def measure_generations(workload, n_gen, n_warm, world=1, rank=0, weak=True, population=None, duplicate_free=False,
+                        with_extras=True, exchange=None, log_hashes=None):
     """Generations/s of the loop body (mutation -> fitness -> selection -> crossover, each with the
     reference's fitness re-evaluations), with a per-phase breakdown. One GPU: through the GA facade.
-    N GPUs: sharded.ShardedGA over NCCL, population = N x the workload's population (weak scaling),
-    phases bracketed by barriers, time = max over ranks."""
+    N GPUs: sharded.ShardedGA over NCCL; weak scaling = N x the workload's population, strong scaling =
+    the workload's population split over the ranks. Phases bracketed by barriers, time = max over ranks."""
     import random
     import torch
     import torch.distributed as dist
     import config
     rows, cols, P, mode, _ = WORKLOADS[workload]
-    P_total = P * world
+    if population:
+        P = population
+    P_total = P * world if weak else P
     rw, cw = AGENTS[workload]
-    saved = {k: getattr(config, k) for k in ("POPULATION_SIZE", "AGENT_WINDOW_ROW", "AGENT_WINDOW_COLUMN", "GA_ITERATIONS")}
+    saved = {k: getattr(config, k) for k in ("POPULATION_SIZE", "AGENT_WINDOW_ROW", "AGENT_WINDOW_COLUMN", "GA_ITERATIONS",
+                                             "CLONE_RATE")}
     config.POPULATION_SIZE, config.AGENT_WINDOW_ROW, config.AGENT_WINDOW_COLUMN = P_total, rw, cw
 
     def sync():
@@ -289,62 +341,111 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
         if world == 1:
             import GA as ga_mod
             g = ga_mod.GA(seqs, mode)
-            counters = lambda: (g._dev.evals, g._dev.forwards)
-            dedup = lambda: (g._dev.episodes, g._dev.unique_episodes, g._dev.states)
+            pop = lambda: g._dev
+            scores = lambda: (g._dev.sp, g._dev.em, g._dev.al)
         else:
             import sharded
-            g = sharded.ShardedGA(seqs, mode, sharded.DeviceBackend(config.DEVICE))
-            counters = lambda: (g.backend.pop.evals, g.backend.pop.forwards)
-            dedup = lambda: (g.backend.pop.episodes, g.backend.pop.unique_episodes, g.backend.pop.states)
+            g = sharded.ShardedGA(seqs, mode, sharded.DeviceBackend(config.DEVICE, peer=None if exchange is None else
+                                                                   exchange == "peer"))
+            pop = lambda: g.backend.pop
+            scores = lambda: g.g_scores
         t0 = time.perf_counter()
-        g.generate_population()
+        if duplicate_free:
+            assert world == 1
+            g._adopt(*duplicate_free_population(rows, cols, P_total, 77))
+        else:
+            g.generate_population()
         sync()
         t_pop = time.perf_counter() - t0
         g.calculate_fitness_score()
+        if log_hashes is not None:
+            log_hashes.append(score_hash(*scores()))
         # a fresh box idles at 120 MHz and needs about a second of dense work to settle its clocks and power
         # state: burn ~1.5 s of Q-net forwards before any timed generation (on top of the warm-up generations)
         t_burn = time.perf_counter()
-        while time.perf_counter() - t_burn < BURN_SCALE * 1.5:
+        while with_extras and time.perf_counter() - t_burn < BURN_SCALE * 1.5:
             qnet_forward_ms(model, rw, cw, 8192)
         sync()
         phases = {"mutation": 0.0, "fitness": 0.0, "selection": 0.0, "crossover": 0.0}
-        evals = forwards = episodes = 0
         total = 0.0
         per_gen = []
+        acc = {"evals": 0, "forwards": 0, "episodes": 0, "unique_episodes": 0, "states": 0}
+        mut_local = 0.0
         for it in range(n_warm + n_gen):
-            e0, f0 = counters()
-            d0 = dedup()
+            d = pop()
+            c0 = (d.evals, d.forwards, d.episodes, d.unique_episodes, d.states)
             stamps = []
             for name, fn in (("mutation", lambda: g.mutation(model)), ("fitness", g.calculate_fitness_score),
                              ("selection", g.selection), ("crossover", g.horizontal_crossover)):
                 sync()
                 t0 = time.perf_counter()
                 fn()
-                sync()
-                stamps.append((name, time.perf_counter() - t0))
-            d1 = dedup()
-            per_gen.append({"ms": round(1e3 * sum(dt for _, dt in stamps), 2), "forwards": counters()[1] - f0,
-                            "episodes": d1[0] - d0[0], "unique_episodes": d1[1] - d0[1], "states": d1[2] - d0[2],
-                            "timed": it >= n_warm})
+                torch.cuda.synchronize()
+                t_local = time.perf_counter() - t0
+                if world > 1:
+                    dist.barrier()
+                stamps.append((name, time.perf_counter() - t0, t_local))
+                if log_hashes is not None and name != "mutation":
+                    log_hashes.append(score_hash(*scores()))
+            d = pop()
+            c1 = (d.evals, d.forwards, d.episodes, d.unique_episodes, d.states)
+            delta = [b - a for a, b in zip(c0, c1)]
+            per_gen.append({"ms": round(1e3 * sum(dt for _, dt, _ in stamps), 2), "forwards": delta[1], "episodes": delta[2],
+                            "unique_episodes": delta[3], "states": delta[4], "timed": it >= n_warm})
             if it >= n_warm:
-                for name, dt in stamps:
+                for name, dt, t_local in stamps:
                     phases[name] += dt
                     total += dt
-                e1, f1 = counters()
-                evals += e1 - e0
-                forwards += f1 - f0
-                episodes += round(P_total * config.MUTATION_RATE)
+                    if name == "mutation":
+                        mut_local += t_local
+                for k, v in zip(("evals", "forwards", "episodes", "unique_episodes", "states"), delta):
+                    acc[k] += v
+        per_rank = None
         if world > 1:
             t = torch.tensor([total] + [phases[k] for k in sorted(phases)], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total = float(t[0])
             phases = {k: float(v) for k, v in zip(sorted(phases), t[1:])}
-            c = torch.tensor([evals], dtype=torch.float64, device="cuda")
-            dist.all_reduce(c)
-            evals = float(c[0])
+            mine = torch.tensor([acc["evals"], acc["forwards"], acc["episodes"], acc["unique_episodes"], acc["states"],
+                                 1e3 * mut_local], dtype=torch.float64, device="cuda")
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = [{"evals": r[0].item() / n_gen, "forwards": r[1].item() / n_gen, "episodes": r[2].item() / n_gen,
+                         "unique_episodes": r[3].item() / n_gen, "states": r[4].item() / n_gen,
+                         "mutation_ms": r[5].item() / n_gen} for r in allr]
+            for i, k in enumerate(("evals", "forwards", "episodes", "unique_episodes", "states")):
+                acc[k] = sum(r[i].item() for r in allr) if k != "forwards" else max(r[i].item() for r in allr)
         hof = g.hall_of_fame
-        e2e_run = None
-        if world == 1:
+        out = {
+            "value": n_gen / total, "unit": "generations/s", "generations": n_gen, "warmup": n_warm,
+            "ms_per_generation": 1e3 * total / n_gen,
+            "phase_ms": {k: 1e3 * v / n_gen for k, v in phases.items()},
+            "fitness_evals_per_generation": acc["evals"] / n_gen,
+            "episodes_per_generation": acc["episodes"] / n_gen,
+            "unique_episodes_per_generation": acc["unique_episodes"] / n_gen,
+            "qnet_states_per_generation": acc["states"] / n_gen,
+            "lockstep_forwards_per_generation": acc["forwards"] / n_gen,
+            "population_generation_s": t_pop, "agent_window": [rw, cw], "population": P_total, "mode": mode,
+            "scaling": "weak" if weak else "strong",
+            "hall_of_fame_score": list(hof[1]) if hof else None,
+            "reference_net_flops_per_state": QNET_FLOPS.get((rw, cw)),
+            "individuals_per_s": P_total * n_gen / total,
+            "per_generation": per_gen,
+            "note": "episodes = what GA.py:331-373 would run; unique_episodes = the distinct windows that ran here "
+                    "(identical windows share one episode: the eval-mode agent is a pure function of the window)",
+        }
+        if per_rank is not None:
+            out["per_rank"] = per_rank
+        if world > 1:
+            out["collective_bytes_received_per_generation_rank0"] = g.comm_bytes / (n_warm + n_gen)
+            peer = bool(getattr(g.backend, "peer_ready", False))
+            out["exchange"] = "peer" if peer else "allgather"
+            out["parallelism"] = ("population sharded by logical index over %d ranks; per fitness pass an NCCL all-gather "
+                                  "of the scores, per generation %s" % (world, (
+                                      "the crossover kernel reads each child's parent rows from the owning rank's "
+                                      "population over NVLink (symmetric memory)") if peer else
+                                      "an NCCL all-gather of the survivors' boards"))
+        if with_extras and world == 1 and not duplicate_free:
             # the call a user makes: GA(seqs, mode).run(model) - population generated on the host from `random`,
             # uploaded, GA_ITERATIONS generations on the device, the winning alignment read back as strings
             import GA as ga_mod
@@ -357,40 +458,18 @@ def measure_generations(workload, n_gen, n_warm, world=1, rank=0):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             dev2 = g2._dev
-            e2e_run = {"value": config.GA_ITERATIONS / dt, "unit": "generations/s", "seconds": dt,
-                       "generations": config.GA_ITERATIONS, "api": "GA(sequences, mode).run(model_path)",
-                       "h2d_bytes_per_run": int(P_total * rows * dev2.stride + 4 * P_total * rows),
-                       "d2h_bytes_per_run": int(rows * dev2.stride + 32), "alignment_rows": len(best),
-                       "note": "includes host population generation (MT19937 replay), the upload, the initial fitness "
-                               "pass and the read-back of the hall of fame"}
+            out["e2e"] = {"value": config.GA_ITERATIONS / dt, "unit": "generations/s", "seconds": dt,
+                          "generations": config.GA_ITERATIONS, "api": "GA(sequences, mode).run(model_path)",
+                          "h2d_bytes_per_run": int(P_total * rows * dev2.stride + 4 * P_total * rows),
+                          "d2h_bytes_per_run": int(rows * dev2.stride + 32), "alignment_rows": len(best),
+                          "note": "includes host population generation (MT19937 replay), the upload, the initial fitness "
+                                  "pass and the read-back of the hall of fame"}
             del g2
-        tensor = None
-        if rank == 0:
-            tensor = l1_tensor_roofline(model, rw, cw, min(32768, round(P_total * config.MUTATION_RATE)))
-        out = {
-            "value": n_gen / total, "unit": "generations/s", "generations": n_gen, "warmup": n_warm,
-            "ms_per_generation": 1e3 * total / n_gen,
-            "phase_ms": {k: 1e3 * v / n_gen for k, v in phases.items()},
-            "fitness_evals_per_generation": evals / n_gen, "episodes_per_generation": episodes / n_gen,
-            "lockstep_forwards_per_generation": forwards / n_gen,
-            "population_generation_s": t_pop, "agent_window": [rw, cw], "population": P_total, "mode": mode,
-            "hall_of_fame_score": list(hof[1]) if hof else None,
-            "reference_net_flops_per_state": QNET_FLOPS.get((rw, cw)),
-            "individuals_per_s": P_total * n_gen / total,
-            "per_generation": per_gen,
-            "roofline": tensor, "e2e": e2e_run,
-            "forward_ms_full_batch": (qnet_forward_ms(model, rw, cw, min(32768, round(P_total * config.MUTATION_RATE)))
-                                      if rank == 0 else None),
-        }
-        if world > 1:
-            out["collective_bytes_received_per_generation_rank0"] = g.comm_bytes / (n_warm + n_gen)
-            peer = bool(getattr(g.backend, "peer_ready", False))
-            out["exchange"] = "peer" if peer else "allgather"
-            out["parallelism"] = ("population sharded by logical index over %d ranks; per fitness pass an NCCL all-gather "
-                                  "of the scores, per generation %s" % (world, (
-                                      "the crossover kernel reads each child's parent rows from the owning rank's "
-                                      "population over NVLink (symmetric memory)") if peer else
-                                      "an NCCL all-gather of the survivors' boards"))
+        if with_extras and rank == 0:
+            M = min(32768, round(P_total * config.MUTATION_RATE))
+            out["roofline"] = l1_tensor_roofline(model, rw, cw, M)
+            out["forward_ms_full_batch"] = qnet_forward_ms(model, rw, cw, M)
+        out["_hof_board"] = hof[0] if hof else None
         return out
     finally:
         for k, v in saved.items():
@@ -413,10 +492,10 @@ def l1_tensor_roofline(model, rw, cw, M):
             peak, src = float(json.load(fh)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)"
     achieved = fl.value / (ms.value * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "gemm_split_f16_kernel<208> (Q-net l1, tcgen05 kind::f16)", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel_ms": ms.value, "rows": int(M),
-            "flops_per_launch": fl.value, "peak_source": src,
-            "note": "executed FLOPs: three fp16 passes (hi.hi + lo.hi + hi.lo) give fp32-class accuracy; the "
-                    "single-pass-equivalent (algorithmic 2*M*K*N) rate is one third of `achieved`"}
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "frac_algorithmic": achieved / 3.0 / peak,
+            "traffic": None, "kernel_ms": ms.value, "rows": int(M), "flops_per_launch": fl.value, "peak_source": src,
+            "note": "`achieved` counts the executed FLOPs: three fp16 passes (hi.hi + lo.hi + hi.lo) give fp32-class "
+                    "accuracy; `frac_algorithmic` is the reference's 2*M*K*N over the same time"}
 
 
 def qnet_forward_ms(model, rw, cw, B):
@@ -449,69 +528,131 @@ def qnet_forward_ms(model, rw, cw, B):
     return e0.elapsed_time(e1) / 10
 
 
-def cpu_generation_port(workload, cores, n_mut_per_core=3):
-    """The reference's per-generation CPU cost from bounded samples of the oracle port: fitness passes at
-    the measured python-port rate plus round(P*MUTATION_RATE) episodes at the measured per-individual
-    mutation time (the reference's own torch CPU ops in eval mode, one thread per process, agent
-    hoisted out of the per-individual loop - the reference re-creates and re-loads it every time,
-    GA.py:354-355, which is not counted), spread over `cores`."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import multiprocessing as mp
-    rows, cols, P, mode, _ = WORKLOADS[workload]
-    rw, cw = AGENTS[workload]
-    boards, rowlen = synth_population(rows, cols, 4096, 20251019)
-    n_sample = python_sample_size(rows, cols, 4096, cores)
-    pool = python_pool(cores)
-    cpu_python_port(boards, rowlen, mode, min(64 * cores, 4096), cores, pool)
-    fit_rate, _, _ = cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
-    jobs = [(workload, 1000 + i, n_mut_per_core) for i in range(cores)]
-    t0 = time.perf_counter()
-    res = pool.map(_mutation_worker, jobs) if pool is not None else [_mutation_worker(j) for j in jobs]
-    wall = time.perf_counter() - t0
-    if pool is not None:
-        pool.close()
-    per_ind = sum(r[0] for r in res) / sum(r[1] for r in res)
-    steps = sum(r[2] for r in res) / sum(r[1] for r in res)
-    M = round(P * 0.25)
-    S = P // 2
-    gen_s = (2 * P + S) / fit_rate + M * per_ind / cores
-    return {"value": 1.0 / gen_s, "unit": "generations/s", "cores": cores, "kind": "port",
-            "fitness_evals_per_s": fit_rate, "mutation_s_per_individual_1core": per_ind,
-            "episode_steps_mean": steps,
-            "sample": "%d fitness evals and %d mutation episodes timed (%.1f s wall), extrapolated linearly to "
-                      "(2P+S)=%d evals + %d episodes on %d processes" % (n_sample, cores * n_mut_per_core, wall,
-                                                                         2 * P + S, M, cores)}
-
-
-def _mutation_worker(args):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import random
-    import ga_oracle as O
-    workload, seed, n = args
-    rows, cols, P, mode, _ = WORKLOADS[workload]
-    rw, cw = AGENTS[workload]
+# ------------------------------------------------------------------------------------------------
+# parity evidence carried by the bench line
+# ------------------------------------------------------------------------------------------------
+def parity_single_gpu(workload, generations=3):
+    """Duplicate elimination on vs off (GAD_MUTATE_DEDUP): the per-pass score hashes and the hall of fame must
+    be identical - the switch changes how many episodes run, never what they return."""
+    out = {"check": "GAD_MUTATE_DEDUP=1 vs 0, %d generations at the workload's full population" % generations}
+    runs = {}
+    old = os.environ.get("GAD_MUTATE_DEDUP")
     try:
-        import torch
-        torch.set_num_threads(1)
-    except Exception:
-        pass
-    os.environ["OMP_NUM_THREADS"] = "1"
+        for flag in ("1", "0"):
+            os.environ["GAD_MUTATE_DEDUP"] = flag
+            hashes = []
+            g = measure_generations(workload, generations, 0, with_extras=False, log_hashes=hashes)
+            runs[flag] = (hashes, g["_hof_board"], g["hall_of_fame_score"], g["unique_episodes_per_generation"],
+                          g["ms_per_generation"])
+    finally:
+        if old is None:
+            os.environ.pop("GAD_MUTATE_DEDUP", None)
+        else:
+            os.environ["GAD_MUTATE_DEDUP"] = old
+    import hashlib
+    out["scores_hash_dedup_on"] = hashlib.sha256("".join(runs["1"][0]).encode()).hexdigest()[:16]
+    out["scores_hash_dedup_off"] = hashlib.sha256("".join(runs["0"][0]).encode()).hexdigest()[:16]
+    out["passes_hashed"] = len(runs["1"][0])
+    out["hof_equal"] = runs["1"][1] == runs["0"][1] and runs["1"][2] == runs["0"][2]
+    out["equal"] = bool(runs["1"][0] == runs["0"][0] and out["hof_equal"])
+    out["unique_episodes_per_generation"] = {"dedup_on": runs["1"][3], "dedup_off": runs["0"][3]}
+    out["ms_per_generation"] = {"dedup_on": runs["1"][4], "dedup_off": runs["0"][4]}
+    return out
+
+
+def parity_sharded(workload, world, rank, generations=2):
+    """The sharded loop on N ranks (fused peer exchange and NCCL all-gather exchange) against the single-GPU
+    facade run by rank 0 on the same TOTAL population and the same `random` seed: hash of the (sp, em, al)
+    arrays in logical-index order after every fitness pass, and the hall-of-fame board."""
+    import hashlib
     import torch
-    sd = O.synth_qnet_weights(rw, cw, 7)
-    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
-    forward = lambda states, max_value: O.qnet_forward_torch(sd_t, states, max_value)
-    rng = random.Random(seed)
-    seqs = seq_strings(rows, cols, 20251019)
-    pop = O.generate_population(seqs, n + 1, 0.0, 0.05, rng)[:n]
-    O.fitness_scores(pop, mode)
-    t0 = time.perf_counter()
-    steps = 0
-    for b in pop:
-        _, tile = O.worst_tile(b, mode, rw, cw)
-        trace = []
-        O.mutate_board(b, tile, sd, trace=trace, forward=forward)
-        steps += len(trace)
-    return time.perf_counter() - t0, n, steps
+    import torch.distributed as dist
+    out = {"check": "ShardedGA on %d ranks vs the single-GPU GA facade on rank 0, %d generations, total population "
+                    "%d" % (world, generations, WORKLOADS[workload][2] * world)}
+    hofs = {}
+    for exch in ("peer", "allgather"):
+        hashes = []
+        g = measure_generations(workload, generations, 0, world, rank, with_extras=False, exchange=exch, log_hashes=hashes)
+        out["scores_hash_sharded_" + exch] = hashlib.sha256("".join(hashes).encode()).hexdigest()[:16]
+        out["exchange_used_" + exch] = g.get("exchange")
+        hofs[exch] = (g["_hof_board"], g["hall_of_fame_score"])
+        out["passes_hashed"] = len(hashes)
+    equal = 1
+    if rank == 0:
+        hashes = []
+        import config
+        dev_saved = config.DEVICE
+        g = measure_generations(workload, generations, 0, 1, 0, with_extras=False, log_hashes=hashes,
+                                population=WORKLOADS[workload][2] * world)
+        config.DEVICE = dev_saved
+        out["scores_hash_single"] = hashlib.sha256("".join(hashes).encode()).hexdigest()[:16]
+        single_hof = (g["_hof_board"], g["hall_of_fame_score"])
+        out["hof_equal"] = all(hofs[e] == single_hof for e in hofs)
+        out["equal"] = bool(out["hof_equal"] and all(out["scores_hash_sharded_" + e] == out["scores_hash_single"]
+                                                     for e in hofs))
+        equal = int(out["equal"])
+    flag = torch.tensor([equal], dtype=torch.int32, device="cuda")
+    dist.broadcast(flag, src=0)
+    out["equal"] = bool(flag.item())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference on the host cores (oracle/_ref through oracle/ref_bench.py, always in its own process)
+# ------------------------------------------------------------------------------------------------
+def reference_available():
+    return os.path.isfile("/root/reference/GA.py") or os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "GA.py"))
+
+
+def run_ref_bench(workload, cores, fitness_sample=0, fitness_reps=1, mutation_sample=0, one_core=False, timeout=900):
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--workload", workload, "--procs", str(cores),
+           "--fitness-sample", str(fitness_sample), "--fitness-reps", str(fitness_reps), "--mutation-sample",
+           str(mutation_sample)] + (["--one-core"] if one_core else [])
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("oracle/ref_bench.py failed: " + res.stderr[-800:])
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def reference_generation_estimate(ref, workload):
+    """Per-generation cost of the reference from its own measured rates: (2P + S) fitness evals at the all-core
+    rate + round(P * MUTATION_RATE) individuals at the measured per-individual mutation time spread over the
+    cores (the reference has no parallelism of its own; this is the most favourable reading)."""
+    rows, cols, P, mode, _ = WORKLOADS[workload]
+    M, S = round(P * 0.25), P // 2
+    cores = ref["procs"]
+    out = {}
+    for name in ("hoisted", "as_shipped"):
+        m = ref.get("mutation_" + name)
+        if not m or "fitness" not in ref:
+            continue
+        gen_s = (2 * P + S) / ref["fitness"]["evals_per_s"] + M * m["seconds_per_individual_1core"] / cores
+        out[name] = {"value": 1.0 / gen_s, "unit": "generations/s", "cores": cores, "kind": "reference",
+                     "fitness_evals_per_s": ref["fitness"]["evals_per_s"],
+                     "mutation_s_per_individual_1core": m["seconds_per_individual_1core"],
+                     "episode_steps_mean": m["episode_steps_mean"],
+                     "sample": "%d fitness evals per step and %d mutated individuals timed on the unmodified reference, "
+                               "extrapolated linearly to (2P+S)=%d evals + %d episodes on %d processes"
+                               % (ref["fitness"]["boards_per_step"], m["individuals"], 2 * P + S, M, cores)}
+    return out
+
+
+def cpu_reference_baseline(workload, with_generation=True):
+    """cpu_baseline of the ours arm: the unmodified reference on all host cores, bounded sample."""
+    cores = os.cpu_count() or 1
+    rows, cols, P, mode, _ = WORKLOADS[workload]
+    n = min(P, max(1024, python_sample_size(rows, cols, P, cores) * 2))
+    ref = run_ref_bench(workload, cores, fitness_sample=n, fitness_reps=2, mutation_sample=2 if with_generation else 0,
+                        one_core=True)
+    base = {"value": ref["fitness"]["evals_per_s"], "unit": "evals/s", "cores": cores, "kind": "reference",
+            "source": "oracle/_ref (byte-identical copy of the reference's python files) through oracle/ref_bench.py",
+            "function": ref["fitness"]["function"],
+            "one_core_evals_per_s": ref.get("fitness_one_core", {}).get("evals_per_s"),
+            "sample": "%d boards per step x %d steps spread over the population, %d processes"
+                      % (ref["fitness"]["boards_per_step"], ref["fitness"]["steps"], cores)}
+    return base, reference_generation_estimate(ref, workload)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -525,49 +666,79 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--generations", type=int, default=4, help="timed whole generations (0 = skip)")
     ap.add_argument("--generation-warmup", type=int, default=3)
+    ap.add_argument("--no-extras", action="store_true", help="skip parity runs, the duplicate-free workload, c4 / c5")
     return ap.parse_args()
 
 
 def run_reference(args, rank, world):
-    """The CPU port of the reference's path, all host cores, bounded sample per step."""
+    """--impl reference: the UNMODIFIED reference's GA.calculate_fitness_score on all host cores, a bounded sample of
+    the workload per step (oracle/_ref; the python port only when no copy of the reference exists)."""
     if rank != 0:
         return
     rows, cols, P, mode, desc = WORKLOADS[args.workload]
-    boards, rowlen = synth_population(rows, cols, P, 20251019)
     cores = os.cpu_count() or 1
-    n_sample = python_sample_size(rows, cols, P, cores)
-    pool = python_pool(cores)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
-    t_total, n_total = 0.0, 0
-    for _ in range(args.steps):
-        _, n, dt = cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
-        t_total += dt
-        n_total += n
-    if pool is not None:
-        pool.close()
-    value = n_total / t_total
-    c_rate, c_n, c_dt = cpu_c_port(boards, rowlen, cores)
+    n_sample = min(P, max(1024, python_sample_size(rows, cols, P, cores) * 2))
     line = {
-        "impl": "reference", "metric": "fitness evals/sec (SP+CS)", "value": value, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "rows": rows, "cols": cols, "population": P,
-                   "mode": mode, "sample_per_step": n_sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "language": "pure python lists, the reference's own loop structure",
-                         "sample": "%d boards per step spread over the population, %d processes" % (n_sample, cores)},
-        "cpu_baseline_c_openmp": {"value": c_rate, "unit": "evals/s", "cores": cores, "kind": "port",
-                                  "sample": "%d evals in %.2f s, oracle/ga_oracle.c" % (c_n, c_dt)},
-        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": "fitness evals/sec (SP+CS)", "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args.workload), "gpu_launches": 0,
     }
-    if args.generations > 0:
-        line["generation"] = {"cpu_baseline": cpu_generation_port(args.workload, cores)}
-        line["generation"]["value"] = line["generation"]["cpu_baseline"]["value"]
-        line["generation"]["unit"] = "generations/s"
+    if reference_available():
+        ref = run_ref_bench(args.workload, cores, fitness_sample=n_sample, fitness_reps=args.steps,
+                            mutation_sample=2 if args.generations > 0 else 0, one_core=True)
+        f = ref["fitness"]
+        value = f["evals_per_s"]
+        line.update({"value": value, "ms_per_step": 1e3 * sum(f["seconds_per_step"]) / len(f["seconds_per_step"]),
+                     "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference",
+                                      "source": "oracle/_ref (byte-identical copy of the reference's python files)",
+                                      "function": f["function"],
+                                      "one_core_evals_per_s": ref.get("fitness_one_core", {}).get("evals_per_s"),
+                                      "sample": "%d boards per step spread over the population, %d processes (the reference "
+                                                "is single-threaded: one process per core, each scoring its slice)"
+                                                % (f["boards_per_step"], cores)}})
+        if args.generations > 0:
+            est = reference_generation_estimate(ref, args.workload)
+            line["generation"] = {"cpu_baseline": est.get("hoisted"), "cpu_baseline_as_shipped": est.get("as_shipped"),
+                                  "value": est["hoisted"]["value"], "unit": "generations/s"}
+    else:
+        boards, rowlen = synth_population(rows, cols, P, 20251019)
+        pool = python_pool(cores)
+        cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
+        t_total, n_total = 0.0, 0
+        for _ in range(args.steps):
+            _, n, dt = cpu_python_port(boards, rowlen, mode, n_sample, cores, pool)
+            t_total += dt
+            n_total += n
+        if pool is not None:
+            pool.close()
+        value = n_total / t_total
+        line.update({"value": value, "ms_per_step": 1e3 * t_total / args.steps,
+                     "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                                      "sample": "%d boards per step, %d processes (no copy of the reference available: "
+                                                "oracle port)" % (n_sample, cores)}})
+    line["e2e"] = {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    boards, rowlen = synth_population(rows, cols, min(P, 65536), 20251019)
+    c_rate, c_n, c_dt = cpu_c_port(boards, rowlen, cores)
+    line["cpu_baseline_c_openmp"] = {"value": c_rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                     "sample": "%d evals in %.2f s, oracle/ga_oracle.c (context: a compiled scalar port)"
+                                               % (c_n, c_dt)}
     print(json.dumps(line), flush=True)
+
+
+def timed_graph(fn_list, stream_side):
+    """Capture the launches of fn_list into one CUDA graph and time one replay with CUDA events."""
+    import torch
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream_side):
+        for fn in fn_list:
+            fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), graph
 
 
 def main():
@@ -589,6 +760,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    import config
+    config.DEVICE = "cuda:%d" % local_rank
 
     rows, cols, P, mode, desc = WORKLOADS[args.workload]
     boards_h, rowlen_h = synth_population(rows, cols, P, 20251019 + 1000 * rank)
@@ -604,11 +777,18 @@ def main():
     replicas = []
     for _ in range(n_rep):
         replicas.append(DevicePopulation(pristine_b.clone(), pristine_r.clone()))
+        replicas[-1].width_hint = int(rowlen_h.max())
     algo_bytes = int(rowlen_h.astype(np.int64).max(axis=1).sum()) * rows + 12 * P      # R*W + 12 per eval
 
     def barrier():
         if world > 1:
             dist.barrier()
+        torch.cuda.synchronize()
+
+    def restore():
+        for rep in replicas:
+            rep.boards.copy_(pristine_b)
+            rep.rowlen.copy_(pristine_r)
         torch.cuda.synchronize()
 
     # a fresh box idles at 120 MHz: spin the GPU for about a second so that no timed region sees the clock ramp
@@ -617,69 +797,115 @@ def main():
         for rep in replicas[:2]:
             rep.fitness(MATCH, MISMATCH, GAPW)
         torch.cuda.synchronize()
-    for rep in replicas[:2]:
-        rep.boards.copy_(pristine_b)
-        rep.rowlen.copy_(pristine_r)
+    restore()
 
-    # ---------------- device-resident throughput (`value`) ----------------
-    # The K timed passes (one per fresh replica) are captured once into a CUDA graph and replayed, so
-    # the number is device time, not python launch overhead; eager launches are the fallback.
+    # ---------------- the bare kernel on device-resident boards: K launches, one per fresh replica ----------------
+    # captured once into a CUDA graph and replayed, so the number is device time, not python launch overhead
     side = torch.cuda.Stream()
-    graph = None
-    try:
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for i in range(W):
-                replicas[i % n_rep].fitness(MATCH, MISMATCH, GAPW)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        for rep in replicas:                              # warm-up cleaned them: restore
-            rep.boards.copy_(pristine_b)
-            rep.rowlen.copy_(pristine_r)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(K):
-                replicas[(W + i) % n_rep].fitness(MATCH, MISMATCH, GAPW)
-    except Exception as exc:                               # pragma: no cover - depends on the driver
-        sys.stderr.write("CUDA graph capture unavailable (%s); timing eager launches\n" % exc)
-        graph = None
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(W):
+            replicas[i % n_rep].fitness(MATCH, MISMATCH, GAPW)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    restore()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if graph is not None and fresh:
-        e0.record()
-        graph.replay()
-        e1.record()
-    else:
-        graph = None
+    use_graph = fresh
+    if use_graph:
+        try:
+            total_ms, _graph = timed_graph([(lambda r=replicas[(W + i) % n_rep]: r.fitness(MATCH, MISMATCH, GAPW))
+                                            for i in range(K)], side)
+        except Exception as exc:                               # pragma: no cover - depends on the driver
+            sys.stderr.write("CUDA graph capture unavailable (%s); timing eager launches\n" % exc)
+            use_graph = False
+            restore()
+    if not use_graph:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i in range(W):
             replicas[i % n_rep].fitness(MATCH, MISMATCH, GAPW)
         e0.record()
         for i in range(K):
             replicas[(W + i) % n_rep].fitness(MATCH, MISMATCH, GAPW)
         e1.record()
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
     barrier()
-    total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * P * K / (total_ms_max * 1e-3)
+    kernel_total_ms_max = float(t.item())
+    kernel_value = world * P * K / (kernel_total_ms_max * 1e-3)
+    sp_ref = replicas[(W + K - 1) % n_rep].sp.cpu()
 
-    # ---------------- kernel time for the roofline: the same K back-to-back launches -------------
-    # (the graph holds only fitness_kernel launches and their 4-byte memsets, so total/K is the
-    # kernel's average duration on the launching stream)
+    # what a launch that only READS the same live bytes costs (same replicas, same graph scheme)
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    width = int(rowlen_h.max())
+    def probe(rep):
+        nat.call("gad_probe_read", rep.cur.boards.data_ptr(), P, rows, stride, width, sink.data_ptr(), nat.current_stream_ptr())
+    try:
+        probe_ms, _g2 = timed_graph([(lambda r=replicas[(W + i) % n_rep]: probe(r)) for i in range(K)], side)
+        stream_read_us = 1e3 * probe_ms / K
+    except Exception:                                          # pragma: no cover
+        stream_read_us = None
+
     kern_avg_ms = total_ms / K
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (kern_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fitness_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = "fitness_tma_kernel" if os.environ.get("GAD_FITNESS_TMA", "1") != "0" and width <= 256 else "fitness_kernel"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": profiled_traffic(args.workload),
-                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_avg_ms,
-                "peak_source": peak_src,
-                "note": ("%d launches, one per fresh replica, %s, CUDA events on the launching stream"
-                         % (K, "replayed from one CUDA graph" if graph is not None else "eager"))}
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kern_avg_ms, "peak_source": peak_src,
+                "stream_read_us": stream_read_us,
+                "frac_of_stream_read": (stream_read_us / (1e3 * kern_avg_ms)) if stream_read_us else None,
+                "note": ("%d launches, one per fresh replica, %s, CUDA events on the launching stream. stream_read_us = the "
+                         "same scheme with a kernel that only reads the live cells (gad_probe_read): what one pass over "
+                         "%.1f MB costs at this launch size; the timed pass meets clean boards, so its compaction "
+                         "branch is not taken" % (K, "replayed from one CUDA graph" if use_graph else "eager",
+                                                  algo_bytes / 1e6))}
+
+    # ---------------- the complete pass: GA.calculate_fitness_score / ShardedGA.calculate_fitness_score ----------
+    restore()
+    seqs = seq_strings(rows, cols, 20251019)
+    config.POPULATION_SIZE = P * world
+    if world == 1:
+        import GA as ga_mod
+        g = ga_mod.GA(seqs, mode)
+        def full_pass(rep):
+            g._dev = rep
+            g.calculate_fitness_score()
+    else:
+        import sharded
+        g = sharded.ShardedGA(seqs, mode, sharded.DeviceBackend(config.DEVICE, peer=False))
+        g.gidx = torch.arange(rank, P * world, world, dtype=torch.int64, device=dev)      # individual i lives on rank i % world
+        g.n_global = P * world
+        g.backend.R = rows
+        def full_pass(rep):
+            g.backend.pop = rep
+            g.calculate_fitness_score()
+    for rep in replicas:
+        rep._workspace()                                       # ranking workspace of every replica allocated up front
+    for i in range(W):
+        full_pass(replicas[i % n_rep])
+    restore()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        full_pass(replicas[(W + i) % n_rep])
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pass_ms_max = float(t.item())
+    pass_value = world * P * K / (pass_ms_max * 1e-3)
+    fitness_pass = {"value": pass_value, "unit": "evals/s", "ms_per_step": pass_ms_max / K,
+                    "api": ("GA.calculate_fitness_score: kernel + hall-of-fame decision" if world == 1 else
+                            "ShardedGA.calculate_fitness_score: kernel + NCCL all-gather of (sp, em, al, index) + "
+                            "hall-of-fame decision on every rank (+ broadcast of the winner's board when it changes)"),
+                    "population": P * world}
 
     # ---------------- end to end through the C-ABI host entry point (`e2e`) ---------------------
     pin_b = torch.from_numpy(boards_h).pin_memory()
@@ -704,57 +930,94 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * P * K / float(t.item())
-    sp_ref = replicas[(W + K - 1) % n_rep].sp.cpu()
     assert torch.equal(out[0], sp_ref), "e2e scores differ from the device-resident pass"
     e2e = {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": boards_h.nbytes + rowlen_h.nbytes,
            "d2h_bytes_per_step": 12 * P, "ms_per_step": 1e3 * float(t.item()) / K,
            "api": "gad_fitness_host (C-ABI, pinned host buffers)"}
 
+    cfg = workload_config(args.workload)
+    cfg["stride"] = stride
+    cfg["parallelism"] = ("one GPU" if world == 1 else
+                          "population sharded by logical index over %d ranks (weak scaling: %d individuals per rank); "
+                          "`value` is the sharded pass with its score all-gather" % (world, P))
+    if world == 1:
+        value, ms_step, launches = kernel_value, kernel_total_ms_max / K, K
+    else:
+        value, ms_step, launches = pass_value, pass_ms_max / K, K
     line = {
         "metric": "fitness evals/sec (SP+CS)", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, desc), "rows": rows, "cols": cols,
-                   "population_per_gpu": P, "mode": mode, "stride": stride,
-                   "scores": [MATCH, MISMATCH, GAPW],
-                   "l2": ("every step scores a fresh replica of the population (%d replicas x %.1f MB = %.0f MB > "
-                          "126 MB L2)%s" % (n_rep, board_bytes / 1e6, n_rep * board_bytes / 1e6,
-                                            "" if fresh else "; replicas reused round-robin")),
-                   "parallelism": "population sharded by index, %d rank(s), no data-path collective" % world},
-        "e2e": e2e, "roofline": roofline, "gpu_launches": K,
+        "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+        "e2e": e2e, "roofline": roofline, "gpu_launches": launches, "fitness_pass": fitness_pass,
+        "fitness_kernel_only": {"value": kernel_value, "unit": "evals/s", "ms_per_step": kernel_total_ms_max / K},
     }
 
-    # ---------------- whole generations (N=1; the sharded loop is measured by --gpus N via the GA facade) ----
+    rc = 0
+    # ---------------- whole generations ----------------
     if args.generations > 0:
-        del replicas, pristine_b, pristine_r
+        del replicas, pristine_b, pristine_r, g
         torch.cuda.empty_cache()
-        import config
-        config.DEVICE = "cuda:%d" % local_rank
-        line["generation"] = measure_generations(args.workload, args.generations, args.generation_warmup, world, rank)
+        gen = measure_generations(args.workload, args.generations, args.generation_warmup, world, rank)
+        gen.pop("_hof_board", None)
+        line["generation"] = gen
+        if not args.no_extras:
+            if world == 1:
+                dfree = measure_generations(args.workload, 3, 1, duplicate_free=True, with_extras=False)
+                dfree.pop("_hof_board", None)
+                dfree.pop("per_rank", None)
+                gen["duplicate_free_workload"] = {k: dfree[k] for k in (
+                    "value", "ms_per_generation", "phase_ms", "episodes_per_generation", "unique_episodes_per_generation",
+                    "qnet_states_per_generation", "lockstep_forwards_per_generation", "per_generation")}
+                gen["duplicate_free_workload"]["note"] = ("CLONE_RATE = 0 and a different random base per individual: every "
+                                                          "episode is distinct, the Q-net kernels run full batches")
+                line["parity"] = parity_single_gpu(args.workload)
+            else:
+                line["parity"] = parity_sharded(args.workload, world, rank)
+                torch.cuda.empty_cache()
+                c4 = measure_generations("c4", 3, 4, world, rank, weak=False, with_extras=False)
+                c4.pop("_hof_board", None)
+                line["strong_scaling_c4"] = c4
+                if world == 8 and os.environ.get("GAD_BENCH_C5", "1") != "0":
+                    torch.cuda.empty_cache()
+                    WORKLOADS["c5"] = (64, 1000, 1048576, "mo", "synthetic 64x1000 boards, 1M individuals over 8 GPUs")
+                    AGENTS["c5"] = (3, 30)
+                    c5 = measure_generations("c5", 2, 1, world, rank, weak=False, with_extras=False)
+                    c5.pop("_hof_board", None)
+                    line["c5"] = c5
+            if not line["parity"]["equal"]:
+                rc = 3
 
     line["clocks"] = sampler.stop()          # sampled from the first timed pass to the last timed generation
 
     # ---------------- CPU baselines on rank 0 at N=1 ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_sample = python_sample_size(rows, cols, P, cores) * 4
-        pool = python_pool(cores)
-        cpu_python_port(boards_h, rowlen_h, mode, 64 * cores, cores, pool)            # warm the workers
-        py_rate, py_n, py_dt = cpu_python_port(boards_h, rowlen_h, mode, n_sample, cores, pool)
-        if pool is not None:
-            pool.close()
+        if reference_available():
+            base, est = cpu_reference_baseline(args.workload, args.generations > 0)
+            line["cpu_baseline"] = base
+            if args.generations > 0 and est:
+                line["generation"]["cpu_baseline"] = est.get("hoisted")
+                line["generation"]["cpu_baseline_as_shipped"] = est.get("as_shipped")
+        else:
+            n_sample = python_sample_size(rows, cols, P, cores) * 4
+            pool = python_pool(cores)
+            cpu_python_port(boards_h, rowlen_h, mode, 64 * cores, cores, pool)
+            py_rate, py_n, py_dt = cpu_python_port(boards_h, rowlen_h, mode, n_sample, cores, pool)
+            if pool is not None:
+                pool.close()
+            line["cpu_baseline"] = {"value": py_rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                    "sample": "%d boards in %.2f s on %d processes (oracle port: no copy of the "
+                                              "reference available)" % (py_n, py_dt, cores)}
         c_rate, c_n, c_dt = cpu_c_port(boards_h, rowlen_h, cores)
-        line["cpu_baseline"] = {"value": py_rate, "unit": "evals/s", "cores": cores, "kind": "port",
-                                "language": "pure python lists, the reference's own loop structure",
-                                "sample": "%d boards in %.2f s on %d processes" % (py_n, py_dt, cores)}
         line["cpu_baseline_c_openmp"] = {"value": c_rate, "unit": "evals/s", "cores": cores, "kind": "port",
                                          "sample": "%d evals in %.2f s, oracle/ga_oracle.c" % (c_n, c_dt)}
-        if args.generations > 0:
-            line["generation"]["cpu_baseline"] = cpu_generation_port(args.workload, cores)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rc:
+        sys.stderr.write("PARITY MISMATCH: %s\n" % json.dumps(line.get("parity")))
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

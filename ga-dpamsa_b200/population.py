@@ -419,6 +419,15 @@ class Ranker:
                  nat.ptr(self.dst), nat.ptr(self.count), nat.ptr(self.ws), self.ws.numel(), nat.current_stream_ptr())
         return self.keep[:n], self.dst[:n], int(self.count.item())
 
+    def argbest_device(self, scores, n, mode, hof_dev):
+        """Like argbest with the hall-of-fame record given as a device int32[8] (or None) and the winner left on the
+        device (int32[1] tensor): nothing is read back."""
+        sp, em, al = (t.contiguous() for t in scores)
+        nat.call("gad_hof_argbest", nat.ptr(sp), nat.ptr(em), nat.ptr(al), n, MODE_ID[mode],
+                 None if hof_dev is None else nat.ptr(hof_dev), nat.ptr(self.winner), nat.ptr(self.ws), self.ws.numel(),
+                 nat.current_stream_ptr())
+        return self.winner.clone()
+
     def argbest(self, scores, n, mode, hof_score):
         sp, em, al = scores
         hof_ptr = None

@@ -55,6 +55,11 @@ class ShardedGA:
         self.hof_board = None        # replicated on every rank: (boards uint8 [R, w] tensor)
         self.hof_score = None        # (logical index, sp, em, al)
         self.comm_bytes = 0          # bytes this rank received through collectives
+        self._counts_cache = None    # individuals per rank (device backends: kept on the host between phases)
+        self._owner_pattern = None
+        self._hof_dev = None         # device backends: hall-of-fame record / board stay on the device
+        self._hof_board_dev = None
+        self._hof_valid = False
 
     # ------------------------------------------------------------------ collectives
     def _all_gather_padded(self, t: torch.Tensor, counts, compact=True):
@@ -101,6 +106,8 @@ class ShardedGA:
 
     # ------------------------------------------------------------------ a4 + a8
     def calculate_fitness_score(self):
+        if getattr(self.backend, "device_pass", False) and self.world > 1:
+            return self._fitness_pass_device()
         sp, em, al = self.backend.fitness()                       # local, no collective
         counts = self._counts(int(self.gidx.numel()))
         packed = torch.stack((sp.to(torch.int64), em.to(torch.int64), al.to(torch.int64), self.gidx), dim=1)
@@ -114,6 +121,78 @@ class ShardedGA:
                                                torch.tensor(counts, device=dev))
         self.owner = torch.zeros(n, dtype=torch.int64, device=dev).index_copy_(0, g, owner_of_pos)
         self.update_hall_of_fame()
+
+    # -- the same pass without a single host synchronisation (device backends) ---------------------------------
+    def _rank_counts(self):
+        """Individuals per rank, cached: they only change in selection and crossover, which know them."""
+        if self._counts_cache is None or sum(self._counts_cache) != self.n_global:
+            self._counts_cache = self._counts(int(self.gidx.numel()))
+        return self._counts_cache
+
+    def _fitness_pass_device(self):
+        """calculate_fitness_score + update_hall_of_fame as a stream of kernels and two collectives, nothing read
+        back by the host: (1) the local fitness kernel; (2) ONE all-gather of (sp, em, al, logical index) as int32,
+        ranks padded to the largest share with entries that point at a spare slot; (3) a scatter into the
+        logical-index order; (4) the hall-of-fame decision on every rank (gad_hof_argbest, winner index stays on
+        the device); (5) the winner's board by an all-reduce in which only the owner contributes non-zero bytes
+        (a board is ~1 kB: cheaper than learning the owner on the host for a broadcast); (6) a device-side select
+        between the new and the old record. Decisions are the same kernels as the single-GPU path."""
+        be = self.backend
+        dev = be.device
+        sp, em, al = be.fitness()
+        counts = self._rank_counts()
+        n, n_loc, mx = self.n_global, int(self.gidx.numel()), max(counts)
+        packed = torch.empty((mx, 4), dtype=torch.int32, device=dev)
+        packed[:n_loc, 0] = sp
+        packed[:n_loc, 1] = em
+        packed[:n_loc, 2] = al
+        packed[:n_loc, 3] = self.gidx
+        if n_loc < mx:
+            packed[n_loc:] = torch.tensor([0, 0, 1, n], dtype=torch.int32, device=dev)      # padding -> spare slot n
+        allp = torch.empty((self.world * mx, 4), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, packed, group=self.group)
+        self.comm_bytes += packed.numel() * 4 * (self.world - 1)
+        g = allp[:, 3].to(torch.int64)
+        buf = torch.zeros((4, n + 1), dtype=torch.int32, device=dev)
+        buf[0].index_copy_(0, g, allp[:, 0])
+        buf[1].index_copy_(0, g, allp[:, 1])
+        buf[2].index_copy_(0, g, allp[:, 2])
+        if self._owner_pattern is None or self._owner_pattern.numel() != self.world * mx:
+            self._owner_pattern = torch.arange(self.world, device=dev, dtype=torch.int32).repeat_interleave(mx)
+        buf[3].index_copy_(0, g, self._owner_pattern)
+        self.g_scores = (buf[0, :n], buf[1, :n], buf[2, :n])
+        self.owner = buf[3, :n].to(torch.int64)
+        # hall of fame, device side
+        if self._hof_dev is None:
+            self._hof_dev = torch.zeros(8, dtype=torch.int32, device=dev)                  # {valid, index, sp, em, al}
+            self._hof_board_dev = torch.full((be.R, be.pop.stride), 5, dtype=torch.uint8, device=dev)
+        if self._hof_board_dev.shape[1] != be.pop.stride:                                 # the population was re-laid out
+            wide = torch.full((be.R, be.pop.stride), 5, dtype=torch.uint8, device=dev)
+            wide[:, :self._hof_board_dev.shape[1]] = self._hof_board_dev
+            self._hof_board_dev = wide
+        w = be.argbest_device(self.g_scores, n, self.mode, self._hof_dev if self._hof_valid else None)   # int32[1]; == n: the record stays
+        self._hof_valid = True
+        changed = w < n                                                                    # bool[1]
+        wl = torch.clamp(w, max=n - 1).to(torch.int64)
+        slot = torch.full((n + 1,), -1, dtype=torch.int64, device=dev)
+        slot.index_copy_(0, self.gidx, torch.arange(n_loc, device=dev))
+        my_slot = slot.index_select(0, wl)                                                 # -1: another rank owns the winner
+        mine = (my_slot >= 0) & changed
+        cand = be.pop.cur.boards.index_select(0, torch.clamp(my_slot, min=0))[0] * mine.to(torch.uint8)
+        dist.all_reduce(cand, group=self.group)                                            # only the owner's bytes are non-zero
+        self.comm_bytes += cand.numel()
+        self._hof_board_dev = torch.where(changed, cand, self._hof_board_dev)
+        new = torch.stack((torch.ones_like(w), w, buf[0].index_select(0, wl), buf[1].index_select(0, wl),
+                           buf[2].index_select(0, wl))).flatten()
+        old = self._hof_dev[:5].clone()
+        old[1] = n                                                                         # GA.py:127-132: the record re-enters as index n
+        self._hof_dev[:5] = torch.where(changed, new, old)
+        self.hof_board, self.hof_score = None, None                                        # materialised on demand
+
+    def _hof_from_device(self):
+        rec = self._hof_dev.cpu().tolist()
+        self.hof_score = (rec[1], rec[2], rec[3], rec[4])
+        self.hof_board = self._hof_board_dev[:, :rec[4]].clone()
 
     def update_hall_of_fame(self):
         """GA.py:110-136 on the gathered scores; the winner's board is broadcast by its owner."""
@@ -137,6 +216,8 @@ class ShardedGA:
 
     @property
     def hall_of_fame(self):
+        if self.hof_board is None and self._hof_dev is not None:
+            self._hof_from_device()
         if self.hof_board is None:
             return []
         idx, sp, em, al = self.hof_score
@@ -347,6 +428,11 @@ class DeviceBackend:
 
     def hof_argbest(self, scores, n, mode, hof_score):
         return self._ranker(n).argbest(scores, n, mode, hof_score)
+
+    device_pass = True            # ShardedGA._fitness_pass_device: the whole pass without a host synchronisation
+
+    def argbest_device(self, scores, n, mode, hof_dev):
+        return self._ranker(n).argbest_device(scores, n, mode, hof_dev)
 
     def select_flags(self, scores, n, mode, top_n):
         return self._ranker(n).select_flags(scores, n, mode, top_n)

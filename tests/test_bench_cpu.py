@@ -20,7 +20,9 @@ def test_reference_arm_json_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.isfile("/root/reference/GA.py") or os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "GA.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline_c_openmp"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
 
@@ -46,3 +48,11 @@ def test_synthetic_population_follows_the_reference_recipe():
             assert int((row == 5).sum()) - int((boards[0, r, :60] == 5).sum()) == 3      # three gaps more than the clone
             assert row[row != 5].tolist() == boards[0, r, :60][boards[0, r, :60] != 5].tolist()
     assert (boards[:, :, 63:] == 5).all() and set(np.unique(boards)) <= {1, 2, 3, 4, 5}
+
+
+def test_both_arms_report_the_same_config():
+    """`config` is built by one function for both arms (the driver compares them)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.workload_config("c3")
+    assert a == bench.workload_config("c3") and a["population_per_gpu"] == 65536 and a["agent_window"] == [6, 30]
