@@ -1109,22 +1109,22 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
 }
 
 __global__ void __launch_bounds__(256)
-dedup_kernel(const gad_qnet net, long long M, int32_t *__restrict__ table, unsigned int mask,
-             int32_t *__restrict__ rep, int32_t *__restrict__ uniq, int32_t *__restrict__ n_uniq, int enable)
+dedup_kernel(const uint8_t *__restrict__ windows, const int32_t *__restrict__ steps, int rc, long long M,
+             int32_t *__restrict__ table, unsigned int mask, int32_t *__restrict__ rep, int32_t *__restrict__ uniq,
+             int32_t *__restrict__ n_uniq, int enable)
 {
     const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (m >= M) return;
     const int lane = threadIdx.x & 31;
-    const int rc = net.rows * net.cols;
-    if (net.steps[m] < 0) {                               // no tile fits: not mutated, nothing to share
+    if (steps && steps[m] < 0) {                          // no tile fits: not mutated, nothing to share
         if (lane == 0) rep[m] = (int32_t)m;
         return;
     }
-    const uint8_t *mine = net.sub + (size_t)m * rc;
+    const uint8_t *mine = windows + (size_t)m * rc;
     if (!enable) {
         if (lane == 0) {
             rep[m] = (int32_t)m;
-            uniq[atomicAdd(n_uniq, 1)] = (int32_t)m;
+            if (uniq) uniq[atomicAdd(n_uniq, 1)] = (int32_t)m;
         }
         return;
     }
@@ -1139,11 +1139,11 @@ dedup_kernel(const gad_qnet net, long long M, int32_t *__restrict__ table, unsig
         if (prev == -1) {                                 // first of its kind: this episode runs
             if (lane == 0) {
                 rep[m] = (int32_t)m;
-                uniq[atomicAdd(n_uniq, 1)] = (int32_t)m;
+                if (uniq) uniq[atomicAdd(n_uniq, 1)] = (int32_t)m;
             }
             return;
         }
-        const uint8_t *other = net.sub + (size_t)prev * rc;
+        const uint8_t *other = windows + (size_t)prev * rc;
         bool same = true;
         for (int i = lane; i < rc; i += 32) same &= mine[i] == other[i];
         if (__all_sync(0xFFFFFFFFu, same)) {
@@ -1160,23 +1160,56 @@ __global__ void set_i32_kernel(int32_t *dst, int32_t v0, int32_t v1)
     dst[1] = v1;
 }
 
+// rep[m] -> the SMALLEST index among the windows identical to m (dedup_kernel's representative depends on timing;
+// ranks of a sharded run must agree on it): min over each group, then relabel.
+__global__ void rep_min_kernel(const int32_t *__restrict__ rep, int32_t *__restrict__ lowest, long long M)
+{
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) atomicMin(&lowest[rep[m]], (int32_t)m);
+}
+__global__ void rep_relabel_kernel(int32_t *__restrict__ rep, const int32_t *__restrict__ lowest, long long M)
+{
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < M) rep[m] = lowest[rep[m]];
+}
+
+// episode e starts from window list[e] (or e) of an explicit window array
+__global__ void episodes_from_windows_kernel(const gad_qnet net, const uint8_t *__restrict__ windows,
+                                             const int32_t *__restrict__ list, long long U)
+{
+    const long long e = blockIdx.x;
+    const int rc = net.rows * net.cols;
+    const long long src = list ? list[e] : e;
+    for (int i = threadIdx.x; i < rc; i += blockDim.x) net.sub[(size_t)e * rc + i] = windows[(size_t)src * rc + i];
+    if (threadIdx.x < net.rows) net.heads[(size_t)e * net.rows + threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        net.steps[e] = 0;
+        net.uniq[e] = (int32_t)e;
+    }
+}
+
 // Environment.padding (env.py:344-351) + the splice of GA.py:369-373, one warp per episode.
 // The tile's rows become old[:fc] + aligned + leftovers + gaps + old[fc+cols:], i.e. they grow by
 // d = steps + longest leftover - cols >= 0; the other rows keep their cells.
+// res_of[m] = the episode whose result individual m takes (aligned / heads / steps are indexed by it). m's own
+// window (identical content to that episode's) is windows[m] when own_windows is set, else windows[res_of[m]].
 __global__ void __launch_bounds__(128)
-splice_kernel(const gad_qnet net, uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, int R, int stride,
-              const int32_t *__restrict__ idx, const int32_t *__restrict__ tile, long long M,
+splice_kernel(int rows, int cols, const int32_t *__restrict__ res_of, int own_windows,
+              const uint8_t *__restrict__ aligned, const uint8_t *__restrict__ heads, const int32_t *__restrict__ steps,
+              const uint8_t *__restrict__ windows, uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen, int R,
+              int stride, const int32_t *__restrict__ idx, const int32_t *__restrict__ tile, long long M,
               int32_t *__restrict__ status)
 {
     const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (m >= M) return;
     const int lane = threadIdx.x & 31;
-    const int rows = net.rows, cols = net.cols, cap = rows * cols;
+    const int cap = rows * cols;
     const long long p = idx ? idx[m] : m;
     const int fr = tile[2 * m], fc = tile[2 * m + 1];
-    const long long e = net.rep[m];                 // the episode that ran for this window (m itself if unique)
-    const uint8_t *hd = net.heads + (size_t)e * rows;
-    const int T = net.steps[e];
+    const long long e = res_of[m];                  // the episode that ran for this window (m itself if unique)
+    const long long wm = own_windows ? m : e;
+    const uint8_t *hd = heads + (size_t)e * rows;
+    const int T = steps[e];
     if (T < 0) return;
     int longest = 0;
     for (int r = 0; r < rows; ++r) longest = max(longest, cols - (int)hd[r]);
@@ -1208,8 +1241,8 @@ splice_kernel(const gad_qnet net, uint8_t *__restrict__ boards, int32_t *__restr
                 __syncwarp();
             }
         }
-        const uint8_t *al = net.aligned + ((size_t)e * rows + r) * cap;
-        const uint8_t *sub = net.sub + ((size_t)e * rows + r) * cols;
+        const uint8_t *al = aligned + ((size_t)e * rows + r) * cap;
+        const uint8_t *sub = windows + ((size_t)wm * rows + r) * cols;
         const int h = hd[r];
         for (int c = lane; c < newlen; c += 32) {
             uint8_t v;
@@ -1639,6 +1672,9 @@ extern "C" int gad_qnet_forward_host(gad_qnet *q, const uint8_t *h_states, int64
     return GAD_OK;
 }
 
+static int run_lockstep(gad_qnet *q, long long n_unique, float max_value, cudaStream_t st, int64_t *forwards_out);
+static int finish_mutate(gad_qnet *q, long long n_unique, int64_t forwards, int64_t *h_forwards, cudaStream_t st);
+
 // GA.mutation for M individuals (GA.py:335-373): d_idx[m] is the individual, d_tile[m] = {from_row,
 // from_col} of its worst tile (gad_worst_tiles). Runs the greedy episodes in lock-step chunks, then
 // pads and splices the aligned sub-boards back. The stride must leave room for the growth:
@@ -1674,13 +1710,26 @@ extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int
     // 1. every episode's window; 2. one representative per distinct window
     episode_init_kernel<<<(unsigned)M, 64, 0, st>>>(*q, d_boards, R, stride, d_idx, d_tile, M, nullptr, nullptr);
     GAD_LAUNCH_CHECK();
-    dedup_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(*q, M, q->table, (unsigned int)(slots - 1), q->rep, q->uniq,
-                                                            q->counts, dedup);
+    dedup_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(q->sub, q->steps, q->rows * q->cols, M, q->table,
+                                                            (unsigned int)(slots - 1), q->rep, q->uniq, q->counts, dedup);
     GAD_LAUNCH_CHECK();
     GAD_CUDA(cudaMemcpyAsync(q->h_count, q->counts, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GAD_CUDA(cudaStreamSynchronize(st));
     const long long n_unique = q->h_count[0];
     // 3. the representatives' greedy episodes in lock-step chunks
+    if ((rc = run_lockstep(q, n_unique, max_value, st, &forwards))) return rc;
+    // 4. every individual takes the aligned rows of its window's representative
+    splice_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(q->rows, q->cols, q->rep, 0, q->aligned, q->heads, q->steps,
+                                                           q->sub, d_boards, d_rowlen, R, stride, d_idx, d_tile, M, d_status);
+    GAD_LAUNCH_CHECK();
+    return finish_mutate(q, n_unique, forwards, h_forwards, st);
+}
+
+// the greedy episodes of q->uniq[0 .. n_unique) in lock-step chunks (episode state in q->sub / heads / aligned / steps)
+static int run_lockstep(gad_qnet *q, long long n_unique, float max_value, cudaStream_t st, int64_t *forwards_out)
+{
+    int rc;
+    int64_t forwards = 0;
     for (long long u0 = 0; u0 < n_unique; u0 += kMaxBatch) {
         const long long nb = n_unique - u0 < kMaxBatch ? n_unique - u0 : kMaxBatch;
         if ((rc = ensure_states(q, nb))) return rc;
@@ -1704,9 +1753,12 @@ extern "C" int gad_mutate(gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int
             }
         }
     }
-    // 4. every individual takes the aligned rows of its window's representative
-    splice_kernel<<<(unsigned)((M + 3) / 4), 128, 0, st>>>(*q, d_boards, d_rowlen, R, stride, d_idx, d_tile, M, d_status);
-    GAD_LAUNCH_CHECK();
+    *forwards_out += forwards;
+    return GAD_OK;
+}
+
+static int finish_mutate(gad_qnet *q, long long n_unique, int64_t forwards, int64_t *h_forwards, cudaStream_t st)
+{
     unsigned long long h_stats[2] = {0, 0};
     GAD_CUDA(cudaMemcpyAsync(h_stats, q->d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     GAD_CUDA(cudaStreamSynchronize(st));
@@ -1724,6 +1776,106 @@ extern "C" int gad_mutate_stats(const gad_qnet *q, int64_t *out4)
 {
     GAD_REQUIRE(q && out4, "gad_mutate_stats: null pointer");
     for (int i = 0; i < 4; ++i) out4[i] = q->last_stats[i];
+    return GAD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same mutation in separate steps, for a population sharded over several GPUs: the windows of ALL ranks
+// are gathered, every rank finds the distinct ones (identically), runs its share of them and the results are
+// gathered back - each distinct window runs once in the whole job and the ranks do equal work.
+//   gad_mutate_windows   windows of the local individuals            (GA.py:338-350)
+//   gad_windows_rep      rep[m] = smallest index of a window identical to m (deterministic across ranks)
+//   gad_episodes_run     greedy episodes of listed windows           (GA.py:353-366, env.py:231-259)
+//   gad_splice_results   padding + splice from gathered results      (env.py:338-351, GA.py:369-373)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void windows_kernel(int rows, int cols, const uint8_t *__restrict__ boards, int R, int stride,
+                               const int32_t *__restrict__ idx, const int32_t *__restrict__ tile, uint8_t *__restrict__ out)
+{
+    const long long m = blockIdx.x;
+    const long long p = idx ? idx[m] : m;
+    const int fr = tile[2 * m], fc = tile[2 * m + 1];
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int r = i / cols, c = i - r * cols;
+        out[(size_t)m * rows * cols + i] = (fr < 0 || fc < 0) ? (uint8_t)0 : boards[((size_t)p * R + fr + r) * stride + fc + c];
+    }
+}
+}  // namespace
+
+extern "C" int gad_mutate_windows(const gad_qnet *q, const uint8_t *d_boards, int R, int stride, const int32_t *d_idx,
+                                  const int32_t *d_tile, int64_t M, uint8_t *d_windows, void *stream)
+{
+    if (M == 0) return GAD_OK;
+    GAD_REQUIRE(q && d_boards && d_tile && d_windows && M > 0 && R >= q->rows, "gad_mutate_windows: bad argument");
+    windows_kernel<<<(unsigned)M, 64, 0, gad_stream(stream)>>>(q->rows, q->cols, d_boards, R, stride, d_idx, d_tile, d_windows);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// d_table: int32 scratch of table_slots entries (a power of two >= 2 * M); d_tmp: int32[M] scratch.
+extern "C" int gad_windows_rep(const uint8_t *d_windows, int64_t M, int window_bytes, int32_t *d_rep, int32_t *d_table,
+                               int64_t table_slots, int32_t *d_tmp, void *stream)
+{
+    if (M == 0) return GAD_OK;
+    GAD_REQUIRE(d_windows && d_rep && d_table && d_tmp && M > 0 && window_bytes >= 1, "gad_windows_rep: bad argument");
+    GAD_REQUIRE(table_slots >= 2 * M && (table_slots & (table_slots - 1)) == 0 && M < (1ll << 30),
+                "gad_windows_rep: the table needs a power-of-two number of slots >= 2 * M");
+    if (M == 0) return GAD_OK;
+    cudaStream_t st = gad_stream(stream);
+    GAD_CUDA(cudaMemsetAsync(d_table, 0xFF, (size_t)table_slots * sizeof(int32_t), st));
+    GAD_CUDA(cudaMemsetAsync(d_tmp, 0x7F, (size_t)M * sizeof(int32_t), st));
+    dedup_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(d_windows, nullptr, window_bytes, M, d_table,
+                                                            (unsigned int)(table_slots - 1), d_rep, nullptr, nullptr, 1);
+    rep_min_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_rep, d_tmp, M);
+    rep_relabel_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(d_rep, d_tmp, M);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// Episodes of the windows d_list[0 .. U) (indices into d_windows; NULL = the first U windows). Results, indexed by
+// position in the list: d_aligned uint8 [U][rows][rows*cols] (the first d_steps[e] columns are valid), d_heads
+// uint8 [U][rows] (tokens consumed per row), d_steps int32 [U]. Synchronises.
+extern "C" int gad_episodes_run(gad_qnet *q, const uint8_t *d_windows, const int32_t *d_list, int64_t U, float max_value,
+                                uint8_t *d_aligned, uint8_t *d_heads, int32_t *d_steps, int64_t *h_forwards, void *stream)
+{
+    GAD_REQUIRE(q && U >= 0 && U < (1ll << 30), "gad_episodes_run: bad argument");
+    cudaStream_t st = gad_stream(stream);
+    q->last_stats[0] = U; q->last_stats[1] = q->last_stats[2] = q->last_stats[3] = 0;
+    int64_t forwards = 0;
+    if (U == 0) {
+        if (h_forwards) *h_forwards = 0;
+        return GAD_OK;
+    }
+    GAD_REQUIRE(d_windows && d_aligned && d_heads && d_steps, "gad_episodes_run: null pointer");
+    int rc = ensure_episodes(q, U);
+    if (!rc) rc = ensure_states(q, U < kMaxBatch ? U : kMaxBatch);
+    if (rc) return rc;
+    GAD_CUDA(cudaMemsetAsync(q->d_stats, 0, 2 * sizeof(unsigned long long), st));
+    episodes_from_windows_kernel<<<(unsigned)U, 64, 0, st>>>(*q, d_windows, d_list, U);
+    GAD_LAUNCH_CHECK();
+    if ((rc = run_lockstep(q, U, max_value, st, &forwards))) return rc;
+    const size_t cap = (size_t)q->rows * q->cols;
+    GAD_CUDA(cudaMemcpyAsync(d_aligned, q->aligned, (size_t)U * q->rows * cap, cudaMemcpyDeviceToDevice, st));
+    GAD_CUDA(cudaMemcpyAsync(d_heads, q->heads, (size_t)U * q->rows, cudaMemcpyDeviceToDevice, st));
+    GAD_CUDA(cudaMemcpyAsync(d_steps, q->steps, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return finish_mutate(q, U, forwards, h_forwards, st);
+}
+
+// d_windows: the local individuals' own windows [M][rows*cols]; d_slot[m]: which entry of the result arrays
+// (d_aligned / d_heads / d_steps, e.g. all-gathered from every rank) individual m takes. Asynchronous.
+extern "C" int gad_splice_results(const gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int R, int stride,
+                                  const int32_t *d_idx, const int32_t *d_tile, int64_t M, const uint8_t *d_windows,
+                                  const int32_t *d_slot, const uint8_t *d_aligned, const uint8_t *d_heads,
+                                  const int32_t *d_steps, int32_t *d_status, void *stream)
+{
+    if (M == 0) return GAD_OK;
+    GAD_REQUIRE(q && d_boards && d_rowlen && d_tile && d_windows && d_slot && d_aligned && d_heads && d_steps && d_status,
+                "gad_splice_results: null pointer");
+    GAD_REQUIRE(M > 0 && R >= q->rows && stride >= 16 && stride % 16 == 0, "gad_splice_results: bad shape");
+    splice_kernel<<<(unsigned)((M + 3) / 4), 128, 0, gad_stream(stream)>>>(q->rows, q->cols, d_slot, 1, d_aligned, d_heads,
+                                                                          d_steps, d_windows, d_boards, d_rowlen, R, stride,
+                                                                          d_idx, d_tile, M, d_status);
+    GAD_LAUNCH_CHECK();
     return GAD_OK;
 }
 

@@ -18,6 +18,7 @@ exercised on CPU (tests/test_sharded_cpu.py plugs the oracle in); ``DeviceBacken
 """
 from __future__ import annotations
 
+import os
 import random
 
 import numpy as np
@@ -302,7 +303,51 @@ class ShardedGA:
         chosen[order.to(torch.int64)] = True
         local = chosen[self.gidx].nonzero().flatten().to(torch.int32)
         # the stride must grow identically on every rank (the survivor all-gather needs equal strides)
-        self.backend.mutate(local, model_path, self.mode, int(self.g_scores[2].max().item()))
+        width = int(self.g_scores[2].max().item())
+        if self.world > 1 and getattr(self.backend, "global_mutation", False):
+            self._mutation_global(local, chosen, model_path, width)
+        else:
+            self.backend.mutate(local, model_path, self.mode, width)
+
+    def _mutation_global(self, local, chosen, model_path, width):
+        """The mutation phase with the windows of ALL ranks pooled: every rank extracts the windows of its own
+        individuals (180 bytes each for a 6x30 agent), one all-gather makes the pool identical everywhere, every rank
+        finds the distinct windows (deterministically: the representative is the smallest index), the u-th distinct
+        window runs on rank u % world, and one all-gather of the results (aligned rows, heads, step count) lets every
+        rank splice its own individuals. Each distinct window runs ONCE in the whole job - duplicates across ranks
+        included - and every rank runs the same number of episodes. Results are those of the single-GPU path: an
+        episode is a pure function of its window and Q-values do not depend on the batch (gemm_tc.cu)."""
+        be, dev, world, rank = self.backend, self.backend.device, self.world, self.rank
+        # individuals to mutate per rank, from the replicated ranking (no collective): one host read
+        counts = torch.bincount(self.owner[chosen], minlength=world).cpu().tolist()
+        m_loc = int(local.numel())
+        assert m_loc == counts[rank]
+        if sum(counts) == 0:
+            return
+        windows, tile = be.mutation_windows(local, model_path, self.mode, width)          # uint8 [m_loc, rows*cols]
+        pool = self._all_gather_padded(windows, counts)                                    # [M, rows*cols], rank-major
+        M = int(pool.shape[0])
+        rep = be.windows_rep(pool)                                                         # int32 [M]
+        flags = rep == torch.arange(M, dtype=torch.int32, device=dev)
+        uidx = torch.cumsum(flags.to(torch.int64), 0) - 1                                  # ordinal of every distinct window
+        n_unique = int(flags.sum().item())
+        per_rank = -(-n_unique // world)
+        mine = (flags & (uidx % world == rank)).nonzero().flatten().to(torch.int32)        # ascending: j-th = ordinal rank + j*world
+        aligned, heads, steps = be.run_episodes(pool, mine, per_rank)
+        if world > 1:
+            a_all = torch.empty((world * per_rank,) + tuple(aligned.shape[1:]), dtype=torch.uint8, device=dev)
+            h_all = torch.empty((world * per_rank,) + tuple(heads.shape[1:]), dtype=torch.uint8, device=dev)
+            s_all = torch.empty((world * per_rank,), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(a_all, aligned, group=self.group)
+            dist.all_gather_into_tensor(h_all, heads, group=self.group)
+            dist.all_gather_into_tensor(s_all, steps, group=self.group)
+            self.comm_bytes += (aligned.numel() + heads.numel() + 4 * steps.numel()) * (world - 1)
+        else:
+            a_all, h_all, s_all = aligned, heads, steps
+        off = sum(counts[:rank])
+        u = uidx[rep[off:off + m_loc].to(torch.int64)]
+        slot = ((u % world) * per_rank + u // world).to(torch.int32)
+        be.splice_results(local, tile, windows, slot, a_all, h_all, s_all, width)
 
     # ------------------------------------------------------------------ a19
     def run(self, model_path, debug_mode=False):
@@ -454,6 +499,77 @@ class DeviceBackend:
 
     def crossover_from(self, all_boards, all_rowlen, pos, plan):
         self.pop.crossover_from(all_boards, all_rowlen, pos, plan)
+
+    # -- mutation with the windows of all ranks pooled (ShardedGA._mutation_global) ---------------------------
+    global_mutation = os.environ.get("GAD_SHARDED_MUTATION", "global") != "local"      # A/B: every rank on its own windows
+
+    def mutation_windows(self, local_idx, model_path, mode, global_width):
+        from DPAMSA import dqn as _dqn
+        rw, cw = int(config.AGENT_WINDOW_ROW), int(config.AGENT_WINDOW_COLUMN)
+        self.pop.ensure_stride(global_width + (rw - 1) * cw)
+        qnet = _dqn.load_qnet(model_path, rw, cw)
+        M = int(local_idx.numel())
+        tile = self.pop.worst_tiles(local_idx, rw, cw, mode, *self._weights()) if M else \
+            torch.empty((0, 2), dtype=torch.int32, device=self.device)
+        if M and int(tile.min().item()) < 0:
+            raise ValueError("min() arg is an empty sequence")          # no tile fits (utils.py:291)
+        windows = torch.empty((M, rw * cw), dtype=torch.uint8, device=self.device)
+        b = self.pop.cur
+        self.nat.call("gad_mutate_windows", qnet.handle, self.nat.ptr(b.boards), self.R, self.pop.stride,
+                      self.nat.ptr(local_idx), self.nat.ptr(tile), M, self.nat.ptr(windows), self.nat.current_stream_ptr())
+        self._mut_qnet = qnet
+        self._mut_max_value = cw * (rw * (rw - 1) / 2 * config.MATCH_REWARD)
+        return windows, tile
+
+    def windows_rep(self, pool):
+        M = int(pool.shape[0])
+        slots = 1024
+        while slots < 2 * M:
+            slots <<= 1
+        rep = torch.empty(M, dtype=torch.int32, device=self.device)
+        table = torch.empty(slots, dtype=torch.int32, device=self.device)
+        tmp = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)
+        pool = pool.contiguous()
+        self.nat.call("gad_windows_rep", self.nat.ptr(pool), M, int(pool.shape[1]), self.nat.ptr(rep), self.nat.ptr(table),
+                      slots, self.nat.ptr(tmp), self.nat.current_stream_ptr())
+        return rep
+
+    def run_episodes(self, pool, mine, padded):
+        import ctypes
+        q = self._mut_qnet
+        U = int(mine.numel())
+        aligned = torch.zeros((padded, q.rows, q.rows * q.cols), dtype=torch.uint8, device=self.device)
+        heads = torch.zeros((padded, q.rows), dtype=torch.uint8, device=self.device)
+        steps = torch.full((padded,), -1, dtype=torch.int32, device=self.device)
+        fw = ctypes.c_int64(0)
+        pool = pool.contiguous()
+        self.nat.call("gad_episodes_run", q.handle, self.nat.ptr(pool), self.nat.ptr(mine), U, float(self._mut_max_value),
+                      self.nat.ptr(aligned), self.nat.ptr(heads), self.nat.ptr(steps), ctypes.byref(fw),
+                      self.nat.current_stream_ptr())
+        st = (ctypes.c_int64 * 4)()
+        self.nat.call("gad_mutate_stats", q.handle, st)
+        p = self.pop
+        p.forwards += fw.value
+        p.unique_episodes += U
+        p.states += int(st[3])
+        return aligned, heads, steps
+
+    def splice_results(self, local_idx, tile, windows, slot, aligned, heads, steps, width):
+        q = self._mut_qnet
+        p = self.pop
+        M = int(local_idx.numel())
+        p.episodes += M
+        p.width_hint = width + q.cols
+        if M == 0:
+            return
+        p._status.zero_()
+        b = p.cur
+        self.nat.call("gad_splice_results", q.handle, self.nat.ptr(b.boards), self.nat.ptr(b.rowlen), self.R, p.stride,
+                      self.nat.ptr(local_idx), self.nat.ptr(tile), M, self.nat.ptr(windows), self.nat.ptr(slot.contiguous()),
+                      self.nat.ptr(aligned), self.nat.ptr(heads), self.nat.ptr(steps), self.nat.ptr(p._status),
+                      self.nat.current_stream_ptr())
+        if int(p._status.item()) & 1:
+            raise self.nat.GadCapacityError("a mutated row outgrew the board stride")
 
     def mutate(self, local_idx, model_path, mode, global_width):
         from DPAMSA import dqn as _dqn
