@@ -43,6 +43,53 @@ def _mt_restore(arr, meta):
     random.setstate((meta[0], tuple(int(x) for x in arr), meta[1]))
 
 
+class PlanJob:
+    """The crossover plan of GA.py:281-293 drawn ahead of time on a worker thread (ctypes releases the GIL).
+
+    The plan depends only on the number of survivors, the number of rows and the `random` stream - not on any
+    score - so it can be drawn while the GPU runs the phases before the crossover. In 'sp' / 'cs' mode the survivor
+    count is int(population_size * SELECTION_RATE) whatever the scores are, so the job starts with the generation;
+    in 'mo' mode it starts when the selection has counted the survivors. Nothing else consumes `random` in
+    between; the generator state is handed back in finish(). A job whose (parents, children) turn out wrong - a
+    knob changed, a smaller population - or whose generator was touched meanwhile is discarded and the generator
+    is left where it is."""
+
+    def __init__(self, n_parents, n_rows, n_children):
+        import threading
+        self.key = (int(n_parents), int(n_rows), int(n_children))
+        self.plan = np.empty((max(int(n_children), 0), 3), dtype=np.int32)
+        self.state, self.meta = _mt_state()
+        self.start_state = self.state.copy()
+        self.error = None
+        self.thread = threading.Thread(target=self._work, daemon=True)
+        self.thread.start()
+
+    def _work(self):
+        try:
+            nat.call("gad_mt_crossover_plan_host", self.state.ctypes.data, self.key[0], self.key[1], self.key[2], None,
+                     self.plan.ctypes.data)
+        except Exception as exc:              # re-raised by finish()
+            self.error = exc
+
+    @staticmethod
+    def start(n_parents, n_rows, n_children):
+        if n_children <= 0 or n_parents < 2 or n_rows < 2:
+            return None                       # nothing to draw, or a case in which the inline path raises
+        return PlanJob(n_parents, n_rows, n_children)
+
+    def finish(self, n_parents, n_rows, n_children):
+        """The plan, or None when the job does not fit (the caller then draws inline from the untouched generator)."""
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        if self.key != (int(n_parents), int(n_rows), int(n_children)):
+            return None
+        if not np.array_equal(_mt_state()[0], self.start_state):
+            return None                       # somebody reseeded or drew from `random` meanwhile: their stream wins
+        _mt_restore(self.state, self.meta)
+        return self.plan
+
+
 def _on_device(fn):
     """Run a GA phase with the population's GPU current: kernels are launched on that device's current stream
     and the Q-net handle is created there, whatever device the caller (or another GA instance) selected last."""
@@ -62,6 +109,7 @@ class GA:
         self.current_iteration = 0
         self._dev = None                 # DevicePopulation
         self._device = torch.device(config.DEVICE)
+        self._plan_job = None            # crossover plan being drawn ahead of time (PlanJob)
 
     # ------------------------------------------------------------------ device <-> python views
     def _weights(self):
@@ -227,7 +275,9 @@ class GA:
     def selection(self):
         """GA.py:232-260"""
         top_n = int(self.population_size * config.SELECTION_RATE)
-        self._dev.select(self.mode, top_n)
+        n_keep = self._dev.select(self.mode, top_n)
+        if self._plan_job is None and getattr(config, "CROSSOVER_KIND", "horizontal") != "vertical":
+            self._plan_job = PlanJob.start(n_keep, self._dev.R, int(config.POPULATION_SIZE) - n_keep)
         self.calculate_fitness_score()
 
     # ------------------------------------------------------------------ a12 / a13
@@ -239,12 +289,17 @@ class GA:
             widths = None
             if kind == 1:
                 widths = dev.cur.al[:dev.n].cpu().numpy().astype(np.int32)
-            plan = np.empty((n_children, 3), dtype=np.int32)
-            state, meta = _mt_state()
-            nat.call("gad_mt_crossover_plan_host", state.ctypes.data, dev.n, dev.R, n_children,
-                     None if widths is None else widths.ctypes.data, plan.ctypes.data)
-            _mt_restore(state, meta)
+            job, self._plan_job = self._plan_job, None
+            plan = job.finish(dev.n, dev.R, n_children) if (job is not None and kind == 0) else None
+            if plan is None:
+                plan = np.empty((n_children, 3), dtype=np.int32)
+                state, meta = _mt_state()
+                nat.call("gad_mt_crossover_plan_host", state.ctypes.data, dev.n, dev.R, n_children,
+                         None if widths is None else widths.ctypes.data, plan.ctypes.data)
+                _mt_restore(state, meta)
             dev.crossover(plan, kind)
+        else:
+            self._plan_job = None
         self.calculate_fitness_score()
 
     def horizontal_crossover(self):
@@ -264,6 +319,13 @@ class GA:
         rw, cw = int(config.AGENT_WINDOW_ROW), int(config.AGENT_WINDOW_COLUMN)
         n = round(config.POPULATION_SIZE * config.MUTATION_RATE)
         n = min(n, dev.n)
+        # 'sp' / 'cs': the selection will keep exactly top_n individuals, so the crossover plan can be drawn now,
+        # under the whole mutation phase (PlanJob)
+        self._plan_job = None
+        if self.mode in ("sp", "cs") and getattr(config, "CROSSOVER_KIND", "horizontal") != "vertical":
+            top_n = int(self.population_size * config.SELECTION_RATE)
+            if 2 <= top_n <= dev.n:
+                self._plan_job = PlanJob.start(top_n, dev.R, int(config.POPULATION_SIZE) - top_n)
         if n <= 0:
             return
         if rw > dev.R:

@@ -244,6 +244,11 @@ class ShardedGA:
         self.backend.compact(local_keep)
         self.gidx = dst[self.gidx][local_keep].to(torch.int64)
         self.n_global = count
+        # The crossover plan depends only on the survivor count and the `random` stream, not on any score: start
+        # drawing it now (a sequential MT19937 walk over every child of the WHOLE population, on every rank) on a
+        # worker thread, under the compaction and the fitness pass that follow. horizontal_crossover joins it.
+        if hasattr(self.backend, "crossover_plan_start") and getattr(self, "_plan_job", None) is None:
+            self._plan_job = self.backend.crossover_plan_start(count, int(config.POPULATION_SIZE) - count)
         self.calculate_fitness_score()
 
     # ------------------------------------------------------------------ a12
@@ -254,7 +259,11 @@ class ShardedGA:
         S = self.n_global
         n_children = P - S
         if n_children > 0:
-            plan = self.backend.crossover_plan(S, n_children)            # identical on every rank
+            job, self._plan_job = getattr(self, "_plan_job", None), None
+            if job is not None:
+                plan = self.backend.crossover_plan_finish(job, S, n_children)
+            else:
+                plan = self.backend.crossover_plan(S, n_children)        # identical on every rank
             counts = self._counts(int(self.gidx.numel()))
             lo = shard_bounds(P, self.world)
             need = [max(0, (lo[r + 1] - lo[r]) - counts[r]) for r in range(self.world)]
@@ -296,6 +305,13 @@ class ShardedGA:
     # ------------------------------------------------------------------ a14
     def mutation(self, model_path):
         n = min(round(config.POPULATION_SIZE * config.MUTATION_RATE), self.n_global)
+        # 'sp' / 'cs': the selection keeps exactly top_n individuals whatever the scores: draw the crossover plan
+        # (a sequential MT19937 walk over every child of the whole population, on every rank) under the mutation phase
+        self._plan_job = None
+        if self.mode in ("sp", "cs") and hasattr(self.backend, "crossover_plan_start"):
+            top_n = int(self.population_size * config.SELECTION_RATE)
+            if 2 <= top_n <= self.n_global:
+                self._plan_job = self.backend.crossover_plan_start(top_n, int(config.POPULATION_SIZE) - top_n)
         if n <= 0:
             return
         order = self.backend.rank_order(self.g_scores, self.n_global, self.mode, n)      # logical indices
@@ -496,6 +512,15 @@ class DeviceBackend:
                       plan.ctypes.data)
         ga_mod._mt_restore(state, meta)
         return plan
+
+    def crossover_plan_start(self, n_parents, n_children):
+        """GA.PlanJob: the plan drawn on a worker thread while the GPU works on the phases before the crossover."""
+        import GA as ga_mod
+        return ga_mod.PlanJob.start(n_parents, self.R, n_children)
+
+    def crossover_plan_finish(self, job, n_parents, n_children):
+        plan = job.finish(n_parents, self.R, n_children)
+        return plan if plan is not None else self.crossover_plan(n_parents, n_children)
 
     def crossover_from(self, all_boards, all_rowlen, pos, plan):
         self.pop.crossover_from(all_boards, all_rowlen, pos, plan)
