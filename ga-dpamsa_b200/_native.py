@@ -36,6 +36,7 @@ SIGNATURES = {
     "gad_memcpy_d2h": (c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "gad_memset": (c_int, [c_vp, c_int, ctypes.c_size_t, c_vp]),
     "gad_stream_sync": (c_int, [c_vp]),
+    "gad_enable_peer_access": (c_int, [c_int]),
     "gad_fitness": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gad_probe_read": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "gad_fitness_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int]),

@@ -82,3 +82,21 @@ extern "C" int gad_stream_sync(void *stream)
     GAD_CUDA(cudaStreamSynchronize(gad_stream(stream)));
     return GAD_OK;
 }
+
+// Lets kernels launched on the current device dereference pointers into `peer_device`'s memory (NVLink / PCIe P2P).
+// Used by scripts/peer_crossover_probe.py to run gad_crossover_peer in ONE process on two GPUs (so that it can be
+// profiled); the sharded loop gets its peer pointers from symmetric-memory allocations instead.
+extern "C" int gad_enable_peer_access(int peer_device)
+{
+    int can = 0, cur = 0;
+    GAD_CUDA(cudaGetDevice(&cur));
+    GAD_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    GAD_REQUIRE(can, "device %d cannot access device %d", cur, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return GAD_OK;
+    }
+    GAD_CUDA(e);
+    return GAD_OK;
+}

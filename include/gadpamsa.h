@@ -55,7 +55,9 @@ int gad_free_host(void *h_ptr);
 int gad_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
 int gad_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int gad_memset(void *d_dst, int value, size_t bytes, void *stream);
-int gad_stream_sync(void *stream);                         /* synchronises */
+int gad_stream_sync(void *stream);
+/* Allow kernels on the current device to read `peer_device`'s memory (measurement scripts; see api.cu). */
+int gad_enable_peer_access(int peer_device);                         /* synchronises */
 
 /* ---- a4-a7: one fitness pass over the whole population ------------------
  * Replaces GA.calculate_fitness_score's per-board loop (GA.py:156-178):
