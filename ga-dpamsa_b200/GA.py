@@ -125,6 +125,10 @@ class GA:
         wide = np.full((boards.shape[0], boards.shape[1], stride), 5, dtype=np.uint8)
         wide[:, :, :boards.shape[2]] = boards
         self._dev = DevicePopulation.from_numpy(wide, rowlen, device=self._device, capacity=cap)
+        self._keep_hof(old)
+
+    def _keep_hof(self, old):
+        """A new population keeps the hall of fame (and the counters) of the one it replaces (GA.py:71)."""
         if old is not None and old.hof_valid and old.R == self._dev.R:
             self._dev.ensure_stride(old.stride)
             old.ensure_stride(self._dev.stride)
@@ -244,10 +248,59 @@ class GA:
         _mt_restore(state, meta)
         return boards, rowlen
 
+    def _generate_device(self, own_first=0, own_step=1, min_stride=0):
+        """GA.py:71-94 built ON the device (csrc/mt_device.cu: the same MT19937 draws, the same boards, no host
+        copy and no upload). Returns device tensors (boards uint8 [n,R,stride], rowlen int32 [n,R]) of the boards p
+        with p % own_step == own_first, or None for shapes the device generator does not cover / GAD_POPGEN=host."""
+        import os
+        nat.require_device()
+        if os.environ.get("GAD_POPGEN", "device") == "host":
+            return None
+        seqs = [[nucleotides_map[nuc] for nuc in seq] for seq in self.sequences]      # KeyError like GA.py:79
+        R = len(seqs)
+        P = self.population_size
+        n_clone = round(P * config.CLONE_RATE)
+        ngaps = np.array([max(1, round(len(s) * config.GAP_RATE)) for s in seqs], dtype=np.int32)
+        seqlen = np.array([len(s) for s in seqs], dtype=np.int32)
+        if n_clone < P and int(seqlen.min()) < 1:
+            raise ValueError("empty range in randrange(0, 0)")                        # random.randint(0, -1)
+        if int(ngaps.max()) > 64:
+            return None
+        cstride = max(1, int(seqlen.max()))
+        seq_arr = np.full((R, cstride), 5, dtype=np.uint8)
+        for r, s in enumerate(seqs):
+            seq_arr[r, :len(s)] = s
+        stride = max(-(-(cstride + int(ngaps.max())) // 16) * 16, -(-int(min_stride) // 16) * 16)
+        n_own = len(range(own_first, P, own_step))
+        boards = torch.empty((n_own, R, stride), dtype=torch.uint8, device=self._device)
+        rowlen = torch.empty((n_own, R), dtype=torch.int32, device=self._device)
+        state, meta = _mt_state()
+        try:
+            nat.call("gad_population_device", state.ctypes.data, seq_arr.ctypes.data, seqlen.ctypes.data, cstride,
+                     ngaps.ctypes.data, R, P, n_clone, own_first, own_step, nat.ptr(boards), nat.ptr(rowlen), stride,
+                     nat.current_stream_ptr())
+        except ValueError:
+            return None                                    # GAD_EINVAL: a shape outside the device generator
+        _mt_restore(state, meta)
+        return boards, rowlen
+
     @_on_device
     def generate_population(self):
-        """GA.py:71-94: n_clone exact copies, then gap-inserted individuals; uploaded to the device."""
-        self._adopt(*self._generate_host())
+        """GA.py:71-94: n_clone exact copies, then gap-inserted individuals - generated on the device; the host
+        replay (gad_mt_population_host + upload) covers the shapes the device generator does not."""
+        extra = max(16, (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
+        width = max((len(s) for s in self.sequences), default=0)
+        width += max(1, round(width * config.GAP_RATE))
+        made = self._generate_device(min_stride=width + extra)
+        if made is None:
+            self._adopt(*self._generate_host())
+            return
+        boards, rowlen = made
+        old = self._dev
+        cap = max(int(config.POPULATION_SIZE), self.population_size, boards.shape[0])
+        self._dev = DevicePopulation(boards, rowlen, capacity=cap)
+        self._dev.width_hint = width
+        self._keep_hof(old)
 
     # ------------------------------------------------------------------ a4 + a8
     @_on_device

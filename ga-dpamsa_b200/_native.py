@@ -58,6 +58,7 @@ SIGNATURES = {
     "gad_mt_population_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_int]),
     "gad_mt_population_shard_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,
                                              c_int]),
+    "gad_population_device": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_vp]),
     "gad_worst_tiles": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_vp, c_vp]),
     "gad_qnet_create": (c_int, [ctypes.POINTER(c_vp), c_int, c_int, c_int, c_int, c_int, c_int,

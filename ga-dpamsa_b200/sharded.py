@@ -99,9 +99,11 @@ class ShardedGA:
         # interleaved placement (individual i -> rank i % world): the clones - the first CLONE_RATE of the
         # list and usually the best scored, hence the first to be mutated - spread evenly over the ranks.
         # Every rank consumes the whole random stream but materialises only its own boards.
-        boards, rowlen = self.backend.generate_shard(self.sequences, P, self.rank, self.world)
         mine = np.arange(self.rank, P, self.world)
-        self.backend.adopt(boards, rowlen, capacity=lo[1] - lo[0])
+        if not (hasattr(self.backend, "generate_and_adopt") and
+                self.backend.generate_and_adopt(self.sequences, P, self.rank, self.world, lo[1] - lo[0])):
+            boards, rowlen = self.backend.generate_shard(self.sequences, P, self.rank, self.world)
+            self.backend.adopt(boards, rowlen, capacity=lo[1] - lo[0])
         self.gidx = torch.from_numpy(mine).to(self.backend.device, torch.int64)
         self.n_global = P
 
@@ -431,6 +433,30 @@ class DeviceBackend:
         extra = max(32, 2 * (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
         width = max(len(s) for s in sequences) + max(1, round(max(len(s) for s in sequences) * config.GAP_RATE))
         return g._generate_host(rank, world, min_stride=width + extra)     # final stride at once: no second host copy
+
+    def generate_and_adopt(self, sequences, P, rank, world, capacity):
+        """The shard generated on the device (GA._generate_device): every rank walks the whole stream on its own GPU
+        and keeps its own boards. False when the shape is outside the device generator (the host replay follows)."""
+        import GA as ga_mod
+        from population import DevicePopulation
+        g = ga_mod.GA.__new__(ga_mod.GA)
+        g.sequences, g.mode, g.population_size, g._dev = sequences, 'sp', P, None
+        g._device = self.device
+        extra = max(32, 2 * (int(config.AGENT_WINDOW_ROW) - 1) * int(config.AGENT_WINDOW_COLUMN))
+        width = max(len(s) for s in sequences) + max(1, round(max(len(s) for s in sequences) * config.GAP_RATE))
+        made = g._generate_device(rank, world, min_stride=width + extra)
+        if made is None:
+            return False
+        boards, rowlen = made
+        self.pop = DevicePopulation(boards, rowlen, capacity=max(capacity, 1),
+                                    allocator=self._symm_alloc if self._symm else None)
+        self.pop.width_hint = width
+        self.R = self.pop.R
+        if self._symm:
+            self.pop.ensure_alt()
+            self.pop.on_realloc = self._on_realloc
+            self._rendezvous()
+        return True
 
     def adopt(self, boards, rowlen, capacity):
         from population import DevicePopulation

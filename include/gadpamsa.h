@@ -179,6 +179,15 @@ int gad_mt_population_shard_host(uint32_t *mt_state, const uint8_t *h_seqs, cons
                                  const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone, int64_t own_first,
                                  int64_t own_step, uint8_t *h_boards, int32_t *h_rowlen, int stride);
 
+/* The same population built ON THE DEVICE, draw for draw on the same MT19937 stream (csrc/mt_device.cu: one CTA
+ * streams the generator, a chunked finite-state scan resolves the rejection sampling, one warp per row places the
+ * gaps). mt_state is the host copy of CPython's state (in/out); boards p with p % own_step == own_first are
+ * written densely into d_boards / d_rowlen (device). Returns GAD_EINVAL for shapes it does not cover (more than 64
+ * gaps per row, a draw pattern of period above 4096): use gad_mt_population_host then. Synchronises. */
+int gad_population_device(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen, int seq_stride,
+                          const int32_t *h_ngaps, int R, int64_t P, int64_t n_clone, int64_t own_first, int64_t own_step,
+                          uint8_t *d_boards, int32_t *d_rowlen, int stride, void *stream);
+
 /* ---- a15: worst-fitted sub-board of every mutating individual -------------
  * utils.calculate_worst_fitted_sub_board (utils.py:276-313) over the implicit (rw, cw) tile lattice
  * of utils.get_all_different_sub_range (utils.py:230-252). d_idx[m] (NULL = identity) names the
