@@ -73,7 +73,7 @@ SIGNATURES = {
     "gad_mutate_stats": (c_int, [c_vp, c_i64p]),
     "gad_mutate_windows": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "gad_windows_rep": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "gad_episodes_run": (c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, c_vp, c_vp, c_vp, c_i64p, c_vp]),
+    "gad_episodes_run": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_float, c_vp, c_vp, c_vp, c_i64p, c_vp]),
     "gad_splice_results": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 

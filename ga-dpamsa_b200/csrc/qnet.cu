@@ -1835,8 +1835,9 @@ extern "C" int gad_windows_rep(const uint8_t *d_windows, int64_t M, int window_b
 // Episodes of the windows d_list[0 .. U) (indices into d_windows; NULL = the first U windows). Results, indexed by
 // position in the list: d_aligned uint8 [U][rows][rows*cols] (the first d_steps[e] columns are valid), d_heads
 // uint8 [U][rows] (tokens consumed per row), d_steps int32 [U]. Synchronises.
-extern "C" int gad_episodes_run(gad_qnet *q, const uint8_t *d_windows, const int32_t *d_list, int64_t U, float max_value,
-                                uint8_t *d_aligned, uint8_t *d_heads, int32_t *d_steps, int64_t *h_forwards, void *stream)
+extern "C" int gad_episodes_run(gad_qnet *q, const uint8_t *d_windows, const int32_t *d_list, int64_t U, int64_t reserve,
+                                float max_value, uint8_t *d_aligned, uint8_t *d_heads, int32_t *d_steps, int64_t *h_forwards,
+                                void *stream)
 {
     GAD_REQUIRE(q && U >= 0 && U < (1ll << 30), "gad_episodes_run: bad argument");
     cudaStream_t st = gad_stream(stream);
@@ -1847,8 +1848,11 @@ extern "C" int gad_episodes_run(gad_qnet *q, const uint8_t *d_windows, const int
         return GAD_OK;
     }
     GAD_REQUIRE(d_windows && d_aligned && d_heads && d_steps, "gad_episodes_run: null pointer");
-    int rc = ensure_episodes(q, U);
-    if (!rc) rc = ensure_states(q, U < kMaxBatch ? U : kMaxBatch);
+    // buffers for `reserve` episodes (the most this caller can ever ask for): the number of distinct windows changes
+    // from generation to generation and re-allocating in between costs more than the memory
+    const long long room = reserve > U ? reserve : U;
+    int rc = ensure_episodes(q, room);
+    if (!rc) rc = ensure_states(q, room < kMaxBatch ? room : kMaxBatch);
     if (rc) return rc;
     GAD_CUDA(cudaMemsetAsync(q->d_stats, 0, 2 * sizeof(unsigned long long), st));
     episodes_from_windows_kernel<<<(unsigned)U, 64, 0, st>>>(*q, d_windows, d_list, U);

@@ -351,7 +351,7 @@ class ShardedGA:
         n_unique = int(flags.sum().item())
         per_rank = -(-n_unique // world)
         mine = (flags & (uidx % world == rank)).nonzero().flatten().to(torch.int32)        # ascending: j-th = ordinal rank + j*world
-        aligned, heads, steps = be.run_episodes(pool, mine, per_rank)
+        aligned, heads, steps = be.run_episodes(pool, mine, per_rank, reserve=-(-M // world))
         if world > 1:
             a_all = torch.empty((world * per_rank,) + tuple(aligned.shape[1:]), dtype=torch.uint8, device=dev)
             h_all = torch.empty((world * per_rank,) + tuple(heads.shape[1:]), dtype=torch.uint8, device=dev)
@@ -585,7 +585,7 @@ class DeviceBackend:
                       slots, self.nat.ptr(tmp), self.nat.current_stream_ptr())
         return rep
 
-    def run_episodes(self, pool, mine, padded):
+    def run_episodes(self, pool, mine, padded, reserve=0):
         import ctypes
         q = self._mut_qnet
         U = int(mine.numel())
@@ -594,7 +594,8 @@ class DeviceBackend:
         steps = torch.full((padded,), -1, dtype=torch.int32, device=self.device)
         fw = ctypes.c_int64(0)
         pool = pool.contiguous()
-        self.nat.call("gad_episodes_run", q.handle, self.nat.ptr(pool), self.nat.ptr(mine), U, float(self._mut_max_value),
+        self.nat.call("gad_episodes_run", q.handle, self.nat.ptr(pool), self.nat.ptr(mine), U, int(reserve),
+                      float(self._mut_max_value),
                       self.nat.ptr(aligned), self.nat.ptr(heads), self.nat.ptr(steps), ctypes.byref(fw),
                       self.nat.current_stream_ptr())
         st = (ctypes.c_int64 * 4)()

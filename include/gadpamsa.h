@@ -233,7 +233,8 @@ int gad_mutate_stats(const gad_qnet *q, int64_t *out4);
  *  gad_windows_rep     d_rep[m] = smallest index of a window byte-identical to window m. Scratch: d_table int32
  *                      [table_slots] (a power of two >= 2 M), d_tmp int32 [M]
  *  gad_episodes_run    greedy episodes (GA.py:353-366; env.py:231-259) of windows d_list[0..U) (NULL: the first
- *                      U). d_aligned uint8 [U][rows][rows*cols], d_heads uint8 [U][rows], d_steps int32 [U].
+ *                      U; scratch is kept for `reserve` >= U episodes so that later calls do not re-allocate).
+ *                      d_aligned uint8 [U][rows][rows*cols], d_heads uint8 [U][rows], d_steps int32 [U].
  *                      Synchronises; gad_mutate_stats reports it like a gad_mutate of U distinct windows
  *  gad_splice_results  Environment.padding + splice (env.py:338-351, GA.py:369-373): individual m takes entry
  *                      d_slot[m] of the result arrays; d_windows = the local windows of gad_mutate_windows */
@@ -241,8 +242,9 @@ int gad_mutate_windows(const gad_qnet *q, const uint8_t *d_boards, int R, int st
                        const int32_t *d_tile, int64_t M, uint8_t *d_windows, void *stream);
 int gad_windows_rep(const uint8_t *d_windows, int64_t M, int window_bytes, int32_t *d_rep, int32_t *d_table,
                     int64_t table_slots, int32_t *d_tmp, void *stream);
-int gad_episodes_run(gad_qnet *q, const uint8_t *d_windows, const int32_t *d_list, int64_t U, float max_value,
-                     uint8_t *d_aligned, uint8_t *d_heads, int32_t *d_steps, int64_t *h_forwards, void *stream);
+int gad_episodes_run(gad_qnet *q, const uint8_t *d_windows, const int32_t *d_list, int64_t U, int64_t reserve,
+                     float max_value, uint8_t *d_aligned, uint8_t *d_heads, int32_t *d_steps, int64_t *h_forwards,
+                     void *stream);
 int gad_splice_results(const gad_qnet *q, uint8_t *d_boards, int32_t *d_rowlen, int R, int stride,
                        const int32_t *d_idx, const int32_t *d_tile, int64_t M, const uint8_t *d_windows,
                        const int32_t *d_slot, const uint8_t *d_aligned, const uint8_t *d_heads,
