@@ -8,43 +8,33 @@
 
 namespace {
 
-// (SP, EM) of tile rows [fr, fr+rw) x columns [fc, fc+cw), computed by one warp
+// (SP, EM) of tile rows [fr, fr+rw) x columns [fc, fc+cw), computed by ONE lane: a tile of a trained window is
+// a few words wide (30 columns = 8 or 9 words), so a lane per tile keeps all 32 lanes busy on boards with many
+// tiles (c4: 42, c5: 735) and needs no cross-lane reduction per tile.
 __device__ __forceinline__ void tile_score(const uint8_t *board, int stride, int fr, int rw, int fc, int cw,
                                            int match, int mismatch, int gap, long long &sp, int &em)
 {
-    const int lane = threadIdx.x & 31;
     BoardSums bs;
     boardsums_clear(bs);
     const int tc = fc + cw;
     const int j0 = fc >> 2, j1 = (tc + 3) >> 2;
     const uint32_t *base = reinterpret_cast<const uint32_t *>(board + (size_t)fr * stride);
     const int wstride = stride >> 2;
-    for (int j = j0 + lane; j < j1; j += 32) {
-        uint32_t valid = 0u;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int c = 4 * j + b;
-            if (c >= fc && c < tc) valid |= 0x80u << (8 * b);
-        }
+    for (int j = j0; j < j1; ++j) {
+        uint32_t valid = GAD_MSB4;
+        if (4 * j < fc) valid &= GAD_MSB4 << (8 * (fc - 4 * j));                 // first word: columns before the tile
+        if (4 * j + 4 > tc) valid &= GAD_MSB4 >> (8 * (4 * j + 4 - tc));         // last word: columns after it
         ColCounts cc;
         colcounts_clear(cc);
         const uint32_t first = base[j];
         for (int r = 0; r < rw; ++r) colcounts_add(cc, base[(size_t)r * wstride + j], first);
         boardsums_fold(bs, cc, valid, true);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bs.q2 += __shfl_xor_sync(0xFFFFFFFFu, bs.q2, o);
-        bs.s1 += __shfl_xor_sync(0xFFFFFFFFu, bs.s1, o);
-        bs.s2 += __shfl_xor_sync(0xFFFFFFFFu, bs.s2, o);
-        bs.kept += __shfl_xor_sync(0xFFFFFFFFu, bs.kept, o);
-        bs.exact += __shfl_xor_sync(0xFFFFFFFFu, bs.exact, o);
-    }
     sp = sum_of_pairs_closed_form(bs, rw, match, mismatch, gap);
     em = (int)bs.exact;
 }
 
-// one warp per mutating individual
+// one warp per mutating individual, one lane per tile (tiles in row-major order: t = lane, lane + 32, ...)
 __global__ void __launch_bounds__(128)
 worst_tile_kernel(const uint8_t *__restrict__ boards, const int32_t *__restrict__ rowlen, int R, int stride,
                   const int32_t *__restrict__ idx, long long M, int rw, int cw, int mode, int match, int mismatch,
@@ -56,7 +46,9 @@ worst_tile_kernel(const uint8_t *__restrict__ boards, const int32_t *__restrict_
     const long long p = idx ? idx[m] : m;
     const uint8_t *board = boards + (size_t)p * R * stride;
     int n = 0x7fffffff;                                       // utils.py:231: shortest row
-    for (int r = 0; r < R; ++r) n = min(n, rowlen[p * R + r]);
+    for (int r = lane; r < R; r += 32) n = min(n, rowlen[p * R + r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n = min(n, __shfl_xor_sync(0xFFFFFFFFu, n, o));
     const int tr = R / rw, tcn = n / cw;
     if (tr == 0 || tcn == 0) {                                // no tile fits: the reference's min() raises
         if (lane == 0) {
@@ -65,10 +57,11 @@ worst_tile_kernel(const uint8_t *__restrict__ boards, const int32_t *__restrict_
         }
         return;
     }
+    const int ntiles = tr * tcn;
     long long lo_s = 0x7fffffffffffffffll, hi_s = -lo_s - 1;
     int lo_e = 0x7fffffff, hi_e = -1;
-    if (mode == GAD_MODE_MO) {                                // utils.py:296-301 needs min/max first
-        for (int t = 0; t < tr * tcn; ++t) {
+    if (mode == GAD_MODE_MO) {                                // utils.py:296-301 needs min/max over all tiles first
+        for (int t = lane; t < ntiles; t += 32) {
             long long s;
             int e;
             tile_score(board, stride, (t / tcn) * rw, rw, (t % tcn) * cw, cw, match, mismatch, gap, s, e);
@@ -77,12 +70,19 @@ worst_tile_kernel(const uint8_t *__restrict__ boards, const int32_t *__restrict_
             lo_e = min(lo_e, e);
             hi_e = max(hi_e, e);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo_s = min(lo_s, __shfl_xor_sync(0xFFFFFFFFu, lo_s, o));
+            hi_s = max(hi_s, __shfl_xor_sync(0xFFFFFFFFu, hi_s, o));
+            lo_e = min(lo_e, __shfl_xor_sync(0xFFFFFFFFu, lo_e, o));
+            hi_e = max(hi_e, __shfl_xor_sync(0xFFFFFFFFu, hi_e, o));
+        }
     }
     // cs = exact / cw is monotone in exact for a fixed cw, so min/max over cs are those over exact
     const double lo_c = __ddiv_rn((double)lo_e, (double)cw), hi_c = __ddiv_rn((double)hi_e, (double)cw);
     double best = 0.0;
-    int best_t = -1;
-    for (int t = 0; t < tr * tcn; ++t) {
+    int best_t = 0x7fffffff;
+    for (int t = lane; t < ntiles; t += 32) {
         long long s;
         int e;
         tile_score(board, stride, (t / tcn) * rw, rw, (t % tcn) * cw, cw, match, mismatch, gap, s, e);
@@ -97,9 +97,19 @@ worst_tile_kernel(const uint8_t *__restrict__ boards, const int32_t *__restrict_
             const double ncs = hi_c > lo_c ? __ddiv_rn(__dsub_rn(c, lo_c), __dsub_rn(hi_c, lo_c)) : 0.5;
             k = __dadd_rn(nsp, ncs);
         }
-        if (best_t < 0 || k < best) {                         // first minimum wins (python min)
+        if (best_t == 0x7fffffff || k < best) {               // first minimum of this lane's tiles (ascending t)
             best = k;
             best_t = t;
+        }
+    }
+    // first minimum over all tiles (python min): smallest key, ties to the smallest tile number
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        const int ot = __shfl_xor_sync(0xFFFFFFFFu, best_t, o);
+        if (ot != 0x7fffffff && (best_t == 0x7fffffff || ok < best || (ok == best && ot < best_t))) {
+            best = ok;
+            best_t = ot;
         }
     }
     if (lane == 0) {

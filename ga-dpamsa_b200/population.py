@@ -194,7 +194,7 @@ class DevicePopulation:
         need = round_up(need, 16)
         if need <= self.stride:
             return
-        need = max(need, round_up(self.stride + self.stride // 4, 16))      # grow geometrically: re-laying out a
+        need = max(need, round_up(self.stride + self.stride // 2, 16))      # grow geometrically: re-laying out a
         old = self.stride                                                    # sharded population costs a rendezvous
         self.stride = need
         for name in ("cur", "alt"):

@@ -30,6 +30,27 @@ import config
 nucleotides_map = {'A': 1, 'T': 2, 'C': 3, 'G': 4, 'a': 1, 't': 2, 'c': 3, 'g': 4, '-': 5}
 
 
+class _Ticker:
+    """Per-step wall times of a phase (GAD_SHARDED_TIMING=1): synchronises after every step, so only for diagnosis."""
+
+    def __init__(self, sink):
+        import time
+        self.sink, self.time = sink, time
+        torch.cuda.synchronize()
+        self.t = time.perf_counter()
+
+    def __call__(self, name):
+        torch.cuda.synchronize()
+        now = self.time.perf_counter()
+        self.sink[name] = self.sink.get(name, 0.0) + (now - self.t)
+        self.t = now
+
+
+class _NoTicker:
+    def __call__(self, name):
+        pass
+
+
 def shard_bounds(total: int, world: int):
     """Contiguous shares of `total` items: the first total % world ranks get one more."""
     base, extra = divmod(total, world)
@@ -56,6 +77,7 @@ class ShardedGA:
         self.hof_board = None        # replicated on every rank: (boards uint8 [R, w] tensor)
         self.hof_score = None        # (logical index, sp, em, al)
         self.comm_bytes = 0          # bytes this rank received through collectives
+        self.timing = {} if os.environ.get("GAD_SHARDED_TIMING") == "1" else None      # per-step wall times (diagnosis)
         self._counts_cache = None    # individuals per rank (device backends: kept on the host between phases)
         self._owner_pattern = None
         self._hof_dev = None         # device backends: hall-of-fame record / board stay on the device
@@ -336,14 +358,18 @@ class ShardedGA:
         included - and every rank runs the same number of episodes. Results are those of the single-GPU path: an
         episode is a pure function of its window and Q-values do not depend on the batch (gemm_tc.cu)."""
         be, dev, world, rank = self.backend, self.backend.device, self.world, self.rank
+        tick = _Ticker(self.timing) if self.timing is not None else _NoTicker()
         # individuals to mutate per rank, from the replicated ranking (no collective): one host read
         counts = torch.bincount(self.owner[chosen], minlength=world).cpu().tolist()
+        tick("counts")
         m_loc = int(local.numel())
         assert m_loc == counts[rank]
         if sum(counts) == 0:
             return
         windows, tile = be.mutation_windows(local, model_path, self.mode, width)          # uint8 [m_loc, rows*cols]
+        tick("tiles+windows")
         pool = self._all_gather_padded(windows, counts)                                    # [M, rows*cols], rank-major
+        tick("gather windows")
         M = int(pool.shape[0])
         rep = be.windows_rep(pool)                                                         # int32 [M]
         flags = rep == torch.arange(M, dtype=torch.int32, device=dev)
@@ -351,7 +377,9 @@ class ShardedGA:
         n_unique = int(flags.sum().item())
         per_rank = -(-n_unique // world)
         mine = (flags & (uidx % world == rank)).nonzero().flatten().to(torch.int32)        # ascending: j-th = ordinal rank + j*world
+        tick("distinct")
         aligned, heads, steps = be.run_episodes(pool, mine, per_rank, reserve=-(-M // world))
+        tick("episodes")
         if world > 1:
             a_all = torch.empty((world * per_rank,) + tuple(aligned.shape[1:]), dtype=torch.uint8, device=dev)
             h_all = torch.empty((world * per_rank,) + tuple(heads.shape[1:]), dtype=torch.uint8, device=dev)
@@ -362,10 +390,12 @@ class ShardedGA:
             self.comm_bytes += (aligned.numel() + heads.numel() + 4 * steps.numel()) * (world - 1)
         else:
             a_all, h_all, s_all = aligned, heads, steps
+        tick("gather results")
         off = sum(counts[:rank])
         u = uidx[rep[off:off + m_loc].to(torch.int64)]
         slot = ((u % world) * per_rank + u // world).to(torch.int32)
         be.splice_results(local, tile, windows, slot, a_all, h_all, s_all, width)
+        tick("splice")
 
     # ------------------------------------------------------------------ a19
     def run(self, model_path, debug_mode=False):

@@ -1,19 +1,21 @@
-"""Host-side profile of the sharded generation loop (cProfile on rank 0): where the wall time of the non-kernel
-part goes. torchrun --nproc-per-node N scripts/profile_sharded.py"""
-import cProfile
+"""Per-step wall times of the sharded mutation phase (GAD_SHARDED_TIMING=1; every step synchronised).
+torchrun --nproc-per-node N scripts/profile_sharded.py [c3|c4|c5]"""
+import json
 import os
-import pstats
 import random
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "ga-dpamsa_b200"), ROOT]
 os.environ.setdefault("GADPAMSA_PROJECT_ROOT", "/tmp/gadpamsa_project_root")
+os.environ["GAD_SHARDED_TIMING"] = "1"
 import torch
 import torch.distributed as dist
 
 
 def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -23,32 +25,35 @@ def main():
     import config
     import sharded
     config.DEVICE = "cuda:%d" % local
-    rows, cols, P, mode, _ = bench.WORKLOADS["c3"]
-    config.POPULATION_SIZE, config.AGENT_WINDOW_ROW, config.AGENT_WINDOW_COLUMN = P * world, 6, 30
-    model, _ = bench.synth_weight_file(6, 30, tag="_p%d" % rank)
+    bench.WORKLOADS["c5"] = (64, 1000, 131072 * world, "mo", "c5 shape, 131072 individuals per rank")
+    bench.AGENTS["c5"] = (3, 30)
+    rows, cols, P, mode, _ = bench.WORKLOADS[wl]
+    if wl == "c3":
+        P *= world
+    rw, cw = bench.AGENTS[wl]
+    config.POPULATION_SIZE, config.AGENT_WINDOW_ROW, config.AGENT_WINDOW_COLUMN = P, rw, cw
+    model, _ = bench.synth_weight_file(rw, cw, tag="_p%d" % rank)
     random.seed(20251019)
     g = sharded.ShardedGA(bench.seq_strings(rows, cols, 20251019), mode, sharded.DeviceBackend(config.DEVICE))
     g.generate_population()
     g.calculate_fitness_score()
-    def gen():
-        g.mutation(model)
-        g.calculate_fitness_score()
-        g.selection()
-        g.horizontal_crossover()
-    for _ in range(3):
-        gen()
-    torch.cuda.synchronize()
-    dist.barrier()
-    pr = cProfile.Profile()
-    pr.enable()
-    for _ in range(4):
-        gen()
-    torch.cuda.synchronize()
-    pr.disable()
-    if rank == 0:
-        st = pstats.Stats(pr)
-        st.sort_stats("cumulative").print_stats(45)
-        st.sort_stats("tottime").print_stats(25)
+    phases = {}
+    def timed(name, fn):
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+        phases[name] = phases.get(name, 0.0) + time.perf_counter() - t0
+    for it in range(5):
+        if it == 2:
+            phases.clear(); g.timing.clear()
+        timed("mutation", lambda: g.mutation(model))
+        timed("fitness", g.calculate_fitness_score)
+        timed("selection", g.selection)
+        timed("crossover", g.horizontal_crossover)
+    for r in range(world):
+        dist.barrier()
+        if rank == r:
+            print(json.dumps({"workload": wl, "world": world, "rank": rank,
+                              "phases_ms": {k: round(1e3 * v / 3, 3) for k, v in phases.items()},
+                              "mutation_steps_ms": {k: round(1e3 * v / 3, 3) for k, v in g.timing.items()}}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
