@@ -28,6 +28,7 @@ WHAT = [
     ("DPAMSA", (".py",)),
     ("datasets/inference_dataset", (".py",)),
     ("datasets/fasta_files/encode_project_dataset_4x101bp", None),      # what run_benchmarks.py lists (run_benchmarks.py:50-51)
+    ("datasets/training_dataset", (".py",)),                             # DPAMSA training sets (scripts/train_and_evaluate.py)
 ]
 
 
