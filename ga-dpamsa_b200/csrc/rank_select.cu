@@ -11,6 +11,7 @@
 #include "gad_common.cuh"
 
 #include <cub/cub.cuh>
+#include <stdlib.h>
 
 namespace {
 
@@ -36,6 +37,8 @@ struct Workspace {
     int *gstart, *flags, *scan;
     double *part_key;     // per-block argmax partials
     int *part_idx;
+    int *part_lo, *part_hi;       // per-block score ranges of the one-kernel hall-of-fame decision
+    u64 *part_clo, *part_chi;
     void *cub_tmp;
     size_t cub_bytes;
 };
@@ -76,6 +79,10 @@ size_t carve(Workspace &w, void *base, long long n, size_t cub_bytes)
     w.scan = (int *)take(sizeof(int) * n);
     w.part_key = (double *)take(sizeof(double) * kArgBlocks);
     w.part_idx = (int *)take(sizeof(int) * kArgBlocks);
+    w.part_lo = (int *)take(sizeof(int) * kArgBlocks);
+    w.part_hi = (int *)take(sizeof(int) * kArgBlocks);
+    w.part_clo = (u64 *)take(sizeof(u64) * kArgBlocks);
+    w.part_chi = (u64 *)take(sizeof(u64) * kArgBlocks);
     w.cub_tmp = take(cub_bytes);
     w.cub_bytes = cub_bytes;
     return off;
@@ -157,6 +164,17 @@ __global__ void stats_kernel(const int *__restrict__ sp, const int *__restrict__
 }
 
 // utils.py:332-351: single metric -> the metric; MO -> (sp-min)/(max-min) + (cs-min)/(max-min), 0.5 when flat
+__device__ __forceinline__ double make_key(int mode, int s, int e, int a, long long lo, long long hi, u64 cs_min, u64 cs_max)
+{
+    if (mode == GAD_MODE_SP) return (double)s;
+    if (mode == GAD_MODE_CS) return column_score(e, a);
+    const double clo = __longlong_as_double((long long)cs_min), chi = __longlong_as_double((long long)cs_max);
+    const double nsp = hi > lo ? __ddiv_rn((double)((long long)s - lo), (double)(hi - lo)) : 0.5;
+    const double c = column_score(e, a);
+    const double ncs = chi > clo ? __ddiv_rn(__dsub_rn(c, clo), __dsub_rn(chi, clo)) : 0.5;
+    return __dadd_rn(nsp, ncs);
+}
+
 __global__ void keys_kernel(const int *__restrict__ sp, const int *__restrict__ em, const int *__restrict__ al,
                             const int *__restrict__ hof, long long P, long long n, int mode, const Stats *st,
                             double *__restrict__ key)
@@ -165,20 +183,7 @@ __global__ void keys_kernel(const int *__restrict__ sp, const int *__restrict__ 
     if (i >= n) return;
     int s, e, a;
     load_score(sp, em, al, hof, P, i, s, e, a);
-    double k;
-    if (mode == GAD_MODE_SP) {
-        k = (double)s;
-    } else if (mode == GAD_MODE_CS) {
-        k = column_score(e, a);
-    } else {
-        const long long lo = st->sp_min, hi = st->sp_max;
-        const double clo = __longlong_as_double((long long)st->cs_min), chi = __longlong_as_double((long long)st->cs_max);
-        const double nsp = hi > lo ? __ddiv_rn((double)((long long)s - lo), (double)(hi - lo)) : 0.5;
-        const double c = column_score(e, a);
-        const double ncs = chi > clo ? __ddiv_rn(__dsub_rn(c, clo), __dsub_rn(chi, clo)) : 0.5;
-        k = __dadd_rn(nsp, ncs);
-    }
-    key[i] = k;
+    key[i] = make_key(mode, s, e, a, st->sp_min, st->sp_max, st->cs_min, st->cs_max);
 }
 
 int compute_keys(const int *sp, const int *em, const int *al, const int *hof, long long P, int mode, double *key,
@@ -450,6 +455,340 @@ __global__ void hof_commit_kernel(const uint8_t *__restrict__ boards, const int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GA.update_hall_of_fame (GA.py:96-136) as ONE launch: score ranges ('mo'), keys, first maximum, and the
+// winner's board + record - what stats_init / stats / keys / argbest / hof_commit do in five.
+// The grid is at most one block per SM, so all blocks are resident and may meet at a counter: phase A leaves
+// every block's score range in the workspace, the barrier makes them visible, every block folds all of them
+// (a few hundred values); phase B forms each key with the arithmetic of keys_kernel and keeps the best per
+// block; the last block to finish settles the winner and commits. sync[0] = barrier counter, sync[1] = ticket:
+// zero before the first launch, left zero by every launch.
+//
+// Sharded populations (gad_pass_decide): sp/em/al are the rows of this rank's score table - filled by every
+// rank's gad_pass_scatter over NVLink - and the kernel first waits for the arrival flag of every rank. Every
+// rank takes the same decision; the rank that owns the winner stores its board into every rank's hall of fame
+// and raises their `board` flag, the others wait for that flag. No collective call, nothing read by the host.
+// ---------------------------------------------------------------------------------------------
+struct PassPeer {                    // all null / zero for a population that lives on one GPU
+    const long long *peer_base;      // device array [world]: every rank's pass block (symmetric memory)
+    long long flags_off, table_off, hof_off;   // byte offsets inside a pass block
+    long long cap1;                  // table row length (int32 [2][5][cap1])
+    int rank, world;
+    int hof_pitch;                   // row pitch of the hall-of-fame board inside the pass block
+};
+
+// words of the flags area of a pass block (int32 [64])
+enum { PF_ARRIVE = 0, PF_BOARD = 16, PF_SEQ = 32, PF_SCATTER_TICKET = 33, PF_DECIDE_SYNC = 34, PF_ERROR = 36 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// wait until *p >= want (a peer's store); a peer that never arrives must not hang the GPU: trap after 20 s
+__device__ __forceinline__ void wait_flag(const int *p, int want, int *err)
+{
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(p) - want < 0) {
+        if ((++spins & 1023u) == 0u && global_ns() - t0 > 20000000000ull) {
+            *err = 1;
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+// ---- pieces shared by the two shapes of the decision kernel ------------------------------------------------
+struct Range {
+    int lo, hi;
+    u64 clo, chi;        // bit patterns of non-negative doubles (order-preserving)
+};
+
+__device__ __forceinline__ void range_clear(Range &g)
+{
+    g.lo = 0x7fffffff;
+    g.hi = (int)0x80000000;
+    g.clo = ~0ull;
+    g.chi = 0ull;
+}
+
+__device__ __forceinline__ void range_merge(Range &g, int lo, int hi, u64 clo, u64 chi)
+{
+    g.lo = min(g.lo, lo);
+    g.hi = max(g.hi, hi);
+    g.clo = clo < g.clo ? clo : g.clo;
+    g.chi = chi > g.chi ? chi : g.chi;
+}
+
+__device__ __forceinline__ void range_fold_warp(Range &g)
+{
+    for (int o = 16; o > 0; o >>= 1)
+        range_merge(g, __shfl_xor_sync(0xFFFFFFFFu, g.lo, o), __shfl_xor_sync(0xFFFFFFFFu, g.hi, o),
+                    __shfl_xor_sync(0xFFFFFFFFu, g.clo, o), __shfl_xor_sync(0xFFFFFFFFu, g.chi, o));
+}
+
+struct DecideShared {                // up to 32 warps per block
+    Range range[32];
+    double key[32];
+    int idx[32];
+    int winner;
+    bool last;
+};
+
+// score range of the block's elements; result in every thread
+__device__ __forceinline__ Range range_fold_block(Range g, DecideShared &sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    range_fold_warp(g);
+    if (lane == 0) sh.range[wid] = g;
+    __syncthreads();
+    range_clear(g);
+    if (lane < nw) g = sh.range[lane];
+    range_fold_warp(g);
+    __syncthreads();
+    return g;
+}
+
+__device__ __forceinline__ Range range_scan(const int *sp, const int *em, const int *al, const int *hofp, long long P,
+                                            long long n, long long first, long long step)
+{
+    Range g;
+    range_clear(g);
+    for (long long i = first; i < n; i += step) {
+        int s, e, a;
+        load_score(sp, em, al, hofp, P, i, s, e, a);
+        const u64 c = (u64)__double_as_longlong(column_score(e, a));
+        range_merge(g, s, s, c, c);
+    }
+    return g;
+}
+
+__device__ __forceinline__ void best_merge(double &bk, int &bi, double k, int i)
+{
+    if (i != 0x7fffffff && (bi == 0x7fffffff || better(k, i, bk, bi))) {
+        bk = k;
+        bi = i;
+    }
+}
+
+__device__ __forceinline__ void best_fold_warp(double &bk, int &bi)
+{
+    for (int o = 16; o > 0; o >>= 1) best_merge(bk, bi, __shfl_xor_sync(0xFFFFFFFFu, bk, o), __shfl_xor_sync(0xFFFFFFFFu, bi, o));
+}
+
+// best of the block; result in warp 0
+__device__ __forceinline__ void best_fold_block(double &bk, int &bi, DecideShared &sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    best_fold_warp(bk, bi);
+    if (lane == 0) {
+        sh.key[wid] = bk;
+        sh.idx[wid] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bk = lane < nw ? sh.key[lane] : 0.0;
+        bi = lane < nw ? sh.idx[lane] : 0x7fffffff;
+        best_fold_warp(bk, bi);
+    }
+}
+
+__device__ __forceinline__ void best_scan(const int *sp, const int *em, const int *al, const int *hofp, long long P,
+                                          long long n, long long first, long long step, int mode, const Range &g,
+                                          double &bk, int &bi)
+{
+    bk = 0.0;
+    bi = 0x7fffffff;
+    for (long long i = first; i < n; i += step) {
+        int s, e, a;
+        load_score(sp, em, al, hofp, P, i, s, e, a);
+        best_merge(bk, bi, make_key(mode, s, e, a, g.lo, g.hi, g.clo, g.chi), (int)i);
+    }
+}
+
+struct DecideView {                  // where this launch finds its scores, flags and sync words
+    const int *sp, *em, *al, *owner, *slot;
+    int *flags, *sync;
+    int seq;
+};
+
+// Sharded: wait for every rank's arrival flag of this pass and take the pass's table. Whole block.
+__device__ __forceinline__ void decide_enter(DecideView &v, const PassPeer &pp)
+{
+    v.owner = v.slot = nullptr;
+    v.flags = nullptr;
+    v.seq = 0;
+    if (!pp.peer_base) return;
+    char *mine = reinterpret_cast<char *>(pp.peer_base[pp.rank]);
+    v.flags = reinterpret_cast<int *>(mine + pp.flags_off);
+    v.sync = v.flags + PF_DECIDE_SYNC;
+    v.seq = *reinterpret_cast<volatile int *>(v.flags + PF_SEQ);              // set by this pass's scatter kernel
+    if ((int)threadIdx.x < pp.world) wait_flag(v.flags + PF_ARRIVE + threadIdx.x, v.seq, v.flags + PF_ERROR);
+    __syncthreads();
+    const int *table = reinterpret_cast<const int *>(mine + pp.table_off) + (size_t)(v.seq & 1) * 5 * pp.cap1;
+    v.sp = table;
+    v.em = table + pp.cap1;
+    v.al = table + 2 * pp.cap1;
+    v.owner = table + 3 * pp.cap1;
+    v.slot = table + 4 * pp.cap1;
+}
+
+// GA.py:110-136 by one whole block. Winner == P: the record keeps its place under the fresh index len(scores).
+__device__ __forceinline__ void decide_commit(int win, long long P, const DecideView &v, const uint8_t *boards, int R,
+                                              int stride, uint8_t *hof_board, int *hof, const PassPeer &pp)
+{
+    const int tid = threadIdx.x;
+    if (win >= P) {
+        if (tid == 0) hof[1] = (int)P;
+        return;
+    }
+    const int width = v.al[win];
+    const int n16 = min(stride >> 4, (width + 15) >> 4);
+    if (!pp.peer_base) {
+        for (int u = tid; u < R * n16; u += blockDim.x) {
+            const int r = u / n16, j = u - r * n16;
+            reinterpret_cast<uint4 *>(hof_board + (size_t)r * stride)[j] =
+                reinterpret_cast<const uint4 *>(boards + ((size_t)win * R + r) * stride)[j];
+        }
+    } else if (v.owner[win] == pp.rank) {
+        const size_t src = (size_t)v.slot[win] * R;
+        for (int q = 0; q < pp.world; ++q) {
+            uint8_t *dst = reinterpret_cast<uint8_t *>(pp.peer_base[q]) + pp.hof_off;
+            for (int u = tid; u < R * n16; u += blockDim.x) {
+                const int r = u / n16, j = u - r * n16;
+                reinterpret_cast<uint4 *>(dst + (size_t)r * pp.hof_pitch)[j] =
+                    reinterpret_cast<const uint4 *>(boards + (src + r) * stride)[j];
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < pp.world)
+            st_release_sys(reinterpret_cast<int *>(reinterpret_cast<char *>(pp.peer_base[tid]) + pp.flags_off) + PF_BOARD, v.seq);
+    } else if (tid == 0) {
+        wait_flag(v.flags + PF_BOARD, v.seq, v.flags + PF_ERROR);          // the owner's copy of the board has landed here
+    }
+    if (tid == 0) {
+        hof[0] = 1;
+        hof[1] = win;
+        hof[2] = v.sp[win];
+        hof[3] = v.em[win];
+        hof[4] = width;
+    }
+}
+
+// ---- the kernel: any population size; one block per SM at most, blocks meet at a counter ---------------------------
+__global__ void __launch_bounds__(256)
+hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, const int *__restrict__ al_in,
+                  long long P, int mode, int hof_valid, const uint8_t *__restrict__ boards, int R, int stride,
+                  Workspace w, int *sync, uint8_t *__restrict__ hof_board, int *hof, PassPeer pp)
+{
+    __shared__ DecideShared sh;
+    const int tid = threadIdx.x;
+    DecideView v;
+    v.sp = sp_in, v.em = em_in, v.al = al_in, v.sync = sync;
+    decide_enter(v, pp);
+    const int *hofp = hof_valid ? hof : nullptr;
+    const long long n = P + (hof_valid ? 1 : 0);
+    const long long first = (long long)blockIdx.x * blockDim.x + tid, step = (long long)gridDim.x * blockDim.x;
+
+    // ---- phase A ('mo' only): score ranges over the population and the record
+    Range g;
+    range_clear(g);
+    if (mode == GAD_MODE_MO) {
+        g = range_fold_block(range_scan(v.sp, v.em, v.al, hofp, P, n, first, step), sh);
+        if (gridDim.x > 1) {
+            if (tid == 0) {
+                w.part_lo[blockIdx.x] = g.lo;
+                w.part_hi[blockIdx.x] = g.hi;
+                w.part_clo[blockIdx.x] = g.clo;
+                w.part_chi[blockIdx.x] = g.chi;
+                __threadfence();
+                atomicAdd(&v.sync[0], 1);
+                while (*reinterpret_cast<volatile int *>(&v.sync[0]) < (int)gridDim.x) {}
+                __threadfence();
+            }
+            __syncthreads();
+            range_clear(g);
+            for (int b = tid; b < (int)gridDim.x; b += blockDim.x)
+                range_merge(g, __ldcg(&w.part_lo[b]), __ldcg(&w.part_hi[b]), __ldcg(&w.part_clo[b]), __ldcg(&w.part_chi[b]));
+            g = range_fold_block(g, sh);
+        }
+    }
+
+    // ---- phase B: keys and the first maximum
+    double bk;
+    int bi;
+    best_scan(v.sp, v.em, v.al, hofp, P, n, first, step, mode, g, bk, bi);
+    best_fold_block(bk, bi, sh);
+    if (tid == 0) {
+        sh.last = true;
+        if (gridDim.x > 1) {
+            w.part_key[blockIdx.x] = bk;
+            w.part_idx[blockIdx.x] = bi;
+            __threadfence();
+            sh.last = atomicAdd(&v.sync[1], 1) == (int)gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (!sh.last) return;
+    if (gridDim.x > 1) {
+        __threadfence();
+        bk = 0.0;
+        bi = 0x7fffffff;
+        for (int b = tid; b < (int)gridDim.x; b += blockDim.x) best_merge(bk, bi, __ldcg(&w.part_key[b]), __ldcg(&w.part_idx[b]));
+        __syncthreads();
+        best_fold_block(bk, bi, sh);
+    }
+    if (tid == 0) {
+        sh.winner = bi;
+        v.sync[0] = 0;
+        v.sync[1] = 0;
+        w.stats->winner = bi;
+    }
+    __syncthreads();
+    decide_commit(sh.winner, P, v, boards, R, stride, hof_board, hof, pp);
+}
+
+inline unsigned decide_blocks(long long n)
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1)
+            v = GAD_NUM_SMS;
+        sms = v;
+    }
+    long long b = (n + 511) / 512;                   // two elements per thread before another block pays off
+    if (b > sms) b = sms;
+    if (b > kArgBlocks) b = kArgBlocks;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+int launch_decide(const int *sp, const int *em, const int *al, long long P, int mode, int hof_valid, const uint8_t *boards,
+                  int R, int stride, const Workspace &w, int *sync, uint8_t *hof_board, int *hof, const PassPeer &pp,
+                  cudaStream_t st)
+{
+    const long long n = P + (hof_valid ? 1 : 0);
+    hof_decide_kernel<<<decide_blocks(n), 256, 0, st>>>(sp, em, al, P, mode, hof_valid, boards, R, stride, w, sync, hof_board,
+                                                        hof, pp);
+    return GAD_OK;
+}
+
 inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 __global__ void copy_winner_kernel(const Stats *st, int32_t *out) { *out = st->winner; }
@@ -604,8 +943,16 @@ extern "C" int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, cons
     int rc = open_workspace(w, d_ws, ws_bytes, P + 1, "gad_hof_update");
     if (rc) return rc;
     cudaStream_t st = gad_stream(stream);
-    double *key = reinterpret_cast<double *>(w.k0);
     const long long n = P + (hof_valid ? 1 : 0);
+    static const bool unfused = getenv("GAD_HOF_UNFUSED") && atoi(getenv("GAD_HOF_UNFUSED")) != 0;
+    if (!unfused) {                                  // one launch; d_hof[5..6] = its barrier counter and ticket
+        if ((rc = launch_decide(d_sp, d_em, d_al, P, mode, hof_valid ? 1 : 0, d_boards, R, stride, w, d_hof + 5, d_hof_board,
+                                d_hof, PassPeer{}, st)))
+            return rc;
+        GAD_LAUNCH_CHECK();
+        return GAD_OK;
+    }
+    double *key = reinterpret_cast<double *>(w.k0);
     if ((rc = compute_keys(d_sp, d_em, d_al, hof_valid ? d_hof : nullptr, P, mode, key, w, st))) return rc;
     GAD_CUDA(cudaMemsetAsync(&w.stats->ticket, 0, sizeof(unsigned), st));
     unsigned blocks = blocks_for(n, 256 * 4);
@@ -613,6 +960,115 @@ extern "C" int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, cons
     if (blocks < 1) blocks = 1;
     argbest_kernel<<<blocks, 256, 0, st>>>(key, n, w.part_key, w.part_idx, w.stats);
     hof_commit_kernel<<<R, 128, 0, st>>>(d_boards, d_sp, d_em, d_al, P, R, stride, w.stats, d_hof_board, d_hof);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// =============================================================================================
+// The fitness pass of a SHARDED population without a collective call (sharded.py): gad_pass_scatter stores the
+// scores of the local individuals into every rank's score table over NVLink and raises this rank's arrival flag
+// on every rank; gad_pass_decide waits for all flags, takes GA.update_hall_of_fame's decision on the complete
+// table (the same on every rank) and moves the winner's board from its owner into every rank's hall of fame.
+// A pass block (symmetric memory, one per rank, zeroed once): int32 flags[64] | int32 table[2][5][cap1] | board.
+// Tables alternate with the pass number: a rank that runs ahead writes the other table, and cannot start the
+// pass after that before every rank has raised its flag for this one.
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256)
+pass_scatter_kernel(PassPeer pp, const int32_t *__restrict__ sp, const int32_t *__restrict__ em,
+                    const int32_t *__restrict__ al, const long long *__restrict__ gidx, long long n_local)
+{
+    __shared__ bool last;
+    int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(pp.peer_base[pp.rank]) + pp.flags_off);
+    const int seq = *reinterpret_cast<volatile int *>(flags + PF_SEQ) + 1;       // this pass
+    const size_t toff = (size_t)pp.table_off + (size_t)(seq & 1) * 5 * pp.cap1 * sizeof(int32_t);
+    const long long total = n_local * pp.world;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / pp.world;              // consecutive threads: the peers of one individual
+        const int r = (int)(t - i * pp.world);
+        int32_t *table = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(pp.peer_base[r]) + toff);
+        const long long g = gidx[i];
+        table[g] = sp[i];
+        table[pp.cap1 + g] = em[i];
+        table[2 * pp.cap1 + g] = al[i];
+        table[3 * pp.cap1 + g] = pp.rank;
+        table[4 * pp.cap1 + g] = (int32_t)i;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&flags[PF_SCATTER_TICKET], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x < pp.world)
+        st_release_sys(reinterpret_cast<int *>(reinterpret_cast<char *>(pp.peer_base[threadIdx.x]) + pp.flags_off) + PF_ARRIVE + pp.rank, seq);
+    if (threadIdx.x == 0) {
+        flags[PF_SEQ] = seq;
+        flags[PF_SCATTER_TICKET] = 0;
+    }
+}
+
+int check_pass_block(const char *who, const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t hof_off,
+                     int64_t cap1, int rank, int world)
+{
+    GAD_REQUIRE(d_peer_base && cap1 >= 1 && world >= 1 && world <= 16 && rank >= 0 && rank < world, "%s: bad argument", who);
+    GAD_REQUIRE(flags_off >= 0 && flags_off % 16 == 0 && table_off >= 0 && table_off % 16 == 0 && hof_off >= 0 &&
+                hof_off % 16 == 0, "%s: pass-block offsets must be multiples of 16", who);
+    return GAD_OK;
+}
+
+}  // namespace
+
+extern "C" int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t cap1,
+                                const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, const int64_t *d_gidx,
+                                int64_t n_local, int rank, int world, void *stream)
+{
+    int rc = check_pass_block("gad_pass_scatter", d_peer_base, flags_off, table_off, 0, cap1, rank, world);
+    if (rc) return rc;
+    GAD_REQUIRE(n_local >= 0 && (n_local == 0 || (d_sp && d_em && d_al && d_gidx)), "gad_pass_scatter: null pointer");
+    PassPeer pp{};
+    pp.peer_base = reinterpret_cast<const long long *>(d_peer_base);
+    pp.flags_off = flags_off;
+    pp.table_off = table_off;
+    pp.cap1 = cap1;
+    pp.rank = rank;
+    pp.world = world;
+    long long blocks = (n_local * world + 255) / 256;       // a rank without individuals still raises its flag
+    if (blocks < 1) blocks = 1;
+    if (blocks > 4 * GAD_NUM_SMS) blocks = 4 * GAD_NUM_SMS;
+    pass_scatter_kernel<<<(unsigned)blocks, 256, 0, gad_stream(stream)>>>(pp, d_sp, d_em, d_al,
+                                                                          reinterpret_cast<const long long *>(d_gidx), n_local);
+    GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+extern "C" int gad_pass_decide(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t hof_off,
+                               int64_t cap1, int hof_pitch, int64_t n, int mode, int hof_valid, const uint8_t *d_boards,
+                               int R, int stride, int32_t *d_hof, int rank, int world, void *d_ws, size_t ws_bytes,
+                               void *stream)
+{
+    int rc = check_pass_block("gad_pass_decide", d_peer_base, flags_off, table_off, hof_off, cap1, rank, world);
+    if (rc) return rc;
+    GAD_REQUIRE(d_boards && d_hof, "gad_pass_decide: null device pointer");
+    GAD_REQUIRE(mode >= GAD_MODE_SP && mode <= GAD_MODE_MO, "gad_pass_decide: unknown mode %d", mode);
+    GAD_REQUIRE(n >= 1 && n < cap1 && R >= 1 && stride >= 16 && stride % 16 == 0 && hof_pitch >= stride && hof_pitch % 16 == 0,
+                "gad_pass_decide: bad shape");
+    Workspace w;
+    if ((rc = open_workspace(w, d_ws, ws_bytes, n + 1, "gad_pass_decide"))) return rc;
+    PassPeer pp{};
+    pp.peer_base = reinterpret_cast<const long long *>(d_peer_base);
+    pp.flags_off = flags_off;
+    pp.table_off = table_off;
+    pp.hof_off = hof_off;
+    pp.cap1 = cap1;
+    pp.rank = rank;
+    pp.world = world;
+    pp.hof_pitch = hof_pitch;
+    // the kernel finds its table (pass parity), its flags and the sync words inside the pass block
+    if ((rc = launch_decide(nullptr, nullptr, nullptr, n, mode, hof_valid ? 1 : 0, d_boards, R, stride, w, nullptr, nullptr,
+                            d_hof, pp, gad_stream(stream))))
+        return rc;
     GAD_LAUNCH_CHECK();
     return GAD_OK;
 }

@@ -165,8 +165,13 @@ class ShardedGA:
         be = self.backend
         dev = be.device
         sp, em, al = be.fitness()
+        n, n_loc = self.n_global, int(self.gidx.numel())
+        blk = be.pass_block(max(int(config.POPULATION_SIZE), int(self.population_size), n)) \
+            if hasattr(be, "pass_block") else None
+        if blk is not None:
+            return self._fitness_pass_fused(blk, sp, em, al, n, n_loc)
         counts = self._rank_counts()
-        n, n_loc, mx = self.n_global, int(self.gidx.numel()), max(counts)
+        mx = max(counts)
         packed = torch.empty((mx, 4), dtype=torch.int32, device=dev)
         packed[:n_loc, 0] = sp
         packed[:n_loc, 1] = em
@@ -212,6 +217,27 @@ class ShardedGA:
         old = self._hof_dev[:5].clone()
         old[1] = n                                                                         # GA.py:127-132: the record re-enters as index n
         self._hof_dev[:5] = torch.where(changed, new, old)
+        self.hof_board, self.hof_score = None, None                                        # materialised on demand
+
+    def _fitness_pass_fused(self, blk, sp, em, al, n, n_loc):
+        """The pass without a collective call: three launches. (1) the local fitness kernel; (2) gad_pass_scatter -
+        this rank's (sp, em, al, owner, slot) stored straight into EVERY rank's score table over NVLink (symmetric
+        memory), then its arrival flag raised on every rank; (3) gad_pass_decide - waits for all flags, takes
+        GA.update_hall_of_fame's decision on the complete table in one kernel (identically on every rank), and the
+        rank that owns the winner stores its board into every rank's hall of fame while the others wait for it.
+        The tables ARE the logical-index arrays: no packing, no all-gather, no scatter, nothing read by the host.
+        Two tables alternate with the pass number (a rank that runs ahead writes the other one and cannot start
+        the pass after that before every rank has arrived in this one)."""
+        be = self.backend
+        if self._hof_dev is None:
+            self._hof_dev = torch.zeros(8, dtype=torch.int32, device=be.device)            # {valid, index, sp, em, al}
+        table = blk.run_pass(sp, em, al, self.gidx, n_loc, n, self.mode, self._hof_dev, self._hof_valid, self.rank,
+                             self.world)                                                   # int32 [5, cap1]
+        self._hof_valid = True
+        self._hof_board_dev = blk.hof_board
+        self.g_scores = (table[0, :n], table[1, :n], table[2, :n])
+        self.owner = table[3, :n]
+        self.comm_bytes += 20 * n_loc * (self.world - 1)
         self.hof_board, self.hof_score = None, None                                        # materialised on demand
 
     def _hof_from_device(self):
@@ -360,7 +386,7 @@ class ShardedGA:
         be, dev, world, rank = self.backend, self.backend.device, self.world, self.rank
         tick = _Ticker(self.timing) if self.timing is not None else _NoTicker()
         # individuals to mutate per rank, from the replicated ranking (no collective): one host read
-        counts = torch.bincount(self.owner[chosen], minlength=world).cpu().tolist()
+        counts = torch.bincount(self.owner[chosen].to(torch.int64), minlength=world).cpu().tolist()
         tick("counts")
         m_loc = int(local.numel())
         assert m_loc == counts[rank]
@@ -429,6 +455,8 @@ class DeviceBackend:
         self._rank_tmp = None
         self.peer_ready = False
         self._handles = []
+        self._blk = self._blk_hdl = self._blk_peer = self._blk_tables = self.hof_board = None      # the pass block
+        self._blk_cap1 = self._blk_pitch = self._blk_R = self._blk_seq = 0
         want = peer if peer is not None else os.environ.get("GAD_SHARDED_EXCHANGE", "peer") != "allgather"
         self._symm = None
         if want and dist.is_initialized() and dist.get_world_size() > 1:
@@ -547,6 +575,55 @@ class DeviceBackend:
         return self._ranker(n).argbest(scores, n, mode, hof_score)
 
     device_pass = True            # ShardedGA._fitness_pass_device: the whole pass without a host synchronisation
+
+    # -- the pass block (ShardedGA._fitness_pass_fused; layout in include/gadpamsa.h, gad_pass_scatter) ----------
+    FLAGS_BYTES = 256
+
+    def pass_block(self, cap):
+        """This rank's pass block in symmetric memory - int32 flags[64] | int32 tables [2][5][cap + 1] | hall-of-fame
+        board uint8 [R][pitch] - mapped on every rank (collective when it has to be allocated or grown: capacity
+        and stride are the same on every rank, so all ranks arrive here together). None when symmetric memory is
+        not in use (GAD_SHARDED_SCORES=nccl, one rank, no peer access): the NCCL pass follows."""
+        if self._symm is None or os.environ.get("GAD_SHARDED_SCORES", "peer") == "nccl":
+            return None
+        p = self.pop
+        cap1 = int(cap) + 1
+        if self._blk is None or self._blk_cap1 < cap1 or self._blk_pitch < p.stride or self._blk_R != self.R:
+            world = dist.get_world_size()
+            cap1 = max(cap1, self._blk_cap1)
+            pitch = -(-max(2 * p.stride, self._blk_pitch) // 16) * 16
+            table_bytes = -(-(2 * 5 * cap1 * 4) // 256) * 256
+            t = self._symm.empty(self.FLAGS_BYTES + table_bytes + self.R * pitch, dtype=torch.uint8, device=self.device)
+            t.zero_()
+            board = t[self.FLAGS_BYTES + table_bytes:].view(self.R, pitch)
+            board.fill_(5)
+            if self._blk is not None and self._blk_R == self.R:                 # keep the record's board
+                board[:, :self._blk_pitch].copy_(self.hof_board)
+            hdl = self._symm.rendezvous(t, dist.group.WORLD)
+            self._blk, self._blk_hdl, self._blk_cap1, self._blk_pitch, self._blk_R = t, hdl, cap1, pitch, self.R
+            self._blk_table_off = self.FLAGS_BYTES
+            self._blk_hof_off = self.FLAGS_BYTES + table_bytes
+            self._blk_peer = torch.tensor([int(b) for b in hdl.buffer_ptrs[:world]], dtype=torch.int64, device=self.device)
+            self._blk_tables = t[self.FLAGS_BYTES:self.FLAGS_BYTES + 2 * 5 * cap1 * 4].view(torch.int32).view(2, 5, cap1)
+            self.hof_board = board
+            self._blk_seq = 0                                                   # the device counts passes the same way
+            torch.cuda.synchronize(self.device)
+            hdl.barrier(channel=0)                                              # every block is zeroed before anyone stores
+        return self
+
+    def run_pass(self, sp, em, al, gidx, n_loc, n, mode, hof_rec, hof_valid, rank, world):
+        from population import MODE_ID
+        nat, p = self.nat, self.pop
+        st = nat.current_stream_ptr()
+        gidx = gidx.contiguous()
+        nat.call("gad_pass_scatter", nat.ptr(self._blk_peer), 0, self._blk_table_off, self._blk_cap1, nat.ptr(sp),
+                 nat.ptr(em), nat.ptr(al), nat.ptr(gidx), n_loc, rank, world, st)
+        rk = self._ranker(n)
+        nat.call("gad_pass_decide", nat.ptr(self._blk_peer), 0, self._blk_table_off, self._blk_hof_off, self._blk_cap1,
+                 self._blk_pitch, n, MODE_ID[mode], int(bool(hof_valid)), nat.ptr(p.cur.boards), self.R, p.stride,
+                 nat.ptr(hof_rec), rank, world, nat.ptr(rk.ws), rk.ws.numel(), st)
+        self._blk_seq += 1
+        return self._blk_tables[self._blk_seq & 1]
 
     def argbest_device(self, scores, n, mode, hof_dev):
         return self._ranker(n).argbest_device(scores, n, mode, hof_dev)

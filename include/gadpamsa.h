@@ -126,9 +126,11 @@ int gad_compact(const uint8_t *d_src_boards, const int32_t *d_src_rowlen, const 
                 int64_t P, int R, int stride, uint8_t *d_dst_boards, int32_t *d_dst_rowlen, int32_t *d_dst_sp,
                 int32_t *d_dst_em, int32_t *d_dst_al, void *stream);
 
-/* GA.update_hall_of_fame (GA.py:110-136) without the population deep copy. d_hof is int32[8]:
- * {valid, index, sp, em, al, 0, 0, 0}; d_hof_board is uint8[R][stride]. hof_valid = 0 on the first
- * call (GA.py:110-115). On ties a population member replaces the hall of fame (lowest index). */
+/* GA.update_hall_of_fame (GA.py:110-136) without the population deep copy, one launch. d_hof is int32[8]:
+ * {valid, index, sp, em, al, 0, 0, 0} - words 5..7 must be zero before the first call and belong to the library
+ * (grid barrier and ticket of the decision kernel; zero again after every call); d_hof_board is uint8[R][stride].
+ * hof_valid = 0 on the first call (GA.py:110-115). On ties a population member replaces the hall of fame
+ * (lowest index). */
 int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al,
                    int64_t P, int R, int stride, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
                    void *d_ws, size_t ws_bytes, void *stream);
@@ -160,6 +162,24 @@ int gad_crossover_from(const uint8_t *d_src_boards, const int32_t *d_src_rowlen,
 int gad_crossover_peer(const uint8_t *const *d_peer_boards, const int32_t *const *d_peer_rowlen, int64_t peer_slots,
                        uint8_t *d_dst_boards, int32_t *d_dst_rowlen, int64_t dst_first, const int32_t *d_plan,
                        int64_t n_children, int R, int stride, int kind, void *stream);
+
+/* The fitness pass of a SHARDED population without a collective call (sharded.py; replaces the score all-gather +
+ * hall-of-fame broadcast around GA.calculate_fitness_score / GA.update_hall_of_fame, GA.py:96-181).
+ * Every rank owns a PASS BLOCK in symmetric memory, zeroed once: int32 flags[64] at flags_off, the score tables
+ * int32 [2][5][cap1] = {sp, em, al, owner rank, slot on the owner} indexed by LOGICAL index at table_off, and the
+ * hall-of-fame board uint8 [R][hof_pitch] at hof_off. d_peer_base = device array of `world` int64: the address of
+ * every rank's pass block as mapped into this process.
+ * gad_pass_scatter: stores the scores of the n_local local individuals (logical indices d_gidx) into EVERY rank's
+ * table of this pass over NVLink, then raises this rank's arrival flag on every rank.
+ * gad_pass_decide: waits for all arrival flags, decides like gad_hof_update on the n gathered scores (identically
+ * on every rank), writes the record d_hof; the rank that owns the winner stores its board into every rank's pass
+ * block, the others wait for it. Nothing is read back by the host; a flag that does not arrive within 20 s traps. */
+int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t cap1, const int32_t *d_sp,
+                     const int32_t *d_em, const int32_t *d_al, const int64_t *d_gidx, int64_t n_local, int rank,
+                     int world, void *stream);
+int gad_pass_decide(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t hof_off, int64_t cap1,
+                    int hof_pitch, int64_t n, int mode, int hof_valid, const uint8_t *d_boards, int R, int stride,
+                    int32_t *d_hof, int rank, int world, void *d_ws, size_t ws_bytes, void *stream);
 
 /* CPython-compatible MT19937 replay (random.getstate()[1] = 624 words + position, in/out):
  * the (parent1, parent2, cut) triples of GA.py:281-293 for n_children children. h_widths (one

@@ -51,8 +51,8 @@ def evaluate(dataset, mode, model, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--episodes", type=int, default=1500)
-    ap.add_argument("--train-set", type=int, default=0)
-    ap.add_argument("--eval", default="dataset1_6x30bp")
+    ap.add_argument("--train-sets", type=int, default=1, help="sequence sets trained on in turn, weights carried over")
+    ap.add_argument("--eval", nargs="+", default=["synthetic_dataset_3x30bp", "synthetic_dataset_6x30bp"])
     ap.add_argument("--seed", type=int, default=20251020)
     args = ap.parse_args()
     import math
@@ -70,27 +70,38 @@ def main():
     os.makedirs(config.DPAMSA_WEIGHTS_PATH, exist_ok=True)
     train_data = load_module(os.path.join(REF, "datasets", "training_dataset", "synthetic_dataset_3x30bp.py"), "_train")
     t0 = time.perf_counter()
-    hist = dmain.train(train_data, start=args.train_set, end=args.train_set + 1, model_path="trained_3x30",
-                       early_stopping_patience=10 ** 9)
+    log, curve = [], []
+    weights = os.path.join(config.DPAMSA_WEIGHTS_PATH, "trained_3x30.pth")
+    for k in range(args.train_sets):
+        # the reference's trainer looks for "<model>.pth.pth" when it starts a set (main.py:141-144), so its sets never
+        # build on each other; to carry the weights over, the previous result is put where it looks
+        if k > 0:
+            import shutil
+            shutil.copyfile(weights, weights + ".pth")
+        hist = dmain.train(train_data, start=k, end=k + 1, model_path="trained_3x30", early_stopping_patience=10 ** 9)
+        part = next(iter(hist.values()))
+        log += part
+        curve.append({"set": train_data.datasets[k], "first_100_mean_reward": sum(e["reward"] for e in part[:100]) / 100,
+                      "last_100_mean_reward": sum(e["reward"] for e in part[-100:]) / 100, "last_sp": part[-1]["sp"]})
     train_s = time.perf_counter() - t0
-    log = next(iter(hist.values()))
-    curve = [sum(e["reward"] for e in log[i:i + 100]) / len(log[i:i + 100]) for i in range(0, len(log), max(100, len(log) // 10))]
-
     sd = O.synth_qnet_weights(3, 30, 7)
     torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, os.path.join(config.DPAMSA_WEIGHTS_PATH, "random_3x30.pth"))
-    data = load_module(os.path.join(REF, "datasets", "inference_dataset", args.eval + ".py"), "_eval")
     out = {"recipe": {"trainer": "DPAMSA.main.train (reference recipe: eps-greedy 0.8 -> 0, Adam 1e-4, batch 128, replay 1000, "
-                                 "target refresh every 128 updates)", "episodes": args.episodes,
-                      "training_set": "synthetic_dataset_3x30bp." + train_data.datasets[args.train_set], "seed": args.seed,
+                                 "target refresh every 128 updates)", "episodes_per_set": args.episodes,
+                      "training_sets": ["synthetic_dataset_3x30bp." + n for n in train_data.datasets[:args.train_sets]],
+                      "weights_carried_over_between_sets": args.train_sets > 1, "seed": args.seed,
                       "train_seconds": train_s, "steps": sum(e["steps"] for e in log)},
-           "reward_curve_100_episode_means": curve, "final_sp_on_training_set": log[-1]["sp"], "evaluation": {}}
-    for mode in ("sp", "mo"):
+           "per_set": curve, "evaluation": {},
+           "published_GA_DPAMSA_MO_means": {"synthetic_dataset_3x30bp": {"mean_sp": 5.6, "mean_cs": 0.3467},
+                                            "synthetic_dataset_6x30bp": {"mean_sp": 12.8, "mean_cs": 0.2793},
+                                            "source": "reference results/benchmarks/csv/inference/GA-DPAMSA/*_MO_GA_DPAMSA_results.csv "
+                                                      "(pretrained weights that are not in the checkout; GA settings of the paper)"}}
+    for name in args.eval:
+        data = load_module(os.path.join(REF, "datasets", "inference_dataset", name + ".py"), "_eval_" + name)
         for arm, model in (("random_init", "random_3x30"), ("trained", "trained_3x30")):
-            out["evaluation"]["%s/%s" % (mode, arm)] = evaluate(data, mode, model, 11)
-    pub = os.path.join(REF, "..", "..", "tests", "golden", "report_vectors.json.gz")
-    out["note"] = ("evaluation = mainGA.inference on %s with the reference's default knobs (P = 5, 3 generations, 3x30 window); "
-                   "published GA-DPAMSA means (pretrained weights that are not in the checkout) are in the reference's "
-                   "results/benchmarks/csv/inference/GA-DPAMSA/*.csv" % args.eval)
+            out["evaluation"]["%s/mo/%s" % (name, arm)] = evaluate(data, "mo", model, 11)
+    out["note"] = ("evaluation = mainGA.inference, 'mo' mode, the reference's default knobs (P = 5, 3 generations, 3x30 window), "
+                   "same `random` seed for both arms")
     print(json.dumps(out))
 
 

@@ -201,6 +201,36 @@ def test_hall_of_fame_golden(gpu, primitives):
         assert list(got) == want_score
 
 
+@pytest.mark.parametrize("mode", ["sp", "cs", "mo"])
+def test_hall_of_fame_large_random_against_oracle(gpu, mode):
+    """The one-launch decision (hof_decide_kernel) on grids of many blocks: score ranges over a grid barrier,
+    first maximum among many ties, the record re-entering as element n, three updates in a row."""
+    rng = random.Random(23)
+    for n in (1500, 70001, 200000):
+        dev = None
+        hof = None
+        boards = [tagged_board(i) for i in range(n)]
+        for rnd in range(3):
+            hi = 6 + 3 * rnd if rnd < 2 else 4                     # third round: the old record usually stays
+            full = [(i, rng.randint(-hi, hi) * 4, rng.randint(0, 2 * hi) / 21) for i in range(n)]
+            sc = full if mode == "mo" else [(i, s) for i, s, _ in full] if mode == "sp" else [(i, c) for i, _, c in full]
+            if dev is None:
+                dev = device_population(gpu, n, sc, mode)
+            else:
+                sp, em, al = scores_to_arrays(sc, mode)
+                dev.cur.sp[:n].copy_(gpu.from_numpy(sp))
+                dev.cur.em[:n].copy_(gpu.from_numpy(em))
+                dev.cur.al[:n].copy_(gpu.from_numpy(al))
+            dev.hof_update(mode)
+            hof = O.hof_update(hof, boards, sc)
+            rec = dev.hof.cpu().tolist()
+            assert rec[5:] == [0, 0, 0]                            # barrier counter and ticket are back to zero
+            got = (rec[1], rec[2]) if mode == "sp" else (rec[1], rec[3] / rec[4]) if mode == "cs" else \
+                (rec[1], rec[2], rec[3] / rec[4])
+            assert got == tuple(hof[1]), (n, rnd, got, hof[1])
+            assert dev.hof_board[:, :4].cpu().tolist() == [row[:4] for row in hof[0]]
+
+
 # ------------------------------------------------------------------------------------------- a3 / a12 / a13
 def test_population_and_crossover_rng_replay(gpu, primitives, cfg, native_lib):
     """Same CPython `random` stream as the reference: populations, crossover children and the state of
