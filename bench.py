@@ -920,9 +920,14 @@ def main():
     pass_ms_max = float(t.item())
     pass_value = world * P * K / (pass_ms_max * 1e-3)
     fused = world > 1 and getattr(g.backend, "_blk", None) is not None
-    launches_per_pass = 2 if world == 1 else (3 if fused else None)
+    # one GPU: the decision rides in the tail of the TMA-staged fitness kernel (gad_fitness_pass) when the shape allows
+    one_launch = (world == 1 and os.environ.get("GAD_FITNESS_FUSED_HOF", "1") != "0" and
+                  os.environ.get("GAD_FITNESS_TMA", "1") != "0" and P >= 2048 and replicas[0].width_hint <= 256)
+    launches_per_pass = (1 if one_launch else 2) if world == 1 else (3 if fused else None)
     fitness_pass = {"value": pass_value, "unit": "evals/s", "ms_per_step": pass_ms_max / K,
-                    "api": ("GA.calculate_fitness_score: fitness kernel + hall-of-fame decision kernel" if world == 1 else
+                    "api": ("GA.calculate_fitness_score = gad_fitness_pass: ONE launch, the hall-of-fame decision is taken in the "
+                            "tail of the fitness kernel (per-CTA score ranges, one grid barrier, last CTA commits)" if one_launch else
+                            "GA.calculate_fitness_score: fitness kernel + hall-of-fame decision kernel" if world == 1 else
                             "ShardedGA.calculate_fitness_score: fitness kernel + gad_pass_scatter (scores stored into every "
                             "rank's table over NVLink, arrival flags) + gad_pass_decide (hall-of-fame decision on every rank, "
                             "the winner's board pushed by its owner) - no collective call" if fused else

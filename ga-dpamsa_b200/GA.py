@@ -312,8 +312,7 @@ class GA:
         """GA.py:154-181: pad, clean, score every board (one launch), then the hall of fame."""
         if self._dev is None or self._dev.n == 0:
             raise ValueError("empty population")
-        self._dev.fitness(*self._weights())
-        self.update_hall_of_fame()
+        self._dev.fitness_pass(*self._weights(), self.mode)        # scores + update_hall_of_fame, one launch
 
     # ------------------------------------------------------------------ a10 / a11
     @_on_device

@@ -38,6 +38,9 @@ SIGNATURES = {
     "gad_stream_sync": (c_int, [c_vp]),
     "gad_enable_peer_access": (c_int, [c_int]),
     "gad_fitness": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gad_fitness_pass": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int,
+                                 c_vp, c_vp, c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "gad_debug_stamps": (c_int, [c_vp]),
     "gad_probe_read": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "gad_fitness_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int]),
     "gad_window_score_host": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -9,6 +9,7 @@
 // every cell is used exactly once. HBM-bound: R*W bytes in (+R*W' out only for the boards that
 // actually change), 12 bytes of scores out.
 #include "gad_common.cuh"
+#include "hof_decide.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -542,13 +543,259 @@ __device__ __forceinline__ uint32_t nib_keep_word(const NibCounts &n, int hi)
     return nonzero_lanes(s);
 }
 
+// GA.update_hall_of_fame in the tail of the fitness launch (gad_fitness_pass): hof == nullptr = scores only
+struct FtHof {
+    int *hof;                    // record {valid, index, sp, em, al, barrier counter, ticket, -}: words 5 and 6 are zero
+    uint8_t *hof_board;          // between launches
+    int mode, hof_valid;
+    GadDecideParts parts;
+    unsigned long long *stamps;  // measurement hook (gad_debug_stamps): where the tail leaves its timestamps, or nullptr
+};
+
+// timestamps of the decision tail, by thread 0 of CTA 0 (slots 0..7) and of the last CTA (8..11): globaltimer ns
+__device__ __forceinline__ void ft_stamp(const FtHof &fh, int slot, bool who)
+{
+    if (fh.stamps != nullptr && who) fh.stamps[slot] = global_ns();
+}
+
+// What a CTA remembers of the boards it scored, for the decision in its tail: the score tuples and column scores
+// (when its share fits) and, in 'mo' mode, their range - kept with shared-memory atomics by the lane that writes a
+// board's scores, so the tail starts with the CTA's range in hand and never goes back to L2 for a score.
+constexpr int FT_TAIL_CAP = 1024;
+struct FtTail {
+    int lo, hi;
+    u64 clo, chi;                // bit patterns of non-negative doubles (order-preserving)
+    int from_global;             // a board took the global-memory path, or the share exceeds FT_TAIL_CAP: re-read scores
+    int rec[3];                  // CTA 0: the record's (sp, em, al), fetched while the boards stream in
+    int win_sp, win_em, win_al;
+    u64 cs[FT_TAIL_CAP];         // em / al as python computes it ('cs' and 'mo')
+    int sp[FT_TAIL_CAP], em[FT_TAIL_CAP], al[FT_TAIL_CAP];
+};
+
+__device__ __forceinline__ void ft_tail_note(FtTail &t, int mode, int j, int s, int e, int a)
+{
+    const bool fits = j < FT_TAIL_CAP;
+    if (fits) {
+        t.sp[j] = s;
+        t.em[j] = e;
+        t.al[j] = a;
+    }
+    if (mode != GAD_MODE_SP) {
+        const u64 c = (u64)__double_as_longlong(column_score(e, a));
+        if (fits) t.cs[j] = c;
+        if (mode == GAD_MODE_MO) {
+            atomicMin(&t.lo, s);
+            atomicMax(&t.hi, s);
+            atomicMin(&t.clo, c);
+            atomicMax(&t.chi, c);
+        }
+    }
+}
+
+// make_key with the column score already divided (the same IEEE operations in the same order)
+__device__ __forceinline__ double ft_key(int mode, int s, u64 cbits, const Range &g)
+{
+    if (mode == GAD_MODE_SP) return (double)s;
+    const double c = __longlong_as_double((long long)cbits);
+    if (mode == GAD_MODE_CS) return c;
+    const double clo = __longlong_as_double((long long)g.clo), chi = __longlong_as_double((long long)g.chi);
+    const double nsp = g.hi > g.lo ? __ddiv_rn((double)((long long)s - g.lo), (double)((long long)g.hi - g.lo)) : 0.5;
+    const double ncs = chi > clo ? __ddiv_rn(__dsub_rn(c, clo), __dsub_rn(chi, clo)) : 0.5;
+    return __dadd_rn(nsp, ncs);
+}
+
+__device__ __forceinline__ void ft_red_release(int *p)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ int ft_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ft_ticket_acq_rel(int *p)
+{
+    int v;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The hall-of-fame decision (GA.py:110-136) by the consumer threads of every CTA once their boards are scored.
+// Every step that goes to L2 and back costs about a microsecond, so the chain is kept short (measured with
+// gad_debug_stamps, scripts/pass_timing.py): the CTA's score range is already in shared memory (ft_tail_note);
+// 'mo' publishes it and arrives at ONE grid barrier with a release (the grid is one persistent CTA per SM, all
+// resident; thread 0 speaks for the CTA after a CTA barrier, like a cooperative grid sync), polls it with acquire
+// loads, and every WARP folds the partial ranges for itself (no block-wide fold); the keys of the CTA's own boards
+// come from the shared-memory tuples with the arithmetic of make_key; the best per CTA is published with its
+// tuple under an acq_rel ticket, and the last CTA reads every CTA's best and tuple in one trip, settles the first
+// maximum and copies the winner's board. The record takes part as element P (CTA 0). Words 5 and 6 of the record
+// are the barrier counter and the ticket: zero before the launch, left zero by it.
+__device__ __noinline__ void ft_decide_tail(const FtHof &fh, FtTail &ts, int NB, int nk, int P, int R, int stride,
+                                            const uint8_t *boards, const int32_t *sp, const int32_t *em, const int32_t *al,
+                                            int tid, int n_consumers)
+{
+    __shared__ DecideShared sh;
+    const BlockCtx cx{tid, n_consumers, 1};
+    const int mode = fh.mode, lane = tid & 31, grid = (int)gridDim.x;
+    const bool has_rec = fh.hof_valid != 0 && blockIdx.x == 0;          // the record is element P of CTA 0's share
+    int *sync = fh.hof + 5;
+    const int nown = nk * NB;
+    cx.sync();                           // every board of this CTA is scored
+    const bool st0 = blockIdx.x == 0 && tid == 0;
+    ft_stamp(fh, 1, st0);
+    const bool from_global = nown > FT_TAIL_CAP || *reinterpret_cast<volatile int *>(&ts.from_global) != 0;
+    Range g;
+    range_clear(g);
+    if (mode == GAD_MODE_MO) {
+        if (from_global) {               // (own writes: visible to the CTA after the barrier)
+            for (int j = tid; j < nown; j += n_consumers) {
+                const int k = j / NB, p = (blockIdx.x + k * grid) * NB + (j - k * NB);
+                if (p < P) {
+                    const int s = __ldcg(sp + p);
+                    const u64 c = (u64)__double_as_longlong(column_score(__ldcg(em + p), __ldcg(al + p)));
+                    range_merge(g, s, s, c, c);
+                }
+            }
+            g = range_fold_block(g, sh, cx);
+        } else {
+            g.lo = ts.lo, g.hi = ts.hi, g.clo = ts.clo, g.chi = ts.chi;
+        }
+        if (has_rec) {
+            const u64 c = (u64)__double_as_longlong(column_score(ts.rec[1], ts.rec[2]));
+            range_merge(g, ts.rec[0], ts.rec[0], c, c);
+        }
+        if (grid > 1) {
+            uint4 *rec = fh.parts.rec;   // 64 bytes per CTA: {lo, hi, clo, chi} | {key, idx, sp, em, al}
+            if (tid == 0) {
+                rec[4 * blockIdx.x] = make_uint4((unsigned)g.lo, (unsigned)g.hi, (unsigned)g.clo, (unsigned)(g.clo >> 32));
+                rec[4 * blockIdx.x + 1] = make_uint4((unsigned)g.chi, (unsigned)(g.chi >> 32), 0u, 0u);
+                ft_stamp(fh, 2, st0);
+                ft_red_release(&sync[0]);                // the CTA's scores, compacted cells and partials, then the arrival
+                const unsigned long long t0 = global_ns();
+                unsigned spins = 0;
+                while (ft_ld_acquire(&sync[0]) < grid)   // all CTAs are resident; a lost arrival fails loudly
+                    if ((++spins & 1023u) == 0u && global_ns() - t0 > 2000000000ull) __trap();
+                ft_stamp(fh, 3, st0);
+            }
+            cx.sync();
+            // one warp reads every CTA's range - all loads in flight at once, 32 bytes per CTA (148 CTAs reading the
+            // same few lines: 28 warps each doing so queue up in L2 for microseconds) - and hands the fold to the rest
+            if (tid < 32) {
+                range_clear(g);
+                uint4 ra[5], rb[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int b = min(lane + 32 * q, grid - 1);
+                    ra[q] = __ldcg(&rec[4 * b]);
+                    rb[q] = __ldcg(&rec[4 * b + 1]);
+                }
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    range_merge(g, (int)ra[q].x, (int)ra[q].y, (u64)ra[q].z | ((u64)ra[q].w << 32), (u64)rb[q].x | ((u64)rb[q].y << 32));
+                for (int b = lane + 160; b < grid; b += 32) {        // more than one CTA per SM (GAD_FT_CTAS)
+                    const uint4 a4 = __ldcg(&rec[4 * b]), b4 = __ldcg(&rec[4 * b + 1]);
+                    range_merge(g, (int)a4.x, (int)a4.y, (u64)a4.z | ((u64)a4.w << 32), (u64)b4.x | ((u64)b4.y << 32));
+                }
+                range_fold_warp(g);
+                if (lane == 0) sh.range[0] = g;
+            }
+            cx.sync();
+            g = sh.range[0];
+        }
+    }
+    ft_stamp(fh, 5, st0);
+    double bk = 0.0;
+    int bi = 0x7fffffff;
+    for (int j = tid; j < nown; j += n_consumers) {
+        const int k = j / NB, p = (blockIdx.x + k * grid) * NB + (j - k * NB);
+        if (p < P) {
+            double key;
+            if (from_global) key = make_key(mode, __ldcg(sp + p), __ldcg(em + p), __ldcg(al + p), g.lo, g.hi, g.clo, g.chi);
+            else key = ft_key(mode, ts.sp[j], mode != GAD_MODE_SP ? ts.cs[j] : 0ull, g);
+            best_merge(bk, bi, key, p);
+        }
+    }
+    if (has_rec && tid == 0) best_merge(bk, bi, make_key(mode, ts.rec[0], ts.rec[1], ts.rec[2], g.lo, g.hi, g.clo, g.chi), P);
+    best_fold_block(bk, bi, sh, cx);     // the best of the CTA, in warp 0
+    ft_stamp(fh, 6, st0);
+    if (tid == 0) {
+        sh.last = true;
+        sh.winner = bi;
+        if (bi == P) {
+            ts.win_sp = ts.rec[0], ts.win_em = ts.rec[1], ts.win_al = ts.rec[2];
+        } else if (bi != 0x7fffffff) {
+            const int box = bi / NB, j = (box - (int)blockIdx.x) / grid * NB + (bi - box * NB);
+            if (from_global) ts.win_sp = __ldcg(sp + bi), ts.win_em = __ldcg(em + bi), ts.win_al = __ldcg(al + bi);
+            else ts.win_sp = ts.sp[j], ts.win_em = ts.em[j], ts.win_al = ts.al[j];
+        }
+        if (grid > 1) {
+            const u64 kb = (u64)__double_as_longlong(bk);
+            fh.parts.rec[4 * blockIdx.x + 2] = make_uint4((unsigned)kb, (unsigned)(kb >> 32), (unsigned)bi, (unsigned)ts.win_sp);
+            fh.parts.rec[4 * blockIdx.x + 3] = make_uint4((unsigned)ts.win_em, (unsigned)ts.win_al, 0u, 0u);
+            // release: for the whole CTA (the barrier above) - cells compacted by it, its partials; acquire: the others'
+            sh.last = ft_ticket_acq_rel(&sync[1]) == grid - 1;
+        }
+    }
+    ft_stamp(fh, 7, st0);
+    cx.sync();
+    if (!sh.last) return;
+    ft_stamp(fh, 8, tid == 0);
+    if (grid > 1) {
+        bk = 0.0;
+        bi = 0x7fffffff;
+        int ws = 0, we = 0, wa = 0;
+        for (int b = tid; b < grid; b += n_consumers) {
+            const uint4 a4 = __ldcg(&fh.parts.rec[4 * b + 2]), b4 = __ldcg(&fh.parts.rec[4 * b + 3]);
+            const double key = __longlong_as_double((long long)((u64)a4.x | ((u64)a4.y << 32)));
+            const int i = (int)a4.z;
+            if (i != 0x7fffffff && (bi == 0x7fffffff || better(key, i, bk, bi)))
+                bk = key, bi = i, ws = (int)a4.w, we = (int)b4.x, wa = (int)b4.y;
+        }
+        const int cand = bi;
+        best_fold_block(bk, bi, sh, cx);
+        if (tid == 0) sh.winner = bi;
+        cx.sync();
+        if (cand == sh.winner && cand != 0x7fffffff) ts.win_sp = ws, ts.win_em = we, ts.win_al = wa;     // indices are distinct
+    }
+    ft_stamp(fh, 10, tid == 0);
+    if (tid == 0) {
+        sync[0] = 0;
+        sync[1] = 0;
+        *fh.parts.winner = sh.winner;
+    }
+    cx.sync();
+    // GA.py:110-136: the winner's board and score tuple become the hall of fame; winner == P: the record keeps its
+    // place under the fresh index len(scores) (GA.py:127-132)
+    const int win = sh.winner;
+    if (win >= P) {
+        if (tid == 0) fh.hof[1] = P;
+        return;
+    }
+    const int width = ts.win_al;
+    const int n16 = min(stride >> 4, (width + 15) >> 4);
+    for (int u = tid; u < R * n16; u += n_consumers) {
+        const int r = u / n16, q = u - r * n16;
+        reinterpret_cast<uint4 *>(fh.hof_board + (size_t)r * stride)[q] =
+            __ldcg(reinterpret_cast<const uint4 *>(boards + ((size_t)win * R + r) * stride) + q);
+    }
+    if (tid == 0) {
+        fh.hof[0] = 1;
+        fh.hof[1] = win;
+        fh.hof[2] = ts.win_sp;
+        fh.hof[3] = ts.win_em;
+        fh.hof[4] = width;
+    }
+    ft_stamp(fh, 11, tid == 0);
+}
+
 // RT > 0: the row count is RT (loops fully unrolled, row lengths read as vectors); RT = 0: any R
 template <int GS, bool NIB, int RT>
 __global__ void __launch_bounds__(FtThreads<NIB>::CONSUMERS + 32, 1)
 fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict__ boards, int32_t *__restrict__ rowlen,
                    int P, int R_rt, int stride, FtGeom geo, int match, int mismatch, int gap,
                    int32_t *__restrict__ sp, int32_t *__restrict__ em, int32_t *__restrict__ al,
-                   unsigned long long *__restrict__ max_al, unsigned long long max_tag)
+                   unsigned long long *__restrict__ max_al, unsigned long long max_tag, const __grid_constant__ FtHof fh)
 {
     extern __shared__ uint8_t ft_smem_raw[];
     const int R = RT > 0 ? RT : R_rt;
@@ -563,7 +810,14 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
     // set-up) while this grid is still running; it blocks at its own griddepcontrol.wait until this grid has
     // completed and its writes are visible. Without the launch attribute both instructions are no-ops.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ FtTail ts;                                         // used only when the launch takes the decision (fh.hof)
     if (tid == 0) {
+        ts.lo = 0x7fffffff;
+        ts.hi = (int)0x80000000;
+        ts.clo = ~0ull;
+        ts.chi = 0ull;
+        ts.from_global = 0;
+        ts.win_sp = ts.win_em = ts.win_al = 0;
         for (int s2 = 0; s2 < geo.stages; ++s2) {
             ft_mbar_init(full0 + 8u * s2, 1);
             ft_mbar_init(empty0 + 8u * s2, 1u << (geo.team_shift - 5));          // one arrival per warp of the owning team
@@ -572,6 +826,10 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");            // nothing before this line touched global memory
+    if (fh.hof != nullptr) {
+        ft_stamp(fh, 0, blockIdx.x == 0 && tid == 0);
+        if (blockIdx.x == 0 && tid < 3 && fh.hof_valid) ts.rec[tid] = fh.hof[2 + tid];      // read long before the tail needs it
+    }
 
     if (tid >= n_consumers) {
         // ===================== producer: one thread streams this CTA's boxes =====================
@@ -727,6 +985,7 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
                     const uint4 none[7] = {};
                     nk_cols = board_pass_global<GS, !NIB, false>(board, rl, R, stride, gl, gmask, w, wmin, none, false, match,
                                                                 mismatch, gap, sp + p, em + p, al + p);
+                    ts.from_global = 1;
                 } else {
                     if (nk_cols != w) {
                         // utils.py:408-428 from the shared-memory copy: every lane owns one unit; kept bytes go to
@@ -772,9 +1031,11 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
                     if (nk_cols != w || wmin != w)
                         for (int r = gl; r < R; r += GS) rl[r] = nk_cols;
                     if (gl == 0) {
-                        sp[p] = (int32_t)sum_of_pairs_closed_form(bs, R, match, mismatch, gap);
+                        const int32_t spv = (int32_t)sum_of_pairs_closed_form(bs, R, match, mismatch, gap);
+                        sp[p] = spv;
                         em[p] = (int32_t)bs.exact;
                         al[p] = nk_cols;
+                        if (fh.hof != nullptr) ft_tail_note(ts, fh.mode, k * geo.NB + b, spv, (int32_t)bs.exact, nk_cols);
                     }
                 }
             } else {
@@ -782,6 +1043,7 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
                 const uint4 none[7] = {};
                 nk_cols = board_pass_global<GS, !NIB, false>(board, rl, R, stride, gl, gmask, w, wmin, none, false, match, mismatch,
                                                             gap, sp + p, em + p, al + p);
+                ts.from_global = 1;
             }
             local_max = max(local_max, nk_cols);
         }
@@ -792,6 +1054,7 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
         local_max = group_max<32>(local_max, 0xFFFFFFFFu);
         if (lane == 0) atomicMax(max_al, max_tag | (unsigned long long)local_max);
     }
+    if (fh.hof != nullptr) ft_decide_tail(fh, ts, geo.NB, nk, P, R, stride, boards, sp, em, al, tid, n_consumers);
 }
 
 typedef CUresult (*FtEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -801,7 +1064,8 @@ typedef CUresult (*FtEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 // Returns GAD_OK after launching, or 1 when the shape is outside the TMA path (the caller launches the register kernel).
 template <int GS, bool NIB>
 int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int stride, int width, int match, int mismatch,
-                       int gap, int32_t *sp, int32_t *em, int32_t *al, unsigned long long *max_al, unsigned long long max_tag, cudaStream_t st)
+                       int gap, int32_t *sp, int32_t *em, int32_t *al, unsigned long long *max_al, unsigned long long max_tag,
+                       const FtHof &fh, cudaStream_t st)
 {
     static FtEncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -826,7 +1090,10 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
     g.stage_bytes = (nb * board_bytes + 127) / 128 * 128;
     // tuning knobs (A/B): CTAs per SM, shared memory and consumer threads per CTA
     static const int ctas_per_sm = [] { const char *e = getenv("GAD_FT_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
-    static const int smem_kb = [] { const char *e = getenv("GAD_FT_SMEM_KB"); return e && atoi(e) > 0 ? atoi(e) : 200; }();
+    static const int smem_kb = [] {                                  // + 22 KB of static shared memory (FtTail, DecideShared)
+        const char *e = getenv("GAD_FT_SMEM_KB");
+        return e && atoi(e) > 0 ? (atoi(e) < 200 ? atoi(e) : 200) : 200;
+    }();
     static const int max_cons = [] { const char *e = getenv("GAD_FT_CONSUMERS"); return e && atoi(e) > 0 ? atoi(e) : 1 << 20; }();
     g.stages = (smem_kb * 1024 / ctas_per_sm) / g.stage_bytes;
     if (g.stages > FT_MAX_STAGES) g.stages = FT_MAX_STAGES;
@@ -861,7 +1128,7 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
 #define GAD_FT_LAUNCH(RT)                                                                                                  \
     do {                                                                                                                   \
         GAD_CUDA(cudaFuncSetAttribute(fitness_tma_kernel<GS, NIB, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      227 * 1024 - 1024));                                                                 \
+                                      227 * 1024 - 23 * 1024));                                                                 \
         cudaLaunchConfig_t cfg = {};                                                                                       \
         cfg.gridDim = dim3((unsigned)grid);                                                                                \
         cfg.blockDim = dim3((unsigned)threads);                                                                            \
@@ -873,7 +1140,7 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
         cfg.attrs = attr;                                                                                                  \
         cfg.numAttrs = use_pdl ? 1 : 0;                                                                                    \
         GAD_CUDA(cudaLaunchKernelEx(&cfg, fitness_tma_kernel<GS, NIB, RT>, map, boards, rowlen, (int)P, R, stride, g,      \
-                                    match, mismatch, gap, sp, em, al, max_al, max_tag));                                   \
+                                    match, mismatch, gap, sp, em, al, max_al, max_tag, fh));                               \
     } while (0)
     if (NIB && R == 6) GAD_FT_LAUNCH(NIB ? 6 : 0);
     else if (NIB && R == 4) GAD_FT_LAUNCH(NIB ? 4 : 0);
@@ -909,10 +1176,13 @@ int launch_fitness(uint8_t *boards, int32_t *rowlen, long long P, int R, int str
 
 }  // namespace
 
-extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
-                           int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
-                           int64_t *d_max_al, void *stream)
+// gad_fitness, and - with a decision to take (fh.hof != nullptr) - the whole GA.calculate_fitness_score: *fused says
+// whether the launch took the hall-of-fame decision in its tail (the TMA-staged kernel) or the caller still has to
+static int fitness_dispatch(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
+                            int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
+                            int64_t *d_max_al, const FtHof &fh, bool *fused, void *stream)
 {
+    *fused = false;
     GAD_REQUIRE(P >= 0 && R >= 1 && R <= 255, "gad_fitness: need P >= 0 and 1 <= R <= 255 (got P=%lld R=%d)",
                 (long long)P, R);
     GAD_REQUIRE(stride >= 16 && stride % 16 == 0, "gad_fitness: stride must be a positive multiple of 16 (got %d)",
@@ -942,15 +1212,16 @@ extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int 
         int rc = 1;
 #define GAD_FIT_TMA(GS)                                                                                                   \
     rc = R <= 15 ? launch_fitness_tma<GS, true>(d_boards, d_rowlen, P, R, stride, width, match, mismatch, gap, d_sp, d_em, \
-                                                d_al, max_al, max_tag, st)                                                        \
+                                                d_al, max_al, max_tag, fh, st)                                             \
                  : launch_fitness_tma<GS, false>(d_boards, d_rowlen, P, R, stride, width, match, mismatch, gap, d_sp,      \
-                                                 d_em, d_al, max_al, max_tag, st)
+                                                 d_em, d_al, max_al, max_tag, fh, st)
         if (units <= 1) GAD_FIT_TMA(1);
         else if (units <= 2) GAD_FIT_TMA(2);
         else if (units <= 4) GAD_FIT_TMA(4);
         else if (units <= 8) GAD_FIT_TMA(8);
         else GAD_FIT_TMA(16);
 #undef GAD_FIT_TMA
+        if (rc == 0) *fused = fh.hof != nullptr;
         if (rc <= 0) return rc;                            // launched (0) or failed (< 0); 1 = shape outside the TMA path
     }
 #define GAD_FIT(GS) launch_fitness<GS>(d_boards, d_rowlen, P, R, stride, match, mismatch, gap, d_sp, d_em, d_al, max_al, max_tag, st)
@@ -961,6 +1232,56 @@ extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int 
     if (units <= 16) return GAD_FIT(16);
     return GAD_FIT(32);
 #undef GAD_FIT
+}
+
+extern "C" int gad_fitness(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
+                           int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
+                           int64_t *d_max_al, void *stream)
+{
+    bool fused;
+    return fitness_dispatch(d_boards, d_rowlen, P, R, stride, width_hint, match, mismatch, gap, d_sp, d_em, d_al, d_max_al,
+                            FtHof{}, &fused, stream);
+}
+
+// GA.calculate_fitness_score (GA.py:138-181) = gad_fitness + gad_hof_update. With the TMA-staged kernel (boards up
+// to 256 columns, 2 048+ individuals) both are ONE launch: the CTAs that scored the boards take the decision in
+// their tail (ft_decide_tail). Other shapes: the fitness launch followed by the decision kernel. Same result
+// either way; GAD_FITNESS_FUSED_HOF=0 always takes the two launches (A/B).
+// Measurement hook: a device buffer of 16 uint64 where the decision tail of the next gad_fitness_pass launches leaves
+// globaltimer stamps (nullptr switches it off again). Slots: 0 kernel entry, 1 tail entry, 2 before the arrival,
+// 3 barrier passed, 4 fenced, 5 ranges folded, 6 CTA's best known, 7 ticket taken (all CTA 0); 8-11 the last CTA:
+// entry, fenced, winner known, board copied.
+static unsigned long long *g_tail_stamps = nullptr;
+extern "C" int gad_debug_stamps(void *d_buf16)
+{
+    g_tail_stamps = reinterpret_cast<unsigned long long *>(d_buf16);
+    return GAD_OK;
+}
+
+extern "C" int gad_fitness_pass(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
+                                int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
+                                int64_t *d_max_al, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
+                                void *d_ws, size_t ws_bytes, void *stream)
+{
+    GAD_REQUIRE(d_hof_board && d_hof, "gad_fitness_pass: null device pointer");
+    GAD_REQUIRE(mode >= GAD_MODE_SP && mode <= GAD_MODE_MO, "gad_fitness_pass: unknown mode %d", mode);
+    GAD_REQUIRE(P >= 1, "gad_fitness_pass: empty population");
+    static const bool allow = !(getenv("GAD_FITNESS_FUSED_HOF") && atoi(getenv("GAD_FITNESS_FUSED_HOF")) == 0);
+    FtHof fh{};
+    if (allow) {
+        int rc = gad_decide_parts(d_ws, ws_bytes, P + 1, "gad_fitness_pass", &fh.parts);
+        if (rc) return rc;
+        fh.hof = d_hof;
+        fh.hof_board = d_hof_board;
+        fh.mode = mode;
+        fh.hof_valid = hof_valid ? 1 : 0;
+        fh.stamps = g_tail_stamps;
+    }
+    bool fused = false;
+    int rc = fitness_dispatch(d_boards, d_rowlen, P, R, stride, width_hint, match, mismatch, gap, d_sp, d_em, d_al, d_max_al,
+                              fh, &fused, stream);
+    if (rc || fused) return rc;
+    return gad_hof_update(d_boards, d_sp, d_em, d_al, P, R, stride, mode, d_hof_board, d_hof, hof_valid, d_ws, ws_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

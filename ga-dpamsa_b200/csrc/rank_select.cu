@@ -9,13 +9,12 @@
 // device order bit-identical to the reference's. Device-wide sort and scan are CUB primitives
 // (toolkit headers); the kernels that move boards are hand-written.
 #include "gad_common.cuh"
+#include "hof_decide.cuh"
 
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
 namespace {
-
-typedef unsigned long long u64;
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -39,6 +38,8 @@ struct Workspace {
     int *part_idx;
     int *part_lo, *part_hi;       // per-block score ranges of the one-kernel hall-of-fame decision
     u64 *part_clo, *part_chi;
+    uint4 *part_rec;              // 64 bytes per block: its score range and its best element with the score tuple, one
+                                  // 32-byte record each (the decision in the tail of the fitness kernel)
     void *cub_tmp;
     size_t cub_bytes;
 };
@@ -83,6 +84,7 @@ size_t carve(Workspace &w, void *base, long long n, size_t cub_bytes)
     w.part_hi = (int *)take(sizeof(int) * kArgBlocks);
     w.part_clo = (u64 *)take(sizeof(u64) * kArgBlocks);
     w.part_chi = (u64 *)take(sizeof(u64) * kArgBlocks);
+    w.part_rec = (uint4 *)take(64 * (size_t)kArgBlocks);
     w.cub_tmp = take(cub_bytes);
     w.cub_bytes = cub_bytes;
     return off;
@@ -105,9 +107,6 @@ __device__ __forceinline__ u64 sortable(double v)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// python: exact / num_columns (utils.py:128), 0 when there are no columns
-__device__ __forceinline__ double column_score(int em, int al) { return al > 0 ? __ddiv_rn((double)em, (double)al) : 0.0; }
-
 // ---------------------------------------------------------------------------------------------
 // keys
 // ---------------------------------------------------------------------------------------------
@@ -117,21 +116,6 @@ __global__ void stats_init_kernel(Stats *s)
     s->sp_max = (int)0x80000000;
     s->cs_min = ~0ull;
     s->cs_max = 0ull;
-}
-
-// element i < P comes from the population, element P (when n == P + 1) from the hall of fame
-__device__ __forceinline__ void load_score(const int *sp, const int *em, const int *al, const int *hof, long long P,
-                                           long long i, int &s, int &e, int &a)
-{
-    if (i < P) {
-        s = sp[i];
-        e = em[i];
-        a = al[i];
-    } else {
-        s = hof[2];
-        e = hof[3];
-        a = hof[4];
-    }
 }
 
 __global__ void stats_kernel(const int *__restrict__ sp, const int *__restrict__ em, const int *__restrict__ al,
@@ -161,18 +145,6 @@ __global__ void stats_kernel(const int *__restrict__ sp, const int *__restrict__
         atomicMin(&st->cs_min, clo);
         atomicMax(&st->cs_max, chi);
     }
-}
-
-// utils.py:332-351: single metric -> the metric; MO -> (sp-min)/(max-min) + (cs-min)/(max-min), 0.5 when flat
-__device__ __forceinline__ double make_key(int mode, int s, int e, int a, long long lo, long long hi, u64 cs_min, u64 cs_max)
-{
-    if (mode == GAD_MODE_SP) return (double)s;
-    if (mode == GAD_MODE_CS) return column_score(e, a);
-    const double clo = __longlong_as_double((long long)cs_min), chi = __longlong_as_double((long long)cs_max);
-    const double nsp = hi > lo ? __ddiv_rn((double)((long long)s - lo), (double)(hi - lo)) : 0.5;
-    const double c = column_score(e, a);
-    const double ncs = chi > clo ? __ddiv_rn(__dsub_rn(c, clo), __dsub_rn(chi, clo)) : 0.5;
-    return __dadd_rn(nsp, ncs);
 }
 
 __global__ void keys_kernel(const int *__restrict__ sp, const int *__restrict__ em, const int *__restrict__ al,
@@ -351,11 +323,6 @@ compact_kernel(const uint8_t *__restrict__ src, const int *__restrict__ src_rowl
 // ---------------------------------------------------------------------------------------------
 // hall of fame
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool better(double ka, int ia, double kb, int ib)
-{
-    return ka > kb || (ka == kb && ia < ib);      // first maximum wins (stable descending sort, utils.py:340,351)
-}
-
 __global__ void __launch_bounds__(256)
 argbest_kernel(const double *__restrict__ key, long long n, double *__restrict__ part_key,
                int *__restrict__ part_idx, Stats *st)
@@ -492,13 +459,6 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // wait until *p >= want (a peer's store); a peer that never arrives must not hang the GPU: trap after 20 s
 __device__ __forceinline__ void wait_flag(const int *p, int want, int *err)
 {
@@ -514,56 +474,6 @@ __device__ __forceinline__ void wait_flag(const int *p, int want, int *err)
 }
 
 // ---- pieces shared by the two shapes of the decision kernel ------------------------------------------------
-struct Range {
-    int lo, hi;
-    u64 clo, chi;        // bit patterns of non-negative doubles (order-preserving)
-};
-
-__device__ __forceinline__ void range_clear(Range &g)
-{
-    g.lo = 0x7fffffff;
-    g.hi = (int)0x80000000;
-    g.clo = ~0ull;
-    g.chi = 0ull;
-}
-
-__device__ __forceinline__ void range_merge(Range &g, int lo, int hi, u64 clo, u64 chi)
-{
-    g.lo = min(g.lo, lo);
-    g.hi = max(g.hi, hi);
-    g.clo = clo < g.clo ? clo : g.clo;
-    g.chi = chi > g.chi ? chi : g.chi;
-}
-
-__device__ __forceinline__ void range_fold_warp(Range &g)
-{
-    for (int o = 16; o > 0; o >>= 1)
-        range_merge(g, __shfl_xor_sync(0xFFFFFFFFu, g.lo, o), __shfl_xor_sync(0xFFFFFFFFu, g.hi, o),
-                    __shfl_xor_sync(0xFFFFFFFFu, g.clo, o), __shfl_xor_sync(0xFFFFFFFFu, g.chi, o));
-}
-
-struct DecideShared {                // up to 32 warps per block
-    Range range[32];
-    double key[32];
-    int idx[32];
-    int winner;
-    bool last;
-};
-
-// score range of the block's elements; result in every thread
-__device__ __forceinline__ Range range_fold_block(Range g, DecideShared &sh)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    range_fold_warp(g);
-    if (lane == 0) sh.range[wid] = g;
-    __syncthreads();
-    range_clear(g);
-    if (lane < nw) g = sh.range[lane];
-    range_fold_warp(g);
-    __syncthreads();
-    return g;
-}
-
 __device__ __forceinline__ Range range_scan(const int *sp, const int *em, const int *al, const int *hofp, long long P,
                                             long long n, long long first, long long step)
 {
@@ -576,36 +486,6 @@ __device__ __forceinline__ Range range_scan(const int *sp, const int *em, const 
         range_merge(g, s, s, c, c);
     }
     return g;
-}
-
-__device__ __forceinline__ void best_merge(double &bk, int &bi, double k, int i)
-{
-    if (i != 0x7fffffff && (bi == 0x7fffffff || better(k, i, bk, bi))) {
-        bk = k;
-        bi = i;
-    }
-}
-
-__device__ __forceinline__ void best_fold_warp(double &bk, int &bi)
-{
-    for (int o = 16; o > 0; o >>= 1) best_merge(bk, bi, __shfl_xor_sync(0xFFFFFFFFu, bk, o), __shfl_xor_sync(0xFFFFFFFFu, bi, o));
-}
-
-// best of the block; result in warp 0
-__device__ __forceinline__ void best_fold_block(double &bk, int &bi, DecideShared &sh)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    best_fold_warp(bk, bi);
-    if (lane == 0) {
-        sh.key[wid] = bk;
-        sh.idx[wid] = bi;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        bk = lane < nw ? sh.key[lane] : 0.0;
-        bi = lane < nw ? sh.idx[lane] : 0x7fffffff;
-        best_fold_warp(bk, bi);
-    }
 }
 
 __device__ __forceinline__ void best_scan(const int *sp, const int *em, const int *al, const int *hofp, long long P,
@@ -699,6 +579,7 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
 {
     __shared__ DecideShared sh;
     const int tid = threadIdx.x;
+    const BlockCtx cx{tid, (int)blockDim.x, 0};
     DecideView v;
     v.sp = sp_in, v.em = em_in, v.al = al_in, v.sync = sync;
     decide_enter(v, pp);
@@ -710,7 +591,7 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
     Range g;
     range_clear(g);
     if (mode == GAD_MODE_MO) {
-        g = range_fold_block(range_scan(v.sp, v.em, v.al, hofp, P, n, first, step), sh);
+        g = range_fold_block(range_scan(v.sp, v.em, v.al, hofp, P, n, first, step), sh, cx);
         if (gridDim.x > 1) {
             if (tid == 0) {
                 w.part_lo[blockIdx.x] = g.lo;
@@ -726,7 +607,7 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
             range_clear(g);
             for (int b = tid; b < (int)gridDim.x; b += blockDim.x)
                 range_merge(g, __ldcg(&w.part_lo[b]), __ldcg(&w.part_hi[b]), __ldcg(&w.part_clo[b]), __ldcg(&w.part_chi[b]));
-            g = range_fold_block(g, sh);
+            g = range_fold_block(g, sh, cx);
         }
     }
 
@@ -734,7 +615,7 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
     double bk;
     int bi;
     best_scan(v.sp, v.em, v.al, hofp, P, n, first, step, mode, g, bk, bi);
-    best_fold_block(bk, bi, sh);
+    best_fold_block(bk, bi, sh, cx);
     if (tid == 0) {
         sh.last = true;
         if (gridDim.x > 1) {
@@ -752,7 +633,7 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
         bi = 0x7fffffff;
         for (int b = tid; b < (int)gridDim.x; b += blockDim.x) best_merge(bk, bi, __ldcg(&w.part_key[b]), __ldcg(&w.part_idx[b]));
         __syncthreads();
-        best_fold_block(bk, bi, sh);
+        best_fold_block(bk, bi, sh, cx);
     }
     if (tid == 0) {
         sh.winner = bi;
@@ -929,6 +810,23 @@ extern "C" int gad_hof_argbest(const int32_t *d_sp, const int32_t *d_em, const i
     argbest_kernel<<<blocks, 256, 0, st>>>(key, n, w.part_key, w.part_idx, w.stats);
     copy_winner_kernel<<<1, 1, 0, st>>>(w.stats, d_winner);
     GAD_LAUNCH_CHECK();
+    return GAD_OK;
+}
+
+// fitness.cu (gad_fitness_pass): where a decision taken in the tail of the fitness kernel leaves its partials
+int gad_decide_parts(void *d_ws, size_t ws_bytes, long long n, const char *who, GadDecideParts *out)
+{
+    Workspace w;
+    int rc = open_workspace(w, d_ws, ws_bytes, n, who);
+    if (rc) return rc;
+    out->key = w.part_key;
+    out->idx = w.part_idx;
+    out->lo = w.part_lo;
+    out->hi = w.part_hi;
+    out->clo = w.part_clo;
+    out->chi = w.part_chi;
+    out->rec = w.part_rec;
+    out->winner = &w.stats->winner;
     return GAD_OK;
 }
 

@@ -239,6 +239,19 @@ class DevicePopulation:
         self.evals += self.n
         return self.sp, self.em, self.al
 
+    def fitness_pass(self, match: int, mismatch: int, gap: int, mode: str):
+        """GA.calculate_fitness_score (GA.py:138-181): the scoring pass and GA.update_hall_of_fame - one launch for
+        the shapes the TMA-staged kernel takes (the decision rides in the kernel's tail), else two."""
+        ws = self._workspace()
+        b = self.cur
+        nat.call("gad_fitness_pass", nat.ptr(b.boards), nat.ptr(b.rowlen), self.n, self.R, self.stride,
+                 int(self.width_hint), int(match), int(mismatch), int(gap), nat.ptr(b.sp), nat.ptr(b.em),
+                 nat.ptr(b.al), nat.ptr(self.max_al), MODE_ID[mode], nat.ptr(self.hof_board), nat.ptr(self.hof),
+                 int(self.hof_valid), nat.ptr(ws), ws.numel(), self._stream())
+        self.evals += self.n
+        self.hof_valid = True
+        return self.sp, self.em, self.al
+
     def hof_update(self, mode: str):
         """GA.update_hall_of_fame (GA.py:110-136) on device."""
         ws = self._workspace()

@@ -135,6 +135,20 @@ int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, const int32_t *
                    int64_t P, int R, int stride, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
                    void *d_ws, size_t ws_bytes, void *stream);
 
+/* GA.calculate_fitness_score as a whole (GA.py:138-181): gad_fitness followed by gad_hof_update, same arguments,
+ * same results. For populations the TMA-staged kernel takes (boards up to 256 columns, 2 048+ individuals, 16-byte
+ * aligned) it is ONE launch: the CTAs that scored the boards take the hall-of-fame decision in their tail (per-CTA
+ * score ranges, one grid barrier, keys of the CTA's own boards, last CTA commits); otherwise the two launches.
+ * GAD_FITNESS_FUSED_HOF=0 forces the two launches (A/B). Workspace: gad_workspace_bytes(P). */
+int gad_fitness_pass(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
+                     int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
+                     int64_t *d_max_al, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
+                     void *d_ws, size_t ws_bytes, void *stream);
+
+/* Measurement hook (scripts/pass_timing.py): d_buf16 = device uint64[16] where the decision tail of the following
+ * gad_fitness_pass launches leaves %globaltimer stamps of its steps (NULL switches it off). Not part of the path. */
+int gad_debug_stamps(void *d_buf16);
+
 /* The decision of gad_hof_update alone: *d_winner = index of the best of population + hall of fame
  * (P = the hall of fame keeps its place). Used when the boards are sharded over several GPUs and
  * the winner's board has to be fetched from its owner. */

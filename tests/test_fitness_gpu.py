@@ -296,3 +296,76 @@ def test_tma_and_register_kernels_agree_at_baseline_shapes(gpu, monkeypatch):
         for x, y in zip(out["1"][:4], out["0"][:4]):
             assert np.array_equal(x, y)
         assert out["1"][4] == out["0"][4]
+
+
+# ------------------------------------------------------------------ GA.calculate_fitness_score as one launch
+def _random_population(rng, P, R, C, ragged, min_flips=0):
+    """Boards of R copies of one random sequence with a few random cells (symbols or gaps) changed; a share of them
+    ragged and with all-gap columns (the cleaning branch)."""
+    base = np.repeat(rng.integers(1, 5, size=(1, C)), R, axis=0)
+    pop = []
+    for p in range(P):
+        b = base.copy()
+        flips = rng.integers(0, R * C, size=rng.integers(min_flips, 12))
+        b.flat[flips] = rng.integers(1, 6, size=len(flips))
+        rows = [list(map(int, r)) for r in b]
+        if ragged and p % 5 == 0:
+            col = int(rng.integers(0, C))
+            for r in rows:
+                r.insert(col, 5)                       # an all-gap column: cleaned away by the pass
+            rows[int(rng.integers(0, R))].extend([5] * int(rng.integers(1, 4)))
+        pop.append(rows)
+    return pop
+
+
+@pytest.mark.parametrize("mode", ["sp", "cs", "mo"])
+@pytest.mark.parametrize("P,R,C", [(5000, 6, 60), (2500, 20, 120), (2048, 3, 30), (600, 6, 60)])
+def test_fitness_pass_one_launch_equals_two_launches_and_the_oracle(gpu, mode, P, R, C):
+    """gad_fitness_pass (the hall-of-fame decision in the tail of the TMA-staged fitness kernel; P = 600 takes the
+    two launches) against gad_fitness + gad_hof_update on a copy and against the oracle's GA.update_hall_of_fame,
+    three passes in a row: first record, a better population, a worse one (the record keeps its place)."""
+    from population import DevicePopulation
+    rng = np.random.default_rng(P + R)
+    hof = None
+    one = two = None
+    for rnd in range(3):
+        pop = _random_population(rng, P, R, C, ragged=True, min_flips=2 if rnd == 0 else 0)
+        if rnd == 2:                                    # everybody worse than the record: rows of gaps and one symbol
+            pop = [[[5] * C for _ in range(R)] for _ in range(P)]
+            for p, b in enumerate(pop):
+                b[p % R][p % C] = 1 + p % 4
+        boards, rowlen = O.to_arrays(copy.deepcopy(pop), stride=-(-(C + 8) // 16) * 16)
+        if one is None:
+            one = DevicePopulation.from_numpy(boards.copy(), rowlen.copy())
+            two = DevicePopulation.from_numpy(boards.copy(), rowlen.copy())
+        else:
+            for dev in (one, two):
+                dev.cur.boards[:P].copy_(gpu.from_numpy(boards))
+                dev.cur.rowlen[:P].copy_(gpu.from_numpy(rowlen))
+        one.fitness_pass(4, -4, -4, mode)
+        two.fitness(4, -4, -4)
+        two.hof_update(mode)
+        gpu.cuda.synchronize()
+        osp, oem, oal = O.fitness_population_c(boards, rowlen)          # cleans `boards` in place like the pass
+        for a, b2 in ((one.sp, two.sp), (one.em, two.em), (one.al, two.al)):
+            assert gpu.equal(a[:P], b2[:P])
+        assert np.array_equal(one.sp[:P].cpu().numpy(), osp) and np.array_equal(one.al[:P].cpu().numpy(), oal)
+        assert one.to_lists() == two.to_lists() == O.to_lists(boards, rowlen)
+        rec1, rec2 = one.hof.cpu().tolist(), two.hof.cpu().tolist()
+        assert rec1 == rec2 and rec1[5:] == [0, 0, 0], (rnd, rec1, rec2)
+        assert gpu.equal(one.hof_board, two.hof_board)
+        cleaned = O.to_lists(boards, rowlen)
+        if mode == "sp":
+            sc = [(i, int(osp[i])) for i in range(P)]
+        elif mode == "cs":
+            sc = [(i, int(oem[i]) / int(oal[i]) if oal[i] else 0.0) for i in range(P)]
+        else:
+            sc = [(i, int(osp[i]), int(oem[i]) / int(oal[i]) if oal[i] else 0.0) for i in range(P)]
+        hof = O.hof_update(hof, cleaned, sc)
+        got = (rec1[1], rec1[2]) if mode == "sp" else (rec1[1], rec1[3] / rec1[4]) if mode == "cs" else \
+            (rec1[1], rec1[2], rec1[3] / rec1[4])
+        assert got == tuple(hof[1]), (rnd, got, hof[1])
+        board, _ = one.hof_numpy()
+        assert board.tolist() == hof[0]
+        if rnd == 2:
+            assert rec1[1] == P                         # the record won against the whole population
