@@ -461,21 +461,21 @@ __device__ __forceinline__ void count_unit_smem(uint32_t sb, int R, int pitch, i
         ColCounts nn[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) colcounts_clear(nn[k]);
-        int r = 0, pairs = 0;
-        for (; r + 2 <= R; r += 2) {
-            const uint4 x0 = lds128(a0 + (uint32_t)(r * pitch)), x1 = lds128(a0 + (uint32_t)((r + 1) * pitch));
-            colcounts_add2(nn[0], x0.x, x1.x, f2[0]);
-            colcounts_add2(nn[1], x0.y, x1.y, f2[1]);
-            colcounts_add2(nn[2], x0.z, x1.z, f2[2]);
-            colcounts_add2(nn[3], x0.w, x1.w, f2[3]);
-            if (++pairs >= 14) {                              // 4-bit counters hold at most 15
-#pragma unroll
-                for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
-                pairs = 0;
+        int r = 0;
+        const int rp = R & ~1;
+        while (r < rp) {                                      // epochs of at most 14 row pairs: 4-bit counters hold 15
+            const int rend = min(rp, r + 28);
+#pragma unroll 2
+            for (; r < rend; r += 2) {
+                const uint4 x0 = lds128(a0 + (uint32_t)(r * pitch)), x1 = lds128(a0 + (uint32_t)((r + 1) * pitch));
+                colcounts_add2(nn[0], x0.x, x1.x, f2[0]);
+                colcounts_add2(nn[1], x0.y, x1.y, f2[1]);
+                colcounts_add2(nn[2], x0.z, x1.z, f2[2]);
+                colcounts_add2(nn[3], x0.w, x1.w, f2[3]);
             }
-        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
+            for (int k = 0; k < 4; ++k) colcounts_flush2(cc[k], nn[k]);
+        }
         if (r < R) {
             const uint4 x0 = lds128(a0 + (uint32_t)(r * pitch));
             colcounts_add(cc[0], x0.x, first.x);
@@ -501,6 +501,7 @@ struct FtGeom {
     int spt;           // stages per team = stages / nteams
     int team_shift;    // log2(NB * GS)
     int nboxes;        // ceil(P / NB)
+    int rev;           // odd boards walk their rows backwards (see the kernel: shared-memory bank conflicts)
 };
 
 // Fold the nibble counters of 8 columns (words w and w + 1 of the board; w even) into the board sums.
@@ -561,7 +562,7 @@ __device__ __forceinline__ void ft_stamp(const FtHof &fh, int slot, bool who)
 // What a CTA remembers of the boards it scored, for the decision in its tail: the score tuples and column scores
 // (when its share fits) and, in 'mo' mode, their range - kept with shared-memory atomics by the lane that writes a
 // board's scores, so the tail starts with the CTA's range in hand and never goes back to L2 for a score.
-constexpr int FT_TAIL_CAP = 1024;
+constexpr int FT_TAIL_CAP = 2048;  // c3: 443 boards per CTA, c4: 1 771
 struct FtTail {
     int lo, hi;
     u64 clo, chi;                // bit patterns of non-negative doubles (order-preserving)
@@ -569,7 +570,8 @@ struct FtTail {
     int rec[3];                  // CTA 0: the record's (sp, em, al), fetched while the boards stream in
     int win_sp, win_em, win_al;
     u64 cs[FT_TAIL_CAP];         // em / al as python computes it ('cs' and 'mo')
-    int sp[FT_TAIL_CAP], em[FT_TAIL_CAP], al[FT_TAIL_CAP];
+    int sp[FT_TAIL_CAP];
+    int ea[FT_TAIL_CAP];         // em | al << 16 (boards of this kernel are at most 256 columns wide)
 };
 
 __device__ __forceinline__ void ft_tail_note(FtTail &t, int mode, int j, int s, int e, int a)
@@ -577,8 +579,7 @@ __device__ __forceinline__ void ft_tail_note(FtTail &t, int mode, int j, int s, 
     const bool fits = j < FT_TAIL_CAP;
     if (fits) {
         t.sp[j] = s;
-        t.em[j] = e;
-        t.al[j] = a;
+        t.ea[j] = e | (a << 16);
     }
     if (mode != GAD_MODE_SP) {
         const u64 c = (u64)__double_as_longlong(column_score(e, a));
@@ -727,7 +728,7 @@ __device__ __noinline__ void ft_decide_tail(const FtHof &fh, FtTail &ts, int NB,
         } else if (bi != 0x7fffffff) {
             const int box = bi / NB, j = (box - (int)blockIdx.x) / grid * NB + (bi - box * NB);
             if (from_global) ts.win_sp = __ldcg(sp + bi), ts.win_em = __ldcg(em + bi), ts.win_al = __ldcg(al + bi);
-            else ts.win_sp = ts.sp[j], ts.win_em = ts.em[j], ts.win_al = ts.al[j];
+            else ts.win_sp = ts.sp[j], ts.win_em = ts.ea[j] & 0xFFFF, ts.win_al = ts.ea[j] >> 16;
         }
         if (grid > 1) {
             const u64 kb = (u64)__double_as_longlong(bk);
@@ -924,8 +925,16 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
                 BoardSums bs;
                 boardsums_clear(bs);
                 if constexpr (NIB) {
+                    // 64-byte rows, an even row count, two boards per quarter-warp (c3): the same unit of two neighbouring
+                    // boards lies a multiple of 128 bytes apart, so every lds128 would be a 2-way bank conflict (ncu: half
+                    // of the shared-load wavefronts). Odd boards walk their rows backwards: rows r and R-1-r are an odd
+                    // multiple of 64 bytes apart, the pair covers all 32 banks. The counts do not depend on the row
+                    // order, and any fixed row serves as the reference of the "all rows equal" test.
+                    const bool back = geo.rev != 0 && (b & 1) != 0;
+                    const int rstep = back ? -pitch : pitch;
+                    const uint32_t sb0 = back ? sb + (uint32_t)((R - 1) * pitch) : sb;
                     for (int u = gl; u < nunits; u += GS) {
-                        const uint32_t a0 = sb + 16u * u;
+                        const uint32_t a0 = sb0 + 16u * u;
                         // words at or beyond nwords hold stale bytes of any value: a stale high word must not carry into
                         // the valid low word it is packed with, so its multiplier is 0 instead of 16
                         const bool v1 = 4 * u + 1 < nwords, v2 = 4 * u + 2 < nwords, v3 = 4 * u + 3 < nwords;
@@ -938,14 +947,14 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap map, uint8_t *__restrict_
                         if constexpr (RT > 0) {
 #pragma unroll
                             for (int r = 0; r < RT; ++r) {
-                                const uint4 x = lds128(a0 + (uint32_t)(r * pitch));
+                                const uint4 x = lds128(a0 + (uint32_t)(r * rstep));
                                 nib_add(na, x.y * my + x.x, fa);
                                 nib_add(nb, x.w * mw + x.z, fb);
                             }
                         } else {
 #pragma unroll 2
                             for (int r = 0; r < R; ++r) {
-                                const uint4 x = lds128(a0 + (uint32_t)(r * pitch));
+                                const uint4 x = lds128(a0 + (uint32_t)(r * rstep));
                                 nib_add(na, x.y * my + x.x, fa);
                                 nib_add(nb, x.w * mw + x.z, fb);
                             }
@@ -1090,9 +1099,9 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
     g.stage_bytes = (nb * board_bytes + 127) / 128 * 128;
     // tuning knobs (A/B): CTAs per SM, shared memory and consumer threads per CTA
     static const int ctas_per_sm = [] { const char *e = getenv("GAD_FT_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
-    static const int smem_kb = [] {                                  // + 22 KB of static shared memory (FtTail, DecideShared)
+    static const int smem_kb = [] {                                  // + 34 KB of static shared memory (FtTail, DecideShared)
         const char *e = getenv("GAD_FT_SMEM_KB");
-        return e && atoi(e) > 0 ? (atoi(e) < 200 ? atoi(e) : 200) : 200;
+        return e && atoi(e) > 0 ? (atoi(e) < 190 ? atoi(e) : 190) : 190;
     }();
     static const int max_cons = [] { const char *e = getenv("GAD_FT_CONSUMERS"); return e && atoi(e) > 0 ? atoi(e) : 1 << 20; }();
     g.stages = (smem_kb * 1024 / ctas_per_sm) / g.stage_bytes;
@@ -1112,6 +1121,8 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
     g.spt = g.stages / g.nteams;
     g.team_shift = 0;
     while ((1 << g.team_shift) < nb * GS) ++g.team_shift;
+    static const int allow_rev = [] { const char *e = getenv("GAD_FT_REVERSE"); return e ? atoi(e) : 1; }();      // A/B switch
+    g.rev = allow_rev && NIB && GS == 4 && g.BW == 64 && R % 2 == 0;
 
     alignas(64) CUtensorMap map;
     const cuuint64_t dims[3] = {(cuuint64_t)stride, (cuuint64_t)R, (cuuint64_t)P};
@@ -1128,7 +1139,7 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
 #define GAD_FT_LAUNCH(RT)                                                                                                  \
     do {                                                                                                                   \
         GAD_CUDA(cudaFuncSetAttribute(fitness_tma_kernel<GS, NIB, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                      227 * 1024 - 23 * 1024));                                                                 \
+                                      227 * 1024 - 36 * 1024));                                                                 \
         cudaLaunchConfig_t cfg = {};                                                                                       \
         cfg.gridDim = dim3((unsigned)grid);                                                                                \
         cfg.blockDim = dim3((unsigned)threads);                                                                            \
@@ -1215,10 +1226,15 @@ static int fitness_dispatch(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int
                                                 d_al, max_al, max_tag, fh, st)                                             \
                  : launch_fitness_tma<GS, false>(d_boards, d_rowlen, P, R, stride, width, match, mismatch, gap, d_sp,      \
                                                  d_em, d_al, max_al, max_tag, fh, st)
-        if (units <= 1) GAD_FIT_TMA(1);
-        else if (units <= 2) GAD_FIT_TMA(2);
-        else if (units <= 4) GAD_FIT_TMA(4);
-        else if (units <= 8) GAD_FIT_TMA(8);
+        // 16+ rows (byte-lane counters, 128 registers, 480 consumer threads): one unit per lane - boxes of two boards
+        // instead of four, so that every one of the 15 consumer warps owns a stage (c4: 11 teams -> 15, 0.66 -> 0.69
+        // of the HBM peak); GAD_FITNESS_GS still overrides
+        int tu = units;
+        if (R >= 16 && !getenv("GAD_FITNESS_GS")) tu = (width + 15) / 16;
+        if (tu <= 1) GAD_FIT_TMA(1);
+        else if (tu <= 2) GAD_FIT_TMA(2);
+        else if (tu <= 4) GAD_FIT_TMA(4);
+        else if (tu <= 8) GAD_FIT_TMA(8);
         else GAD_FIT_TMA(16);
 #undef GAD_FIT_TMA
         if (rc == 0) *fused = fh.hof != nullptr;
