@@ -90,6 +90,14 @@ class PlanJob:
         return self.plan
 
 
+def _variants_draw():
+    """True when a paper-style variant (config.py) will draw from `random` inside mutation or selection: the crossover
+    plan must then be drawn in its place in the generation, not ahead of time."""
+    return (getattr(config, "MUTATION_TILE", "worst") != "worst" or float(getattr(config, "MUTATION_PROBABILITY", 1.0)) < 1.0
+            or getattr(config, "SELECTION_SCHEME", "truncation") != "truncation"
+            or float(getattr(config, "CROSSOVER_PROBABILITY", 1.0)) < 1.0)
+
+
 def _on_device(fn):
     """Run a GA phase with the population's GPU current: kernels are launched on that device's current stream
     and the Q-net handle is created there, whatever device the caller (or another GA instance) selected last."""
@@ -327,10 +335,38 @@ class GA:
     def selection(self):
         """GA.py:232-260"""
         top_n = int(self.population_size * config.SELECTION_RATE)
+        if getattr(config, "SELECTION_SCHEME", "truncation") == "tournament":
+            self._tournament_selection(top_n)
+            self.calculate_fitness_score()
+            return
         n_keep = self._dev.select(self.mode, top_n)
-        if self._plan_job is None and getattr(config, "CROSSOVER_KIND", "horizontal") != "vertical":
+        if (self._plan_job is None and getattr(config, "CROSSOVER_KIND", "horizontal") != "vertical"
+                and not _variants_draw()):
             self._plan_job = PlanJob.start(n_keep, self._dev.R, int(config.POPULATION_SIZE) - n_keep)
         self.calculate_fitness_score()
+
+    def _tournament_selection(self, top_n):
+        """Extension (supplement table A3 'tourn'; no reference code): top_n tournaments without replacement. Each
+        draws max(2, ceil(TOURNAMENT_RATE * pool)) contestants with random.sample from the individuals still in the
+        pool; the best ranked one (the ordering of utils.py:332-351 on the device, ties to the lower position)
+        survives and leaves the pool; survivors keep their original order (GA.py:259). Host loop over device
+        ranks: meant for populations of the paper's size (N = 150)."""
+        import math
+        dev = self._dev
+        n = dev.n
+        top_n = min(top_n, n)
+        order = dev.rank_order(self.mode, n).cpu().numpy()
+        rank = np.empty(n, dtype=np.int64)
+        rank[order] = np.arange(n)
+        pool = list(range(n))
+        keep = np.zeros(n, dtype=bool)
+        rate = float(config.TOURNAMENT_RATE)
+        for _ in range(top_n):
+            t = min(len(pool), max(2, math.ceil(rate * len(pool))))
+            winner = min(random.sample(pool, t), key=rank.__getitem__)
+            keep[winner] = True
+            pool.remove(winner)
+        dev.compact_with(torch.from_numpy(keep).to(dev.device))
 
     # ------------------------------------------------------------------ a12 / a13
     @_on_device
@@ -343,6 +379,9 @@ class GA:
                 widths = dev.cur.al[:dev.n].cpu().numpy().astype(np.int32)
             job, self._plan_job = self._plan_job, None
             plan = job.finish(dev.n, dev.R, n_children) if (job is not None and kind == 0) else None
+            c_prob = float(getattr(config, "CROSSOVER_PROBABILITY", 1.0))
+            if c_prob < 1.0:
+                plan = self._plan_with_probability(dev.n, dev.R, n_children, c_prob, widths, kind)
             if plan is None:
                 plan = np.empty((n_children, 3), dtype=np.int32)
                 state, meta = _mt_state()
@@ -352,6 +391,44 @@ class GA:
             dev.crossover(plan, kind)
         else:
             self._plan_job = None
+        self.calculate_fitness_score()
+
+    @staticmethod
+    def _plan_with_probability(n_parents, n_rows, n_children, probability, widths, kind):
+        """Extension (supplement table A3 'c_prob'; no reference code): the reference's draws for every child
+        (GA.py:281-293), then one random.random(); at or above `probability` the child is a copy of parent1 (a cut
+        past the last row / cell). Drawn in python: meant for populations of the paper's size."""
+        if n_children > 0 and (n_parents < 2 or n_rows < 2):
+            raise ValueError("crossover needs at least two survivors and two rows (the reference loops forever, GA.py:285-290)")
+        plan = np.empty((n_children, 3), dtype=np.int32)
+        parents = range(n_parents)
+        c = 0
+        while c < n_children:
+            a = random.choice(parents)
+            b = random.choice(parents)
+            if a == b:
+                continue
+            if kind == 0:
+                cut, copy_cut = random.randint(1, n_rows - 1), n_rows
+            else:
+                cut, copy_cut = random.randint(1, int(min(widths[a], widths[b])) - 1), 1 << 20
+            if random.random() >= probability:
+                cut = copy_cut
+            plan[c] = (a, b, cut)
+            c += 1
+        return plan
+
+    def _elitism(self):
+        """Extension (supplement table A3 'e_prob'; no reference code): with probability ELITISM_PROBABILITY per
+        generation the hall of fame replaces the worst-ranked individual, and the population is scored again."""
+        p = float(getattr(config, "ELITISM_PROBABILITY", 0.0))
+        if p <= 0.0 or random.random() >= p:
+            return
+        dev = self._dev
+        worst = int(dev.rank_order(self.mode, dev.n)[dev.n - 1].item())
+        width = int(dev.hof[4].item())
+        dev.cur.boards[worst].copy_(dev.hof_board)
+        dev.cur.rowlen[worst].fill_(width)
         self.calculate_fitness_score()
 
     def horizontal_crossover(self):
@@ -374,7 +451,8 @@ class GA:
         # 'sp' / 'cs': the selection will keep exactly top_n individuals, so the crossover plan can be drawn now,
         # under the whole mutation phase (PlanJob)
         self._plan_job = None
-        if self.mode in ("sp", "cs") and getattr(config, "CROSSOVER_KIND", "horizontal") != "vertical":
+        if (self.mode in ("sp", "cs") and getattr(config, "CROSSOVER_KIND", "horizontal") != "vertical"
+                and not _variants_draw()):
             top_n = int(self.population_size * config.SELECTION_RATE)
             if 2 <= top_n <= dev.n:
                 self._plan_job = PlanJob.start(top_n, dev.R, int(config.POPULATION_SIZE) - top_n)
@@ -384,11 +462,46 @@ class GA:
             raise ValueError("AGENT_WINDOW_ROW is larger than the sequence count.")
         qnet = _dqn.load_qnet(model_path, rw, cw)
         idx = dev.rank_order(self.mode, n)
-        tile = dev.worst_tiles(idx, rw, cw, self.mode, *self._weights())
+        m_prob = float(getattr(config, "MUTATION_PROBABILITY", 1.0))
+        random_tile = getattr(config, "MUTATION_TILE", "worst") == "random"
+        tile = None
+        if m_prob < 1.0 or random_tile:
+            idx, tile = self._mutation_variant(idx, rw, cw, m_prob, random_tile)
+            if idx is None:
+                return
+        if tile is None:
+            tile = dev.worst_tiles(idx, rw, cw, self.mode, *self._weights())
         if int(tile.min().item()) < 0:
             raise ValueError("min() arg is an empty sequence")          # no tile fits (utils.py:291)
         max_reward = rw * (rw - 1) / 2 * config.MATCH_REWARD            # env.py:79
         dev.mutate(qnet, idx, tile, cw * max_reward)                    # GA.py:354
+
+    def _mutation_variant(self, idx, rw, cw, m_prob, random_tile):
+        """Extensions (supplement tables A3 'm_prob' and A5 'random' mutation; no reference code). In ranking order
+        every selected individual first draws random.random() (only when MUTATION_PROBABILITY < 1) and is skipped at
+        or above the probability; with MUTATION_TILE = 'random' it then draws its tile with random.randrange over
+        the lattice of utils.get_all_different_sub_range (row-major). Returns (device indices, device tiles or None
+        for the worst-tile search); (None, None) when nobody mutates."""
+        dev = self._dev
+        order = idx.cpu().numpy()
+        minlen = dev.cur.rowlen[:dev.n].min(dim=1).values.cpu().numpy() if random_tile else None
+        kept, tiles = [], []
+        for i in order:
+            if m_prob < 1.0 and random.random() >= m_prob:
+                continue
+            if random_tile:
+                n_r = (dev.R - rw) // rw + 1 if dev.R >= rw else 0
+                n_c = (int(minlen[i]) - cw) // cw + 1 if int(minlen[i]) >= cw else 0
+                if n_r * n_c <= 0:
+                    raise ValueError("min() arg is an empty sequence")
+                t = random.randrange(n_r * n_c)
+                tiles.append((t // n_c * rw, t % n_c * cw))
+            kept.append(int(i))
+        if not kept:
+            return None, None
+        d_idx = torch.tensor(kept, dtype=torch.int32, device=dev.device)
+        d_tile = torch.tensor(tiles, dtype=torch.int32, device=dev.device).reshape(-1, 2) if random_tile else None
+        return d_idx, d_tile
 
     # ------------------------------------------------------------------ a22
     def print_hall_of_fame(self):
@@ -455,6 +568,7 @@ class GA:
                 self.vertical_crossover()
             else:
                 self.horizontal_crossover()
+            self._elitism()
             if debug_mode:
                 self.print_population()
         best_chromosome, _ = self.hall_of_fame

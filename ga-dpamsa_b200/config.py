@@ -43,6 +43,17 @@ MUTATION_RATE = 0.25
 # (GA.py:262-301); 'vertical' is the variant of its supplement table A5 / img/vertical-crossover.png.
 CROSSOVER_KIND = "horizontal"
 
+# --- B200 build only: the GA variants of the paper's supplement (tables A3 / A5: tournament selection %, crossover
+# probability, elitism probability, random-tile mutation). The reference checkout has no code for any of them, so
+# their definitions are this build's (GA.py docstrings, oracle/ga_oracle.py restates them); the defaults below are
+# the reference's behaviour and consume no extra `random` draws.
+MUTATION_TILE = "worst"          # 'worst' (utils.calculate_worst_fitted_sub_board) | 'random' (uniform over the tile lattice)
+MUTATION_PROBABILITY = 1.0       # a selected individual mutates only when random.random() < this
+CROSSOVER_PROBABILITY = 1.0      # otherwise the child is a copy of parent1
+SELECTION_SCHEME = "truncation"  # 'truncation' (GA.py:232-260) | 'tournament'
+TOURNAMENT_RATE = 0.25           # share of the remaining pool that enters each tournament
+ELITISM_PROBABILITY = 0.0        # per generation: the hall of fame replaces the worst-ranked individual
+
 for _ok, _msg in (
     (0 < BATCH_SIZE <= REPLAY_MEMORY_SIZE, "batch size must be in (0, replay memory size]"),
     (ALPHA > 0, "alpha must be positive"),

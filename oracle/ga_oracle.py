@@ -533,11 +533,63 @@ def mutate_board(board, tile, sd, w=DEFAULT_W, qdtype=np.float32, trace=None, fo
         board[fr + i][fc:tc] = row
 
 
-def mutation(population, scores, mode, n_mutate, rw, cw, sd, w=DEFAULT_W, qdtype=np.float32):
-    """GA.py:323-373"""
+def mutation(population, scores, mode, n_mutate, rw, cw, sd, w=DEFAULT_W, qdtype=np.float32,
+             tile_choice="worst", probability=1.0, rng=_pyrandom):
+    """GA.py:323-373.  Paper-style variants (PARITY UNPINNED, no reference code; supplement tables A3 / A5):
+    ``probability`` < 1 - every selected individual mutates only when rng.random() < probability;
+    ``tile_choice`` 'random' - the tile is drawn uniformly from the lattice of utils.py:230-252 with
+    rng.randrange instead of being the worst-fitted one.  Draw order per individual: random(), then randrange."""
     for idx in rank_best(scores, n_mutate):
-        _, tile = worst_tile(population[idx], mode, rw, cw, w)
-        mutate_board(population[idx], tile, sd, w, qdtype)
+        if probability < 1.0 and rng.random() >= probability:
+            continue
+        board = population[idx]
+        if tile_choice == "random":
+            tiles = tile_grid(len(board), min(len(r) for r in board), rw, cw)
+            if not tiles:
+                raise ValueError("min() arg is an empty sequence")
+            tile = tiles[rng.randrange(len(tiles))]
+        else:
+            _, tile = worst_tile(board, mode, rw, cw, w)
+        mutate_board(board, tile, sd, w, qdtype)
+
+
+def tournament_keep(scores, mode, population_size, selection_rate, tournament_rate, rng=_pyrandom):
+    """Tournament selection (PARITY UNPINNED: supplement table A3 names it, the reference has no code).  top_n =
+    int(population_size * selection_rate) tournaments without replacement: max(2, ceil(tournament_rate * pool))
+    contestants drawn with rng.sample from the individuals still in the pool (ascending position), the best
+    ranked one (utils.py:332-351 ordering, ties to the lower position) survives and leaves the pool."""
+    import math
+    top_n = min(int(population_size * selection_rate), len(scores))
+    order = rank_best(scores, len(scores))
+    rank = {pos: r for r, pos in enumerate(order)}
+    pool = list(range(len(scores)))
+    keep = set()
+    for _ in range(top_n):
+        t = min(len(pool), max(2, math.ceil(tournament_rate * len(pool))))
+        winner = min(rng.sample(pool, t), key=rank.__getitem__)
+        keep.add(winner)
+        pool.remove(winner)
+    return keep
+
+
+def crossover_plan_variant(n_parents, n_rows, n_children, probability, copy_cut, rng=_pyrandom):
+    """crossover_plan with a crossover probability (PARITY UNPINNED, supplement table A3 c_prob): after the
+    reference's draws for a child (two choice(), retry on equal parents, randint) one rng.random(); at or above
+    ``probability`` the child is a copy of parent1 (cut = copy_cut, i.e. every row / cell from parent1)."""
+    if n_children > 0 and (n_parents < 2 or n_rows < 2):
+        raise ValueError("reference loops forever here (GA.py:285-290)")
+    plan = []
+    parents = range(n_parents)
+    while len(plan) < n_children:
+        a = rng.choice(parents)
+        b = rng.choice(parents)
+        if a == b:
+            continue
+        cut = rng.randint(1, n_rows - 1)
+        if rng.random() >= probability:
+            cut = copy_cut
+        plan.append((a, b, cut))
+    return plan
 
 
 # --------------------------------------------------------------------------- the loop (GA.py:443-545)
@@ -553,6 +605,13 @@ class Knobs:
         self.GAP_RATE = 0.05
         self.SELECTION_RATE = 0.5
         self.MUTATION_RATE = 0.25
+        # paper-style variants (extensions without reference code; the defaults are the reference's behaviour)
+        self.MUTATION_TILE = "worst"
+        self.MUTATION_PROBABILITY = 1.0
+        self.CROSSOVER_PROBABILITY = 1.0
+        self.SELECTION_SCHEME = "truncation"
+        self.TOURNAMENT_RATE = 0.25
+        self.ELITISM_PROBABILITY = 0.0
         self.__dict__.update(kw)
 
 
@@ -578,14 +637,25 @@ def ga_run(seqs, mode, sd, knobs=None, w=DEFAULT_W, rng=_pyrandom, qdtype=np.flo
         raise ValueError("AGENT_WINDOW_COLUMN is larger than the shortest sequence length.")  # GA.py:486-488
     for _ in range(kb.GA_ITERATIONS):
         mutation(pop, scores, mode, round(P * kb.MUTATION_RATE), kb.AGENT_WINDOW_ROW,
-                 kb.AGENT_WINDOW_COLUMN, sd, w, qdtype)
+                 kb.AGENT_WINDOW_COLUMN, sd, w, qdtype, kb.MUTATION_TILE, kb.MUTATION_PROBABILITY, rng)
         scores = evaluate()
-        keep = selection_keep(scores, mode, P, kb.SELECTION_RATE, fast=fast_pareto)
+        if kb.SELECTION_SCHEME == "tournament":
+            keep = tournament_keep(scores, mode, P, kb.SELECTION_RATE, kb.TOURNAMENT_RATE, rng)
+        else:
+            keep = selection_keep(scores, mode, P, kb.SELECTION_RATE, fast=fast_pareto)
         pop[:] = [b for i, b in enumerate(pop) if i in keep]
         scores = evaluate()
-        plan = crossover_plan(len(pop), len(pop[0]), P - len(pop), rng)
+        if kb.CROSSOVER_PROBABILITY < 1.0:
+            plan = crossover_plan_variant(len(pop), len(pop[0]), P - len(pop), kb.CROSSOVER_PROBABILITY, len(pop[0]), rng)
+        else:
+            plan = crossover_plan(len(pop), len(pop[0]), P - len(pop), rng)
         pop.extend(horizontal_child(pop[a], pop[b], c) for a, b, c in plan)
         scores = evaluate()
+        if kb.ELITISM_PROBABILITY > 0.0 and rng.random() < kb.ELITISM_PROBABILITY:
+            # elitism (PARITY UNPINNED, supplement table A3 e_prob): the hall of fame replaces the worst-ranked individual
+            import copy
+            pop[rank_best(scores, len(scores))[-1]] = copy.deepcopy(hof[0])
+            scores = evaluate()
     return decode(hof[0]), tuple(hof[1])
 
 

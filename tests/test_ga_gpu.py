@@ -31,7 +31,9 @@ def cfg():
     """config knobs restored after the test."""
     import config
     names = ["AGENT_WINDOW_ROW", "AGENT_WINDOW_COLUMN", "GA_ITERATIONS", "POPULATION_SIZE", "CLONE_RATE", "GAP_RATE",
-             "SELECTION_RATE", "MUTATION_RATE", "MATCH_REWARD", "MISMATCH_PENALTY", "GAP_PENALTY", "CROSSOVER_KIND"]
+             "SELECTION_RATE", "MUTATION_RATE", "MATCH_REWARD", "MISMATCH_PENALTY", "GAP_PENALTY", "CROSSOVER_KIND",
+             "MUTATION_TILE", "MUTATION_PROBABILITY", "CROSSOVER_PROBABILITY", "SELECTION_SCHEME", "TOURNAMENT_RATE",
+             "ELITISM_PROBABILITY"]
     saved = {n: getattr(config, n) for n in names}
     yield config
     for n, v in saved.items():
@@ -531,6 +533,50 @@ def test_ga_run_against_oracle_larger_population(gpu, weight_files, cfg, dataset
             assert mine["scores"] == [list(s) for s in ref[1]]
             assert mine["hof"] == ref[2] and mine["hof_score"] == list(ref[3])
         assert out == oout
+
+
+PAPER_VARIANTS = [
+    {"MUTATION_TILE": "random"},
+    {"MUTATION_PROBABILITY": 0.85},
+    {"CROSSOVER_PROBABILITY": 0.5},
+    {"SELECTION_SCHEME": "tournament", "TOURNAMENT_RATE": 0.25},
+    {"ELITISM_PROBABILITY": 0.4},
+    {"MUTATION_TILE": "random", "MUTATION_PROBABILITY": 0.85, "CROSSOVER_PROBABILITY": 0.5,
+     "SELECTION_SCHEME": "tournament", "TOURNAMENT_RATE": 0.25, "ELITISM_PROBABILITY": 0.4, "SELECTION_RATE": 0.45},
+]
+
+
+@pytest.mark.parametrize("variant", PAPER_VARIANTS, ids=lambda v: "+".join(sorted(v)))
+def test_paper_variants_against_oracle(gpu, weight_files, cfg, datasets_json, variant):
+    """The GA variants of the paper's supplement (tables A3 / A5: random-tile mutation, mutation / crossover /
+    elitism probabilities, tournament selection) - extensions without reference code, defined in config.py and
+    restated by the oracle: every pass of GA.run (scores, hall of fame) and the final alignment equal the
+    oracle's on the same `random` stream, 'sp' and 'mo'."""
+    name, sd = weight_files[(3, 30)]
+    seqs = datasets_json["synthetic_dataset_6x60bp"]["test3"]
+    for mode in ("sp", "mo"):
+        knobs = {"AGENT_WINDOW_ROW": 3, "AGENT_WINDOW_COLUMN": 30, "GA_ITERATIONS": 3, "POPULATION_SIZE": 60,
+                 "CLONE_RATE": 0.25, "GAP_RATE": 0.05, "SELECTION_RATE": 0.5, "MUTATION_RATE": 0.5}
+        knobs.update(variant)
+        tr = {"knobs": knobs, "seed": 29, "seqs": seqs, "mode": mode}
+        out, log, _ = run_facade(tr, cfg, name)
+        random.seed(29)
+        olog = []
+        oout, _ = O.ga_run(seqs, mode, sd, O.Knobs(**knobs), log=olog, fast_pareto=True)
+        assert len(log) == len(olog), (mode, len(log), len(olog))
+        for k, (mine, ref) in enumerate(zip(log, olog)):
+            assert mine["scores"] == [list(s) for s in ref[1]], (mode, k)
+            assert mine["hof"] == ref[2] and mine["hof_score"] == list(ref[3]), (mode, k)
+        assert out == oout
+    # both sides drew the same numbers in the same order: the generator ends in the same state
+    knobs = {"AGENT_WINDOW_ROW": 3, "AGENT_WINDOW_COLUMN": 30, "GA_ITERATIONS": 1, "POPULATION_SIZE": 24,
+             "CLONE_RATE": 0.25, "GAP_RATE": 0.05, "SELECTION_RATE": 0.5, "MUTATION_RATE": 0.5}
+    knobs.update(variant)
+    run_facade({"knobs": knobs, "seed": 5, "seqs": seqs, "mode": "sp"}, cfg, name)
+    after_facade = random.getstate()
+    random.seed(5)
+    O.ga_run(seqs, "sp", sd, O.Knobs(**knobs), fast_pareto=True)
+    assert random.getstate() == after_facade
 
 
 def test_run_validation_errors(gpu, weight_files, cfg):

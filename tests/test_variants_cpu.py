@@ -1,0 +1,74 @@
+"""The oracle's restatement of the paper-style GA variants (supplement tables A3 / A5; extensions without reference
+code, PARITY UNPINNED): what each knob does, and that the defaults draw nothing from `random` beyond the reference's
+own draws (the recorded reference traces are replayed with them in test_oracle_pins.py)."""
+import copy
+import random
+
+import ga_oracle as O
+
+
+def _scores(n, rng, mode):
+    if mode == "sp":
+        return [(i, rng.randint(-40, 40)) for i in range(n)]
+    return [(i, rng.randint(-40, 40), rng.randint(0, 20) / 20) for i in range(n)]
+
+
+def test_tournament_keeps_top_n_distinct_and_prefers_the_better_ranked():
+    rng = random.Random(1)
+    for mode in ("sp", "mo"):
+        sc = _scores(150, rng, mode)
+        keep = O.tournament_keep(sc, mode, 150, 0.45, 0.25, random.Random(2))
+        assert len(keep) == int(150 * 0.45) and keep <= set(range(150))
+        order = O.rank_best(sc, 150)
+        rank = {p: r for r, p in enumerate(order)}
+        # a quarter of the pool per tournament: the survivors are far better ranked than a uniform draw would be
+        assert sum(rank[p] for p in keep) / len(keep) < 0.6 * (149 / 2)
+    # the whole pool in every tournament = truncation by rank
+    sc = _scores(40, rng, "sp")
+    assert O.tournament_keep(sc, "sp", 40, 0.5, 1.0, random.Random(3)) == set(O.rank_best(sc, 20))
+
+
+def test_crossover_probability_zero_copies_parent1_and_one_equals_the_reference_plan():
+    plan = O.crossover_plan_variant(10, 6, 50, 0.0, 6, random.Random(4))
+    assert all(c == 6 for _, _, c in plan)
+    p1 = [[1, 2, 3]] * 6
+    p2 = [[4, 4, 4]] * 6
+    assert O.horizontal_child(p1, p2, 6) == p1
+    a, b = random.Random(5), random.Random(5)
+    with_prob = O.crossover_plan_variant(10, 6, 50, 1.0, 6, a)
+    plain = O.crossover_plan(10, 6, 50, b)
+    assert len(with_prob) == len(plain) == 50
+    # probability 1 keeps every cut inside the board (one extra random() per child, so the streams differ)
+    assert all(1 <= c <= 5 for _, _, c in with_prob)
+
+
+def test_mutation_probability_and_random_tile():
+    rng = random.Random(6)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(60)) for _ in range(6)]
+    sd = O.synth_qnet_weights(3, 30, 7)
+    pop = O.generate_population(seqs, 12, 0.25, 0.05, random.Random(7))
+    sc = O.fitness_scores(pop, "sp")
+    before = copy.deepcopy(pop)
+    O.mutation(pop, sc, "sp", 6, 3, 30, sd, probability=0.0, rng=random.Random(8))
+    assert pop == before                                    # nobody mutates, and nothing but random() was drawn
+    r = random.Random(9)
+    O.mutation(pop, sc, "sp", 6, 3, 30, sd, tile_choice="random", rng=r)
+    changed = [i for i in range(12) if pop[i] != before[i]]
+    assert changed and set(changed) <= set(O.rank_best(sc, 6))
+    probe = random.Random(9)
+    tiles = O.tile_grid(6, 60, 3, 30)
+    drawn = [tiles[probe.randrange(len(tiles))] for _ in range(6)]
+    assert r.getstate() == probe.getstate() and all(t in tiles for t in drawn)     # one randrange per selected individual
+
+
+def test_defaults_are_the_reference_loop():
+    rng = random.Random(10)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(30)) for _ in range(3)]
+    sd = O.synth_qnet_weights(3, 30, 7)
+    a, b = random.Random(11), random.Random(11)
+    kb = O.Knobs(POPULATION_SIZE=8, GA_ITERATIONS=2)
+    out_a = O.ga_run(seqs, "mo", sd, kb, rng=a)
+    explicit = O.Knobs(POPULATION_SIZE=8, GA_ITERATIONS=2, MUTATION_TILE="worst", MUTATION_PROBABILITY=1.0,
+                       CROSSOVER_PROBABILITY=1.0, SELECTION_SCHEME="truncation", ELITISM_PROBABILITY=0.0)
+    out_b = O.ga_run(seqs, "mo", sd, explicit, rng=b)
+    assert out_a == out_b and a.getstate() == b.getstate()
