@@ -45,7 +45,7 @@ CROSSOVER_KIND = "horizontal"
 
 # --- B200 build only: the GA variants of the paper's supplement (tables A3 / A5: tournament selection %, crossover
 # probability, elitism probability, random-tile mutation). The reference checkout has no code for any of them, so
-# their definitions are this build's (GA.py docstrings, oracle/ga_oracle.py restates them); the defaults below are
+# their definitions are this build's (GA.py docstrings; the test checker restates them); the defaults below are
 # the reference's behaviour and consume no extra `random` draws.
 MUTATION_TILE = "worst"          # 'worst' (utils.calculate_worst_fitted_sub_board) | 'random' (uniform over the tile lattice)
 MUTATION_PROBABILITY = 1.0       # a selected individual mutates only when random.random() < this
