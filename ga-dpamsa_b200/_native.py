@@ -57,9 +57,9 @@ SIGNATURES = {
     "gad_crossover_from": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "gad_crossover_peer": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
     "gad_crossover": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
-    "gad_pass_scatter": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
-    "gad_pass_decide": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp,
-                                c_int, c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "gad_pass_scatter": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
+    "gad_pass_decide": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_int,
+                                c_int, c_vp, c_int, c_int, c_vp, ctypes.c_size_t, c_vp]),
     "gad_mt_crossover_plan_host": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "gad_mt_population_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_int]),
     "gad_mt_population_shard_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,

@@ -442,7 +442,14 @@ struct PassPeer {                    // all null / zero for a population that li
     long long cap1;                  // table row length (int32 [2][5][cap1])
     int rank, world;
     int hof_pitch;                   // row pitch of the hall-of-fame board inside the pass block
+    long long stage_off, cap_s;      // staging area (0 = none): int32 [2][world][4 + 4 * cap_s], see gad_pass_scatter
 };
+
+// one sender's block of a pass in a receiver's staging area: header {count, -, -, -} | sp | em | al | logical index
+__device__ __forceinline__ int *stage_block(char *base, const PassPeer &pp, int parity, int sender)
+{
+    return reinterpret_cast<int *>(base + pp.stage_off) + ((size_t)parity * pp.world + sender) * (size_t)(4 + 4 * pp.cap_s);
+}
 
 // words of the flags area of a pass block (int32 [64])
 enum { PF_ARRIVE = 0, PF_BOARD = 16, PF_SEQ = 32, PF_SCATTER_TICKET = 33, PF_DECIDE_SYNC = 34, PF_ERROR = 36 };
@@ -505,7 +512,56 @@ struct DecideView {                  // where this launch finds its scores, flag
     const int *sp, *em, *al, *owner, *slot;
     int *flags, *sync;
     int seq;
+    int *table;                      // sharded: this pass's table (written here when the scores arrive staged)
+    char *mine;                      // sharded: this rank's pass block
 };
+
+// The same two scans over STAGED scores (gad_pass_scatter with a staging area): every sender left its scores as
+// contiguous arrays with the logical index beside them. The second scan also files every tuple under its logical
+// index in this pass's table - the arrays the ranking and the selection read next - with its owner and slot.
+__device__ __forceinline__ Range range_scan_staged(const DecideView &v, const PassPeer &pp, const int *hofp,
+                                                   long long first, long long step)
+{
+    Range g;
+    range_clear(g);
+    for (int r = 0; r < pp.world; ++r) {
+        const int *blk = stage_block(v.mine, pp, v.seq & 1, r);
+        const int n_r = blk[0];
+        const int *s_sp = blk + 4, *s_em = s_sp + pp.cap_s, *s_al = s_em + pp.cap_s;
+        for (long long i = first; i < n_r; i += step) {
+            const u64 c = (u64)__double_as_longlong(column_score(s_em[i], s_al[i]));
+            range_merge(g, s_sp[i], s_sp[i], c, c);
+        }
+    }
+    if (hofp && first == 0) {
+        const u64 c = (u64)__double_as_longlong(column_score(hofp[3], hofp[4]));
+        range_merge(g, hofp[2], hofp[2], c, c);
+    }
+    return g;
+}
+
+__device__ __forceinline__ void best_scan_staged(const DecideView &v, const PassPeer &pp, const int *hofp, long long P,
+                                                 long long first, long long step, int mode, const Range &g, double &bk, int &bi)
+{
+    bk = 0.0;
+    bi = 0x7fffffff;
+    int *t_sp = v.table, *t_em = t_sp + pp.cap1, *t_al = t_em + pp.cap1, *t_owner = t_al + pp.cap1, *t_slot = t_owner + pp.cap1;
+    for (int r = 0; r < pp.world; ++r) {
+        const int *blk = stage_block(v.mine, pp, v.seq & 1, r);
+        const int n_r = blk[0];
+        const int *s_sp = blk + 4, *s_em = s_sp + pp.cap_s, *s_al = s_em + pp.cap_s, *s_gi = s_al + pp.cap_s;
+        for (long long i = first; i < n_r; i += step) {
+            const int s2 = s_sp[i], e2 = s_em[i], a2 = s_al[i], gi = s_gi[i];
+            t_sp[gi] = s2;
+            t_em[gi] = e2;
+            t_al[gi] = a2;
+            t_owner[gi] = r;
+            t_slot[gi] = (int)i;
+            best_merge(bk, bi, make_key(mode, s2, e2, a2, g.lo, g.hi, g.clo, g.chi), gi);
+        }
+    }
+    if (hofp && first == 0) best_merge(bk, bi, make_key(mode, hofp[2], hofp[3], hofp[4], g.lo, g.hi, g.clo, g.chi), (int)P);
+}
 
 // Sharded: wait for every rank's arrival flag of this pass and take the pass's table. Whole block.
 __device__ __forceinline__ void decide_enter(DecideView &v, const PassPeer &pp)
@@ -513,14 +569,18 @@ __device__ __forceinline__ void decide_enter(DecideView &v, const PassPeer &pp)
     v.owner = v.slot = nullptr;
     v.flags = nullptr;
     v.seq = 0;
+    v.table = nullptr;
+    v.mine = nullptr;
     if (!pp.peer_base) return;
     char *mine = reinterpret_cast<char *>(pp.peer_base[pp.rank]);
+    v.mine = mine;
     v.flags = reinterpret_cast<int *>(mine + pp.flags_off);
     v.sync = v.flags + PF_DECIDE_SYNC;
     v.seq = *reinterpret_cast<volatile int *>(v.flags + PF_SEQ);              // set by this pass's scatter kernel
     if ((int)threadIdx.x < pp.world) wait_flag(v.flags + PF_ARRIVE + threadIdx.x, v.seq, v.flags + PF_ERROR);
     __syncthreads();
-    const int *table = reinterpret_cast<const int *>(mine + pp.table_off) + (size_t)(v.seq & 1) * 5 * pp.cap1;
+    int *table = reinterpret_cast<int *>(mine + pp.table_off) + (size_t)(v.seq & 1) * 5 * pp.cap1;
+    v.table = table;
     v.sp = table;
     v.em = table + pp.cap1;
     v.al = table + 2 * pp.cap1;
@@ -591,7 +651,9 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
     Range g;
     range_clear(g);
     if (mode == GAD_MODE_MO) {
-        g = range_fold_block(range_scan(v.sp, v.em, v.al, hofp, P, n, first, step), sh, cx);
+        const bool staged = pp.peer_base != nullptr && pp.stage_off != 0;
+        g = range_fold_block(staged ? range_scan_staged(v, pp, hofp, first, step)
+                                    : range_scan(v.sp, v.em, v.al, hofp, P, n, first, step), sh, cx);
         if (gridDim.x > 1) {
             if (tid == 0) {
                 w.part_lo[blockIdx.x] = g.lo;
@@ -614,7 +676,8 @@ hof_decide_kernel(const int *__restrict__ sp_in, const int *__restrict__ em_in, 
     // ---- phase B: keys and the first maximum
     double bk;
     int bi;
-    best_scan(v.sp, v.em, v.al, hofp, P, n, first, step, mode, g, bk, bi);
+    if (pp.peer_base != nullptr && pp.stage_off != 0) best_scan_staged(v, pp, hofp, P, first, step, mode, g, bk, bi);
+    else best_scan(v.sp, v.em, v.al, hofp, P, n, first, step, mode, g, bk, bi);
     best_fold_block(bk, bi, sh, cx);
     if (tid == 0) {
         sh.last = true;
@@ -881,7 +944,29 @@ pass_scatter_kernel(PassPeer pp, const int32_t *__restrict__ sp, const int32_t *
     int *flags = reinterpret_cast<int *>(reinterpret_cast<char *>(pp.peer_base[pp.rank]) + pp.flags_off);
     const int seq = *reinterpret_cast<volatile int *>(flags + PF_SEQ) + 1;       // this pass
     const size_t toff = (size_t)pp.table_off + (size_t)(seq & 1) * 5 * pp.cap1 * sizeof(int32_t);
-    const long long total = n_local * pp.world;
+    if (pp.stage_off != 0) {
+        // staged: this rank's block in every receiver's staging area, as contiguous arrays - 16 bytes per store, whole
+        // lines over NVLink instead of 4-byte stores strided by the logical index; the receiver files them itself
+        const long long quads = (n_local + 3) >> 2;
+        const long long total = quads * 4 * pp.world;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+            const long long q = t % quads;                 // consecutive threads: consecutive quads of one array
+            const int k = (int)((t / quads) & 3), r = (int)(t / (quads * 4));
+            int *blk = stage_block(reinterpret_cast<char *>(pp.peer_base[r]), pp, seq & 1, pp.rank);
+            int *dst = blk + 4 + (size_t)k * pp.cap_s + 4 * q;
+            int v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long i = 4 * q + u;
+                v4[u] = i >= n_local ? 0 : k == 0 ? sp[i] : k == 1 ? em[i] : k == 2 ? al[i] : (int)gidx[i];
+            }
+            *reinterpret_cast<int4 *>(dst) = make_int4(v4[0], v4[1], v4[2], v4[3]);
+            if (q == 0 && k == 0) blk[0] = (int)n_local;
+        }
+        if (n_local == 0 && blockIdx.x == 0 && (int)threadIdx.x < pp.world)
+            stage_block(reinterpret_cast<char *>(pp.peer_base[threadIdx.x]), pp, seq & 1, pp.rank)[0] = 0;
+    }
+    const long long total = pp.stage_off != 0 ? 0 : n_local * pp.world;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long i = t / pp.world;              // consecutive threads: the peers of one individual
         const int r = (int)(t - i * pp.world);
@@ -919,9 +1004,12 @@ int check_pass_block(const char *who, const void *d_peer_base, int64_t flags_off
 }  // namespace
 
 extern "C" int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t cap1,
-                                const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, const int64_t *d_gidx,
-                                int64_t n_local, int rank, int world, void *stream)
+                                int64_t stage_off, int64_t cap_s, const int32_t *d_sp, const int32_t *d_em,
+                                const int32_t *d_al, const int64_t *d_gidx, int64_t n_local, int rank, int world, void *stream)
 {
+    GAD_REQUIRE(stage_off >= 0 && stage_off % 16 == 0 && (stage_off == 0 || (cap_s >= n_local && cap_s % 4 == 0)),
+                "gad_pass_scatter: bad staging area (offset %lld, capacity %lld, %lld local individuals)", (long long)stage_off,
+                (long long)cap_s, (long long)n_local);
     int rc = check_pass_block("gad_pass_scatter", d_peer_base, flags_off, table_off, 0, cap1, rank, world);
     if (rc) return rc;
     GAD_REQUIRE(n_local >= 0 && (n_local == 0 || (d_sp && d_em && d_al && d_gidx)), "gad_pass_scatter: null pointer");
@@ -932,6 +1020,8 @@ extern "C" int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int6
     pp.cap1 = cap1;
     pp.rank = rank;
     pp.world = world;
+    pp.stage_off = stage_off;
+    pp.cap_s = cap_s;
     long long blocks = (n_local * world + 255) / 256;       // a rank without individuals still raises its flag
     if (blocks < 1) blocks = 1;
     if (blocks > 4 * GAD_NUM_SMS) blocks = 4 * GAD_NUM_SMS;
@@ -942,10 +1032,12 @@ extern "C" int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int6
 }
 
 extern "C" int gad_pass_decide(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t hof_off,
-                               int64_t cap1, int hof_pitch, int64_t n, int mode, int hof_valid, const uint8_t *d_boards,
-                               int R, int stride, int32_t *d_hof, int rank, int world, void *d_ws, size_t ws_bytes,
-                               void *stream)
+                               int64_t cap1, int64_t stage_off, int64_t cap_s, int hof_pitch, int64_t n, int mode,
+                               int hof_valid, const uint8_t *d_boards, int R, int stride, int32_t *d_hof, int rank,
+                               int world, void *d_ws, size_t ws_bytes, void *stream)
 {
+    GAD_REQUIRE(stage_off >= 0 && stage_off % 16 == 0 && (stage_off == 0 || (cap_s >= 1 && cap_s % 4 == 0)),
+                "gad_pass_decide: bad staging area");
     int rc = check_pass_block("gad_pass_decide", d_peer_base, flags_off, table_off, hof_off, cap1, rank, world);
     if (rc) return rc;
     GAD_REQUIRE(d_boards && d_hof, "gad_pass_decide: null device pointer");
@@ -963,6 +1055,8 @@ extern "C" int gad_pass_decide(const void *d_peer_base, int64_t flags_off, int64
     pp.rank = rank;
     pp.world = world;
     pp.hof_pitch = hof_pitch;
+    pp.stage_off = stage_off;
+    pp.cap_s = cap_s;
     // the kernel finds its table (pass parity), its flags and the sync words inside the pass block
     if ((rc = launch_decide(nullptr, nullptr, nullptr, n, mode, hof_valid ? 1 : 0, d_boards, R, stride, w, nullptr, nullptr,
                             d_hof, pp, gad_stream(stream))))

@@ -593,9 +593,15 @@ class DeviceBackend:
             cap1 = max(cap1, self._blk_cap1)
             pitch = -(-max(2 * p.stride, self._blk_pitch) // 16) * 16
             table_bytes = -(-(2 * 5 * cap1 * 4) // 256) * 256
-            t = self._symm.empty(self.FLAGS_BYTES + table_bytes + self.R * pitch, dtype=torch.uint8, device=self.device)
+            hof_bytes = -(-(self.R * pitch) // 256) * 256
+            # staging area: per pass parity and sender a header and four contiguous int32 arrays (scores + logical
+            # index) of up to cap_s entries; GAD_SHARDED_SCATTER=direct keeps the stores at the logical index
+            staged = os.environ.get("GAD_SHARDED_SCATTER", "staged") != "direct"
+            cap_s = -(-cap1 // 4) * 4 if staged else 0
+            stage_bytes = 2 * world * (16 + 16 * cap_s) if staged else 0
+            t = self._symm.empty(self.FLAGS_BYTES + table_bytes + hof_bytes + stage_bytes, dtype=torch.uint8, device=self.device)
             t.zero_()
-            board = t[self.FLAGS_BYTES + table_bytes:].view(self.R, pitch)
+            board = t[self.FLAGS_BYTES + table_bytes:self.FLAGS_BYTES + table_bytes + self.R * pitch].view(self.R, pitch)
             board.fill_(5)
             if self._blk is not None and self._blk_R == self.R:                 # keep the record's board
                 board[:, :self._blk_pitch].copy_(self.hof_board)
@@ -603,6 +609,8 @@ class DeviceBackend:
             self._blk, self._blk_hdl, self._blk_cap1, self._blk_pitch, self._blk_R = t, hdl, cap1, pitch, self.R
             self._blk_table_off = self.FLAGS_BYTES
             self._blk_hof_off = self.FLAGS_BYTES + table_bytes
+            self._blk_stage_off = self.FLAGS_BYTES + table_bytes + hof_bytes if staged else 0
+            self._blk_cap_s = cap_s
             self._blk_peer = torch.tensor([int(b) for b in hdl.buffer_ptrs[:world]], dtype=torch.int64, device=self.device)
             self._blk_tables = t[self.FLAGS_BYTES:self.FLAGS_BYTES + 2 * 5 * cap1 * 4].view(torch.int32).view(2, 5, cap1)
             self.hof_board = board
@@ -616,11 +624,12 @@ class DeviceBackend:
         nat, p = self.nat, self.pop
         st = nat.current_stream_ptr()
         gidx = gidx.contiguous()
-        nat.call("gad_pass_scatter", nat.ptr(self._blk_peer), 0, self._blk_table_off, self._blk_cap1, nat.ptr(sp),
-                 nat.ptr(em), nat.ptr(al), nat.ptr(gidx), n_loc, rank, world, st)
+        nat.call("gad_pass_scatter", nat.ptr(self._blk_peer), 0, self._blk_table_off, self._blk_cap1, self._blk_stage_off,
+                 self._blk_cap_s, nat.ptr(sp), nat.ptr(em), nat.ptr(al), nat.ptr(gidx), n_loc, rank, world, st)
         rk = self._ranker(n)
         nat.call("gad_pass_decide", nat.ptr(self._blk_peer), 0, self._blk_table_off, self._blk_hof_off, self._blk_cap1,
-                 self._blk_pitch, n, MODE_ID[mode], int(bool(hof_valid)), nat.ptr(p.cur.boards), self.R, p.stride,
+                 self._blk_stage_off, self._blk_cap_s, self._blk_pitch, n, MODE_ID[mode], int(bool(hof_valid)),
+                 nat.ptr(p.cur.boards), self.R, p.stride,
                  nat.ptr(hof_rec), rank, world, nat.ptr(rk.ws), rk.ws.numel(), st)
         self._blk_seq += 1
         return self._blk_tables[self._blk_seq & 1]

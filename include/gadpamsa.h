@@ -183,17 +183,25 @@ int gad_crossover_peer(const uint8_t *const *d_peer_boards, const int32_t *const
  * int32 [2][5][cap1] = {sp, em, al, owner rank, slot on the owner} indexed by LOGICAL index at table_off, and the
  * hall-of-fame board uint8 [R][hof_pitch] at hof_off. d_peer_base = device array of `world` int64: the address of
  * every rank's pass block as mapped into this process.
- * gad_pass_scatter: stores the scores of the n_local local individuals (logical indices d_gidx) into EVERY rank's
- * table of this pass over NVLink, then raises this rank's arrival flag on every rank.
+ * Staging area (stage_off != 0): int32 [2][world][4 + 4 * cap_s] at stage_off - per pass parity and SENDER a header
+ * {count, -, -, -} and the contiguous arrays sp | em | al | logical index (cap_s = capacity per sender, a multiple of
+ * 4, the same on every rank).
+ * gad_pass_scatter: with a staging area, copies the scores and logical indices (d_gidx) of the n_local local
+ * individuals as contiguous 16-byte stores into this rank's block of EVERY rank's staging area over NVLink; without
+ * one (stage_off = 0) it stores every tuple at its logical index in every rank's table directly (4-byte stores
+ * strided by the placement: several times slower from 4 ranks on). Then it raises this rank's arrival flag on
+ * every rank.
  * gad_pass_decide: waits for all arrival flags, decides like gad_hof_update on the n gathered scores (identically
- * on every rank), writes the record d_hof; the rank that owns the winner stores its board into every rank's pass
+ * on every rank) - reading the staged blocks and filing every tuple under its logical index in this pass's table
+ * on the way - writes the record d_hof; the rank that owns the winner stores its board into every rank's pass
  * block, the others wait for it. Nothing is read back by the host; a flag that does not arrive within 20 s traps. */
-int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t cap1, const int32_t *d_sp,
-                     const int32_t *d_em, const int32_t *d_al, const int64_t *d_gidx, int64_t n_local, int rank,
-                     int world, void *stream);
+int gad_pass_scatter(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t cap1, int64_t stage_off,
+                     int64_t cap_s, const int32_t *d_sp, const int32_t *d_em, const int32_t *d_al, const int64_t *d_gidx,
+                     int64_t n_local, int rank, int world, void *stream);
 int gad_pass_decide(const void *d_peer_base, int64_t flags_off, int64_t table_off, int64_t hof_off, int64_t cap1,
-                    int hof_pitch, int64_t n, int mode, int hof_valid, const uint8_t *d_boards, int R, int stride,
-                    int32_t *d_hof, int rank, int world, void *d_ws, size_t ws_bytes, void *stream);
+                    int64_t stage_off, int64_t cap_s, int hof_pitch, int64_t n, int mode, int hof_valid,
+                    const uint8_t *d_boards, int R, int stride, int32_t *d_hof, int rank, int world, void *d_ws,
+                    size_t ws_bytes, void *stream);
 
 /* CPython-compatible MT19937 replay (random.getstate()[1] = 624 words + position, in/out):
  * the (parent1, parent2, cut) triples of GA.py:281-293 for n_children children. h_widths (one
