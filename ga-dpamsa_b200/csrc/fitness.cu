@@ -1098,7 +1098,10 @@ int launch_fitness_tma(uint8_t *boards, int32_t *rowlen, long long P, int R, int
     g.NB = nb;
     g.stage_bytes = (nb * board_bytes + 127) / 128 * 128;
     // tuning knobs (A/B): CTAs per SM, shared memory and consumer threads per CTA
-    static const int ctas_per_sm = [] { const char *e = getenv("GAD_FT_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+    static const int ctas_env = [] { const char *e = getenv("GAD_FT_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+    // a launch that takes the hall-of-fame decision meets at a grid barrier: every CTA must be resident, and with the
+    // tail's static shared memory only one CTA fits an SM
+    const int ctas_per_sm = fh.hof != nullptr ? 1 : ctas_env;
     static const int smem_kb = [] {                                  // + 34 KB of static shared memory (FtTail, DecideShared)
         const char *e = getenv("GAD_FT_SMEM_KB");
         return e && atoi(e) > 0 ? (atoi(e) < 190 ? atoi(e) : 190) : 190;
