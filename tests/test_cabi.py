@@ -31,6 +31,42 @@ def test_binding_table_matches_header(native_lib):
     assert lib.gad_version() >= 100
 
 
+def header_prototypes():
+    """{name: [parameter declarations]} of every gad_* function declared in include/*.h."""
+    protos = {}
+    for hdr in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+        for m in re.finditer(r"\b(gad_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+            params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+            protos[m.group(1)] = [] if params in (["void"], [""]) else params
+    return protos
+
+
+def test_binding_arity_and_kinds_match_the_header(native_lib):
+    """Every ctypes signature has as many arguments as the C prototype, pointers where the header has pointers,
+    64-bit integers where it has int64_t / size_t, and floats where it has float - an ABI drift between
+    include/gadpamsa.h and _native.py would otherwise only show on the GPU box."""
+    protos = header_prototypes()
+    assert set(protos) == set(native_lib.SIGNATURES)
+    pointer_types = (ctypes.c_void_p, ctypes.c_char_p)
+    for name, params in sorted(protos.items()):
+        restype, argtypes = native_lib.SIGNATURES[name]
+        assert len(argtypes) == len(params), (name, len(argtypes), params)
+        for decl, ct in zip(params, argtypes):
+            is_ptr = "*" in decl
+            ct_is_ptr = ct in pointer_types or hasattr(ct, "contents") or getattr(ct, "_type_", None) == "P"
+            assert is_ptr == ct_is_ptr, (name, decl, ct)
+            if not is_ptr:
+                if re.search(r"\b(int64_t|size_t|long long)\b", decl):
+                    assert ctypes.sizeof(ct) == 8, (name, decl, ct)
+                elif re.search(r"\bfloat\b", decl):
+                    assert ct is ctypes.c_float, (name, decl, ct)
+                elif re.search(r"\bdouble\b", decl):
+                    assert ct is ctypes.c_double, (name, decl, ct)
+                else:
+                    assert ctypes.sizeof(ct) == 4, (name, decl, ct)
+
+
 def test_library_has_sm100a_code(native_lib):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", native_lib.LIB_PATH], capture_output=True, text=True).stdout
