@@ -1000,6 +1000,16 @@ def main():
                 gen["duplicate_free_workload"]["note"] = ("CLONE_RATE = 0 and a different random base per individual: every "
                                                           "episode is distinct, the Q-net kernels run full batches")
                 line["parity"] = parity_single_gpu(args.workload)
+                if args.workload == "c3" and os.environ.get("GAD_BENCH_C4", "1") != "0":
+                    # the N = 1 point of the c4 strong-scaling curve the N > 1 lines carry (BASELINE configs[3]:
+                    # 262 144 individuals of 20x200, 'cs', 3x30 agent); an extra - a failure here must not cost the line
+                    try:
+                        torch.cuda.empty_cache()
+                        c4 = measure_generations("c4", 3, 4, world, rank, weak=False, with_extras=False)
+                        c4.pop("_hof_board", None)
+                        line["strong_scaling_c4"] = c4
+                    except Exception as exc:             # pragma: no cover
+                        line["strong_scaling_c4"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
             else:
                 line["parity"] = parity_sharded(args.workload, world, rank)
                 torch.cuda.empty_cache()
