@@ -139,7 +139,11 @@ int gad_hof_update(const uint8_t *d_boards, const int32_t *d_sp, const int32_t *
  * same results. For populations the TMA-staged kernel takes (boards up to 256 columns, 2 048+ individuals, 16-byte
  * aligned) it is ONE launch: the CTAs that scored the boards take the hall-of-fame decision in their tail (per-CTA
  * score ranges, one grid barrier, keys of the CTA's own boards, last CTA commits); otherwise the two launches.
- * GAD_FITNESS_FUSED_HOF=0 forces the two launches (A/B). Workspace: gad_workspace_bytes(P). */
+ * GAD_FITNESS_FUSED_HOF=0 forces the two launches (A/B). Workspace: gad_workspace_bytes(P).
+ * The one-launch form meets at a grid barrier, so all of its CTAs (one per SM) must become resident: do not run two
+ * such launches concurrently on different streams of one device (each would hold some SMs and wait for the rest;
+ * the barrier traps after 2 s instead of hanging). Launches on one stream, CUDA graphs and programmatic dependent
+ * launch are fine. */
 int gad_fitness_pass(uint8_t *d_boards, int32_t *d_rowlen, int64_t P, int R, int stride, int width_hint,
                      int match, int mismatch, int gap, int32_t *d_sp, int32_t *d_em, int32_t *d_al,
                      int64_t *d_max_al, int mode, uint8_t *d_hof_board, int32_t *d_hof, int hof_valid,
