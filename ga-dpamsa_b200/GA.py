@@ -397,25 +397,14 @@ class GA:
     def _plan_with_probability(n_parents, n_rows, n_children, probability, widths, kind):
         """Extension (supplement table A3 'c_prob'; no reference code): the reference's draws for every child
         (GA.py:281-293), then one random.random(); at or above `probability` the child is a copy of parent1 (a cut
-        past the last row / cell). Drawn in python: meant for populations of the paper's size."""
-        if n_children > 0 and (n_parents < 2 or n_rows < 2):
-            raise ValueError("crossover needs at least two survivors and two rows (the reference loops forever, GA.py:285-290)")
+        past the last row / cell). Drawn by the library's replay of CPython's generator
+        (gad_mt_crossover_plan_prob_host), like the plain plan."""
         plan = np.empty((n_children, 3), dtype=np.int32)
-        parents = range(n_parents)
-        c = 0
-        while c < n_children:
-            a = random.choice(parents)
-            b = random.choice(parents)
-            if a == b:
-                continue
-            if kind == 0:
-                cut, copy_cut = random.randint(1, n_rows - 1), n_rows
-            else:
-                cut, copy_cut = random.randint(1, int(min(widths[a], widths[b])) - 1), 1 << 20
-            if random.random() >= probability:
-                cut = copy_cut
-            plan[c] = (a, b, cut)
-            c += 1
+        state, meta = _mt_state()
+        nat.call("gad_mt_crossover_plan_prob_host", state.ctypes.data, n_parents, n_rows, n_children,
+                 None if kind == 0 else widths.ctypes.data, float(probability), n_rows if kind == 0 else 1 << 20,
+                 plan.ctypes.data)
+        _mt_restore(state, meta)
         return plan
 
     def _elitism(self):

@@ -51,6 +51,13 @@ struct MT {
         return y;
     }
 
+    // Random.random(): 53 bits from two words, (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53
+    double random53()
+    {
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+    }
+
     // Random._randbelow_with_getrandbits for 0 < n < 2^32: k = n.bit_length(); draw getrandbits(k) until < n
     uint32_t randbelow(uint32_t n)
     {
@@ -99,8 +106,28 @@ void emit_row(uint8_t *row, const uint8_t *seq, int len0, int ng, const int32_t 
 
 // GA.py:281-293: while children are missing: p1 = choice(pop), p2 = choice(pop); same object -> retry;
 // cut = randint(1, rows - 1). Vertical (h_widths != NULL): cut = randint(1, min(width1, width2) - 1).
+static int crossover_plan_impl(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
+                               const int32_t *h_widths, bool with_probability, double probability, int copy_cut,
+                               int32_t *h_plan);
+
 extern "C" int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
                                           const int32_t *h_widths, int32_t *h_plan)
+{
+    return crossover_plan_impl(mt_state, n_parents, n_rows, n_children, h_widths, false, 1.0, 0, h_plan);
+}
+
+// The same plan with a crossover probability (an extension: the paper's supplement names c_prob, the reference has no
+// code for it): after the draws of a child one random.random(); at or above `probability` the child's cut becomes
+// copy_cut (a cut past the last row / cell: the child is a copy of parent1).
+extern "C" int gad_mt_crossover_plan_prob_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
+                                               const int32_t *h_widths, double probability, int copy_cut, int32_t *h_plan)
+{
+    return crossover_plan_impl(mt_state, n_parents, n_rows, n_children, h_widths, true, probability, copy_cut, h_plan);
+}
+
+static int crossover_plan_impl(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
+                               const int32_t *h_widths, bool with_probability, double probability, int copy_cut,
+                               int32_t *h_plan)
 {
     GAD_REQUIRE(mt_state && (h_plan || n_children == 0), "gad_mt_crossover_plan_host: null pointer");
     GAD_REQUIRE(n_children >= 0 && n_parents >= 0 && n_parents < (1ll << 31), "gad_mt_crossover_plan_host: bad sizes");
@@ -123,6 +150,7 @@ extern "C" int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents,
         } else {
             cut = 1 + (int)g.randbelow((uint32_t)(n_rows - 1));
         }
+        if (with_probability && g.random53() >= probability) cut = copy_cut;
         h_plan[3 * c + 0] = (int32_t)a;
         h_plan[3 * c + 1] = (int32_t)b;
         h_plan[3 * c + 2] = cut;

@@ -213,6 +213,13 @@ int gad_pass_decide(const void *d_peer_base, int64_t flags_off, int64_t table_of
 int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
                                const int32_t *h_widths, int32_t *h_plan);
 
+/* The same plan with a crossover probability - an extension (config.CROSSOVER_PROBABILITY: the paper's supplement
+ * names c_prob, the reference checkout has no code for it): after the reference's draws for a child one
+ * random.random() (53 bits from two words); at or above `probability` the cut becomes copy_cut, a cut past the last
+ * row (horizontal) or cell (vertical), i.e. the child is a copy of parent1. */
+int gad_mt_crossover_plan_prob_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
+                                    const int32_t *h_widths, double probability, int copy_cut, int32_t *h_plan);
+
 /* GA.generate_population (GA.py:71-94) with the same replay: n_clone copies, then h_ngaps[r]
  * gaps per row inserted one at a time at randint(0, len-1). Host buffers in the library layout. */
 int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen, int seq_stride,

@@ -101,3 +101,47 @@ def test_crossover_plan_host(native_lib):
         native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, 1, 6, 4, None, plan.ctypes.data)
     with pytest.raises(ValueError):
         native_lib.call("gad_mt_crossover_plan_host", state.ctypes.data, 5, 1, 4, None, plan.ctypes.data)
+
+
+@pytest.mark.parametrize("seed,n_parents,n_rows,n_children,prob", [(0, 2, 2, 50, 0.5), (1, 75, 6, 75, 0.5), (2, 500, 20, 2000, 0.85),
+                                                                  (3, 10, 3, 400, 0.0), (4, 10, 3, 400, 1.0)])
+def test_crossover_plan_with_probability_matches_python_random(native_lib, seed, n_parents, n_rows, n_children, prob):
+    """gad_mt_crossover_plan_prob_host == the oracle's restatement on CPython's `random` (choice, choice, retry on equal
+    parents, randint, then random.random() against the probability), horizontal and vertical, generator state included."""
+    random.seed(seed)
+    want = O.crossover_plan_variant(n_parents, n_rows, n_children, prob, n_rows)
+    after = random.random()
+    random.seed(seed)
+    plan = np.empty((n_children, 3), np.int32)
+    state, meta = mt_state()
+    native_lib.call("gad_mt_crossover_plan_prob_host", state.ctypes.data, n_parents, n_rows, n_children, None, float(prob),
+                    n_rows, plan.ctypes.data)
+    mt_restore(state, meta)
+    assert [tuple(int(v) for v in row) for row in plan] == want
+    assert random.random() == after
+    if prob == 0.0:
+        assert (plan[:, 2] == n_rows).all()
+    if prob == 1.0:
+        assert ((plan[:, 2] >= 1) & (plan[:, 2] < n_rows)).all()
+    # vertical: the cut comes from the narrower parent's width
+    wrng = random.Random(50 + seed)
+    widths = np.array([wrng.randint(2, 90) for _ in range(n_parents)], np.int32)
+    random.seed(1000 + seed)
+    want_v = []
+    while len(want_v) < n_children:
+        a = random.choice(range(n_parents))
+        b = random.choice(range(n_parents))
+        if a == b:
+            continue
+        cut = random.randint(1, int(min(widths[a], widths[b])) - 1)
+        if random.random() >= prob:
+            cut = 1 << 20
+        want_v.append((a, b, cut))
+    after = random.random()
+    random.seed(1000 + seed)
+    state, meta = mt_state()
+    native_lib.call("gad_mt_crossover_plan_prob_host", state.ctypes.data, n_parents, n_rows, n_children, widths.ctypes.data,
+                    float(prob), 1 << 20, plan.ctypes.data)
+    mt_restore(state, meta)
+    assert [tuple(int(v) for v in row) for row in plan] == want_v
+    assert random.random() == after
