@@ -473,23 +473,28 @@ class GA:
         for the worst-tile search); (None, None) when nobody mutates."""
         dev = self._dev
         order = idx.cpu().numpy()
-        minlen = dev.cur.rowlen[:dev.n].min(dim=1).values.cpu().numpy() if random_tile else None
-        kept, tiles = [], []
-        for i in order:
-            if m_prob < 1.0 and random.random() >= m_prob:
-                continue
-            if random_tile:
-                n_r = (dev.R - rw) // rw + 1 if dev.R >= rw else 0
-                n_c = (int(minlen[i]) - cw) // cw + 1 if int(minlen[i]) >= cw else 0
-                if n_r * n_c <= 0:
-                    raise ValueError("min() arg is an empty sequence")
-                t = random.randrange(n_r * n_c)
-                tiles.append((t // n_c * rw, t % n_c * cw))
-            kept.append(int(i))
-        if not kept:
+        n = int(order.shape[0])
+        ntiles = n_c = None
+        if random_tile:
+            minlen = dev.cur.rowlen[:dev.n].min(dim=1).values.cpu().numpy().astype(np.int64)[order]
+            n_r = (dev.R - rw) // rw + 1 if dev.R >= rw else 0
+            n_c = np.where(minlen >= cw, (minlen - cw) // cw + 1, 0)
+            ntiles = np.ascontiguousarray(n_r * n_c, dtype=np.int32)
+        keep = np.empty(n, dtype=np.uint8)
+        tile = np.empty(n, dtype=np.int32)
+        state, meta = _mt_state()                       # the library's replay of CPython's generator draws them
+        nat.call("gad_mt_mutation_draws_host", state.ctypes.data, n, float(m_prob),
+                 None if ntiles is None else ntiles.ctypes.data, keep.ctypes.data, tile.ctypes.data)
+        _mt_restore(state, meta)
+        sel = np.nonzero(keep)[0]
+        if sel.size == 0:
             return None, None
-        d_idx = torch.tensor(kept, dtype=torch.int32, device=dev.device)
-        d_tile = torch.tensor(tiles, dtype=torch.int32, device=dev.device).reshape(-1, 2) if random_tile else None
+        d_idx = torch.from_numpy(np.ascontiguousarray(order[sel], dtype=np.int32)).to(dev.device)
+        d_tile = None
+        if random_tile:
+            t, nc = tile[sel].astype(np.int64), n_c[sel]
+            coords = np.stack((t // nc * rw, t % nc * cw), axis=1).astype(np.int32)
+            d_tile = torch.from_numpy(np.ascontiguousarray(coords)).to(dev.device)
         return d_idx, d_tile
 
     # ------------------------------------------------------------------ a22

@@ -61,6 +61,7 @@ SIGNATURES = {
     "gad_pass_decide": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_int,
                                 c_int, c_vp, c_int, c_int, c_vp, ctypes.c_size_t, c_vp]),
     "gad_mt_crossover_plan_host": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
+    "gad_mt_mutation_draws_host": (c_int, [c_vp, c_i64, ctypes.c_double, c_vp, c_vp, c_vp]),
     "gad_mt_crossover_plan_prob_host": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, ctypes.c_double, c_int, c_vp]),
     "gad_mt_population_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_int]),
     "gad_mt_population_shard_host": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,

@@ -160,6 +160,34 @@ static int crossover_plan_impl(uint32_t *mt_state, int64_t n_parents, int n_rows
     return GAD_OK;
 }
 
+// The draws of the mutation variants (extensions, config.MUTATION_PROBABILITY / MUTATION_TILE = 'random': the paper's
+// supplement names them, the reference has no code): for every selected individual in ranking order one
+// random.random() when probability < 1 - at or above it the individual is skipped - and then, when h_ntiles is not
+// NULL, one random.randrange(h_ntiles[i]) for its tile. h_keep[i] = 1 / 0, h_tile[i] = the tile ordinal (row-major
+// in the lattice of utils.py:230-252) or -1.
+extern "C" int gad_mt_mutation_draws_host(uint32_t *mt_state, int64_t n, double probability, const int32_t *h_ntiles,
+                                          uint8_t *h_keep, int32_t *h_tile)
+{
+    GAD_REQUIRE(mt_state && (n == 0 || (h_keep && h_tile)), "gad_mt_mutation_draws_host: null pointer");
+    GAD_REQUIRE(n >= 0, "gad_mt_mutation_draws_host: bad size");
+    MT g{mt_state, (int)mt_state[624]};
+    GAD_REQUIRE(g.pos >= 0 && g.pos <= 624, "gad_mt_mutation_draws_host: corrupt MT19937 position %d", g.pos);
+    for (int64_t i = 0; i < n; ++i) {
+        h_keep[i] = 1;
+        h_tile[i] = -1;
+        if (probability < 1.0 && g.random53() >= probability) {
+            h_keep[i] = 0;
+            continue;
+        }
+        if (h_ntiles) {
+            GAD_REQUIRE(h_ntiles[i] >= 1, "min() arg is an empty sequence");          // no tile fits (utils.py:291)
+            h_tile[i] = (int32_t)g.randbelow((uint32_t)h_ntiles[i]);
+        }
+    }
+    mt_state[624] = (uint32_t)g.pos;
+    return GAD_OK;
+}
+
 // GA.py:71-94: n_clone exact copies first, then every row of every other individual gets h_ngaps[r] gaps
 // inserted one at a time at randint(0, len_now - 1) (the row grows with every insert; never appended).
 // Output in the library's layout: uint8 boards[P][R][stride] (gap code beyond each row), int32 rowlen[P][R].

@@ -220,6 +220,14 @@ int gad_mt_crossover_plan_host(uint32_t *mt_state, int64_t n_parents, int n_rows
 int gad_mt_crossover_plan_prob_host(uint32_t *mt_state, int64_t n_parents, int n_rows, int64_t n_children,
                                     const int32_t *h_widths, double probability, int copy_cut, int32_t *h_plan);
 
+/* The draws of the mutation variants - extensions (config.MUTATION_PROBABILITY, config.MUTATION_TILE = 'random'; the
+ * paper's supplement names them, the reference checkout has no code): for each of the n selected individuals in
+ * ranking order one random.random() when probability < 1 (at or above it h_keep[i] = 0, nothing else is drawn for
+ * it), then - h_ntiles not NULL - h_tile[i] = random.randrange(h_ntiles[i]), the ordinal of its tile in the row-major
+ * lattice of utils.get_all_different_sub_range (utils.py:230-252); h_tile[i] = -1 otherwise. */
+int gad_mt_mutation_draws_host(uint32_t *mt_state, int64_t n, double probability, const int32_t *h_ntiles,
+                               uint8_t *h_keep, int32_t *h_tile);
+
 /* GA.generate_population (GA.py:71-94) with the same replay: n_clone copies, then h_ngaps[r]
  * gaps per row inserted one at a time at randint(0, len-1). Host buffers in the library layout. */
 int gad_mt_population_host(uint32_t *mt_state, const uint8_t *h_seqs, const int32_t *h_seqlen, int seq_stride,

@@ -145,3 +145,39 @@ def test_crossover_plan_with_probability_matches_python_random(native_lib, seed,
     mt_restore(state, meta)
     assert [tuple(int(v) for v in row) for row in plan] == want_v
     assert random.random() == after
+
+
+@pytest.mark.parametrize("seed,n,prob,tiles", [(0, 40, 0.85, True), (1, 1000, 0.5, False), (2, 300, 1.0, True), (3, 64, 0.0, True),
+                                               (4, 5000, 0.85, True)])
+def test_mutation_variant_draws_match_python_random(native_lib, seed, n, prob, tiles):
+    """gad_mt_mutation_draws_host == python: per selected individual random.random() (only below probability 1), a skip
+    at or above the probability, then random.randrange(number of tiles); generator state included."""
+    trng = random.Random(70 + seed)
+    ntiles = np.array([trng.randint(1, 40) for _ in range(n)], np.int32)
+    random.seed(seed)
+    want_keep, want_tile = [], []
+    for i in range(n):
+        if prob < 1.0 and random.random() >= prob:
+            want_keep.append(0)
+            want_tile.append(-1)
+            continue
+        want_keep.append(1)
+        want_tile.append(random.randrange(int(ntiles[i])) if tiles else -1)
+    after = random.random()
+    random.seed(seed)
+    keep = np.empty(n, np.uint8)
+    tile = np.empty(n, np.int32)
+    state, meta = mt_state()
+    native_lib.call("gad_mt_mutation_draws_host", state.ctypes.data, n, float(prob), ntiles.ctypes.data if tiles else None,
+                    keep.ctypes.data, tile.ctypes.data)
+    mt_restore(state, meta)
+    assert keep.tolist() == want_keep and tile.tolist() == want_tile
+    assert random.random() == after
+    if tiles:
+        bad = ntiles.copy()
+        bad[n // 2] = 0
+        state, meta = mt_state()
+        if prob > 0.0:
+            with pytest.raises(ValueError):
+                native_lib.call("gad_mt_mutation_draws_host", state.ctypes.data, n, 1.0, bad.ctypes.data, keep.ctypes.data,
+                                tile.ctypes.data)

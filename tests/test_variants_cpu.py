@@ -72,3 +72,75 @@ def test_defaults_are_the_reference_loop():
                        CROSSOVER_PROBABILITY=1.0, SELECTION_SCHEME="truncation", ELITISM_PROBABILITY=0.0)
     out_b = O.ga_run(seqs, "mo", sd, explicit, rng=b)
     assert out_a == out_b and a.getstate() == b.getstate()
+
+
+def test_facade_mutation_variant_host_logic_matches_the_python_loop(native_lib):
+    """GA._mutation_variant (draws by the library's MT19937 replay, tile coordinates vectorised) against the plain
+    python loop over `random` it replaces, on a stand-in population object (no GPU involved: host logic only)."""
+    import types
+
+    import numpy as np
+    import torch
+
+    import GA as ga_mod
+
+    rng = random.Random(21)
+    n_pop, R, rw, cw = 500, 7, 3, 30
+    minlen = [rng.randint(30, 200) for _ in range(n_pop)]
+    rowlen = torch.tensor([[m + rng.randint(0, 3) if r else m for r in range(R)] for m in minlen], dtype=torch.int32)
+    order = list(range(n_pop))
+    rng.shuffle(order)
+    order = order[:200]
+    dev = types.SimpleNamespace(cur=types.SimpleNamespace(rowlen=rowlen), n=n_pop, R=R, device="cpu")
+    me = types.SimpleNamespace(_dev=dev)
+    for m_prob, random_tile in ((0.85, True), (1.0, True), (0.5, False)):
+        random.seed(33)
+        kept, tiles = [], []
+        for i in order:                                   # the loop the oracle's `mutation` runs
+            if m_prob < 1.0 and random.random() >= m_prob:
+                continue
+            if random_tile:
+                grid = O.tile_grid(R, minlen[i], rw, cw)
+                fr, _, fc, _ = grid[random.randrange(len(grid))]
+                tiles.append([fr, fc])
+            kept.append(i)
+        after = random.random()
+        random.seed(33)
+        d_idx, d_tile = ga_mod.GA._mutation_variant(me, torch.tensor(order, dtype=torch.int32), rw, cw, m_prob, random_tile)
+        assert d_idx.dtype == torch.int32 and d_idx.tolist() == kept
+        assert (d_tile is None) == (not random_tile)
+        if random_tile:
+            assert d_tile.dtype == torch.int32 and d_tile.tolist() == tiles
+        assert random.random() == after
+    random.seed(1)
+    assert ga_mod.GA._mutation_variant(me, torch.tensor(order, dtype=torch.int32), rw, cw, 0.0, True) == (None, None)
+
+
+def test_facade_tournament_selection_host_logic_matches_the_oracle(native_lib, monkeypatch):
+    """GA._tournament_selection on a stand-in population whose ranking comes from the oracle: the survivor set and
+    the generator state equal oracle.tournament_keep's."""
+    import types
+
+    import torch
+
+    import config
+    import GA as ga_mod
+
+    rng = random.Random(5)
+    for mode in ("sp", "mo"):
+        n = 150
+        sc = _scores(n, rng, mode)
+        got = {}
+        dev = types.SimpleNamespace(n=n, device="cpu",
+                                    rank_order=lambda m, k, sc=sc: torch.tensor(O.rank_best(sc, k), dtype=torch.int32),
+                                    compact_with=lambda keep: got.update(keep=keep.clone()))
+        me = types.SimpleNamespace(_dev=dev, mode=mode)
+        monkeypatch.setattr(config, "TOURNAMENT_RATE", 0.25)
+        top_n = int(n * 0.45)
+        random.seed(8)
+        ga_mod.GA._tournament_selection(me, top_n)
+        after = random.random()
+        random.seed(8)
+        want = O.tournament_keep(sc, mode, n, 0.45, 0.25)
+        assert set(torch.nonzero(got["keep"]).flatten().tolist()) == want
+        assert random.random() == after
