@@ -10,6 +10,10 @@ bf16 product for scale. Per variant: max |dQ| / max_value against the float64 fo
 share of states whose top-2 margin is below twice that error (what a margin-gated scheme would have to re-run).
 
     python scripts/l1_precision_flips.py > profiles/r02_l1_precision_flips.json        (CPU only, about a minute)
+    python scripts/l1_precision_flips.py --episodes 3000 > profiles/r02_l1_precision_flips_100k.json
+        also simulates that many greedy episodes per window in lock step (float64 actions, windows cut from a
+        population generated like GA.generate_population at the c3 shape) and measures the same on every state they
+        visit - 100 000+ states per window, a quarter of an hour on 8 cores
 """
 import json
 import os
@@ -61,7 +65,93 @@ def post_l1(W, h, max_value):
     return np.tanh(h) * max_value
 
 
+def measure(sd, states, max_value, chunk=2048):
+    """per variant: max |dQ|, flips, and the margins of all states (for the gate statistics), streamed in chunks"""
+    W1 = np.asarray(sd["l1.weight"], np.float64)
+    s = int(np.floor(np.log2(32768.0 / np.abs(W1).max())))          # the kernel's weight pre-scale 2^s
+    wh, wl = split16(W1 * 2.0 ** s)
+    w32, wbf = W1.astype(np.float32), to_bf16(W1)
+    inv = 2.0 ** -s
+    names = ["fp32 (plain float32 product)", "bf16 x bf16, 1 term", "fp16 split, 1 term (hi.hi)",
+             "fp16 split, 2 terms (hi.hi + lo.hi)", "fp16 split, 2 terms (hi.hi + hi.lo)",
+             "fp16 split, 3 terms (hi.hi + lo.hi + hi.lo) - what the kernel issues"]
+    err = {n: 0.0 for n in names}
+    flips = {n: 0 for n in names}
+    margins, actions = [], []
+    for c0 in range(0, states.shape[0], chunk):
+        Z, W = pre_l1(sd, states[c0:c0 + chunk])
+        b1 = W["l1.bias"]
+        q_ref = post_l1(W, Z @ W["l1.weight"].T + b1, max_value)
+        a_ref = q_ref.argmax(1)
+        srt = np.sort(q_ref, 1)
+        margins.append(srt[:, -1] - srt[:, -2])
+        actions.append(a_ref)
+        zh, zl = split16(Z)
+        hh, lh, hl = zh @ wh.T, zl @ wh.T, zh @ wl.T
+        hs = [Z.astype(np.float32) @ w32.T, to_bf16(Z) @ wbf.T, hh * inv, (hh + lh) * inv, (hh + hl) * inv, (hh + lh + hl) * inv]
+        for n, h in zip(names, hs):
+            qv = post_l1(W, h.astype(np.float64) + b1, max_value)
+            err[n] = max(err[n], float(np.abs(qv - q_ref).max()))
+            flips[n] += int((qv.argmax(1) != a_ref).sum())
+    margin = np.concatenate(margins)
+    res = {n: {"max_abs_dq_over_max_value": err[n] / max_value, "max_abs_dq": err[n], "flipped_actions": flips[n],
+               "states_with_margin_below_2x_error": int((margin < 2 * err[n]).sum())} for n in names}
+    return res, margin, np.concatenate(actions), s
+
+
+def simulate(sd, rows, cols, episodes, max_value, seed):
+    """`episodes` greedy episodes in lock step (float64 forward = the reference's actions): every state visited"""
+    import random
+    rng = random.Random(seed)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(60)) for _ in range(6)]
+    pop = O.generate_population(seqs, episodes, 0.0, 0.05, rng)              # every board different
+    envs = []
+    for board in pop:
+        grid = O.tile_grid(len(board), min(len(r) for r in board), rows, cols)
+        fr, tr, fc, tc = grid[rng.randrange(len(grid))]
+        envs.append(O.Env([row[fc:tc] for row in board[fr:tr]]))
+    live = list(range(episodes))
+    visited = []
+    while live:
+        st = np.array([envs[i].state() for i in live], np.int64)
+        visited.append(st)
+        acts = []
+        for c0 in range(0, st.shape[0], 2048):
+            acts.append(O.qnet_forward(sd, st[c0:c0 + 2048], max_value).argmax(1))
+        acts = np.concatenate(acts)
+        nxt = []
+        for i, a in zip(live, acts):
+            _, _, cont = envs[i].step(int(a))                                 # greedy: argmax (dqn.py:153-154)
+            if cont:
+                nxt.append(i)
+        live = nxt
+    return np.concatenate(visited)
+
+
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--episodes", type=int, default=0)
+    args = ap.parse_args()
+    if args.episodes > 0:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "qnet_states_big.npz"))
+        seed = int(z["weight_seed"])
+        out = {"source": "%d greedy episodes per window simulated in lock step with the float64 forward (windows cut from a "
+                         "population generated like GA.generate_population: 6x60 sequences, 5 %% gaps), substitute weights "
+                         "seed %d" % (args.episodes, seed),
+               "emulation": "l1 only; float64 before and after; fp16 split operands, float32 accumulation by BLAS", "windows": {}}
+        for rows, cols in ((3, 30), (6, 30)):
+            sd = O.synth_qnet_weights(rows, cols, seed)
+            max_value = cols * rows * (rows - 1) / 2 * 4.0
+            states = simulate(sd, rows, cols, args.episodes, max_value, 99 + rows)
+            res, margin, _, s2 = measure(sd, states, max_value)
+            out["windows"]["%dx%d" % (rows, cols)] = {
+                "states": int(states.shape[0]), "episodes": args.episodes, "max_value": max_value, "weight_prescale_log2": s2,
+                "smallest_top2_margin": float(margin.min()),
+                "margin_percentiles_1_10_50": [float(np.percentile(margin, p)) for p in (1, 10, 50)], "variants": res}
+            sys.stderr.write("%dx%d: %d states done\n" % (rows, cols, states.shape[0]))
+        print(json.dumps(out, indent=1))
+        return
     z = np.load(os.path.join(ROOT, "tests", "golden", "qnet_states_big.npz"))
     seed = int(z["weight_seed"])
     out = {"source": "tests/golden/qnet_states_big.npz (reference greedy trajectories), substitute weights seed %d" % seed,

@@ -144,3 +144,51 @@ def test_facade_tournament_selection_host_logic_matches_the_oracle(native_lib, m
         want = O.tournament_keep(sc, mode, n, 0.45, 0.25)
         assert set(torch.nonzero(got["keep"]).flatten().tolist()) == want
         assert random.random() == after
+
+
+def test_facade_elitism_host_logic(native_lib, monkeypatch):
+    """GA._elitism on a stand-in population: one random.random() per generation (none at probability 0); below the
+    probability the hall-of-fame board and width overwrite the worst-ranked individual and the population is scored
+    again."""
+    import types
+
+    import torch
+
+    import config
+    import GA as ga_mod
+
+    n, R, stride = 6, 3, 16
+    boards = torch.arange(n * R * stride, dtype=torch.int64).reshape(n, R, stride).to(torch.uint8)
+    rowlen = torch.full((n, R), 12, dtype=torch.int32)
+    hof_board = torch.full((R, stride), 7, dtype=torch.uint8)
+    order = torch.tensor([2, 0, 5, 1, 3, 4], dtype=torch.int32)             # worst-ranked individual: 4
+    calls = []
+    dev = types.SimpleNamespace(n=n, cur=types.SimpleNamespace(boards=boards.clone(), rowlen=rowlen.clone()),
+                                hof=torch.tensor([1, 2, 40, 9, 10, 0, 0, 0], dtype=torch.int32), hof_board=hof_board,
+                                rank_order=lambda mode, k: order[:k])
+    me = types.SimpleNamespace(_dev=dev, mode="sp", calculate_fitness_score=lambda: calls.append(1))
+    monkeypatch.setattr(config, "ELITISM_PROBABILITY", 0.0)
+    before = random.getstate()
+    ga_mod.GA._elitism(me)
+    assert random.getstate() == before and not calls and torch.equal(dev.cur.boards, boards)
+    monkeypatch.setattr(config, "ELITISM_PROBABILITY", 0.4)
+    hits = 0
+    for seed in range(12):
+        dev.cur.boards.copy_(boards)
+        dev.cur.rowlen.copy_(rowlen)
+        calls.clear()
+        random.seed(seed)
+        expect = random.random() < 0.4
+        after = random.random()
+        random.seed(seed)
+        ga_mod.GA._elitism(me)
+        assert random.random() == after
+        assert bool(calls) == expect
+        if expect:
+            hits += 1
+            assert torch.equal(dev.cur.boards[4], hof_board) and dev.cur.rowlen[4].tolist() == [10] * R
+            keep = [i for i in range(n) if i != 4]
+            assert torch.equal(dev.cur.boards[keep], boards[keep])
+        else:
+            assert torch.equal(dev.cur.boards, boards)
+    assert 0 < hits < 12
