@@ -4,6 +4,8 @@ own draws (the recorded reference traces are replayed with them in test_oracle_p
 import copy
 import random
 
+import pytest
+
 import ga_oracle as O
 
 
@@ -192,3 +194,22 @@ def test_facade_elitism_host_logic(native_lib, monkeypatch):
         else:
             assert torch.equal(dev.cur.boards, boards)
     assert 0 < hits < 12
+
+
+def test_facade_crossover_plan_with_probability_matches_the_oracle(native_lib):
+    """GA._plan_with_probability (the library's replay of CPython's generator) == oracle.crossover_plan_variant on
+    `random`, generator state included."""
+    import numpy as np
+
+    import GA as ga_mod
+
+    for seed, (n_parents, n_rows, n_children, prob) in enumerate([(30, 6, 30, 0.5), (75, 6, 75, 0.85), (4, 2, 200, 0.1)]):
+        random.seed(seed)
+        want = O.crossover_plan_variant(n_parents, n_rows, n_children, prob, n_rows)
+        after = random.random()
+        random.seed(seed)
+        plan = ga_mod.GA._plan_with_probability(n_parents, n_rows, n_children, prob, None, 0)
+        assert plan.dtype == np.int32 and [tuple(int(v) for v in r) for r in plan] == want
+        assert random.random() == after
+    with pytest.raises(ValueError):
+        ga_mod.GA._plan_with_probability(1, 6, 4, 0.5, None, 0)
